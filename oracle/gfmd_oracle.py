@@ -1,0 +1,375 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY.
+
+numpy restatement of the per-step elastic-force path of ``fix gfmd`` plus thin
+ctypes bindings to the two oracle libraries built by ``oracle/Makefile``:
+
+* ``oracle/_ref/libgfmd_oracle.so`` -- the plain-C restatement (gfmd_oracle.c)
+* ``oracle/_ref/libgfmd_ref.so``    -- the reference's OWN sources compiled
+  unchanged against ``oracle/shim`` (see ref_driver.cpp)
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  Nothing under
+``user-gfmd_b200/`` does.
+
+Reference lines restated here:
+  post_force      src/solvers/gfmd_solver_static.cpp:145-249
+  fft_forward     src/solvers/gfmd_solver_fft.cpp:96-147  (unnormalised, exp(-i q r))
+  fft_reverse     src/solvers/gfmd_solver_fft.cpp:150-195 (unnormalised, exp(+i q r), real part)
+  q ordering      src/main/gfmd_misc.cpp:43-48
+  grid partition  src/main/gfmd_solver.cpp:95-135
+  gather          src/main/fix_gfmd.cpp:734-803
+  scatter         src/main/fix_gfmd.cpp:952-1010, :896-902
+
+PINNING: checked against libgfmd_ref.so and tests/golden in tests/test_oracle.py.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_DIR = os.path.join(_HERE, "_ref")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+# --------------------------------------------------------------------------
+# numpy restatement
+# --------------------------------------------------------------------------
+
+def q_vectors(nx, ny):
+    """qx[i], qy[j] exactly as fill_phi_buffer builds them (gfmd_misc.cpp:43-48)."""
+    i = np.arange(nx)
+    j = np.arange(ny)
+    qx = np.where(i <= nx // 2, 2.0 * np.pi * i / nx, 2.0 * np.pi * (i - nx) / nx)
+    qy = np.where(j <= ny // 2, 2.0 * np.pi * j / ny, 2.0 * np.pi * (j - ny) / ny)
+    return qx, qy
+
+
+def grid_partition(nx, ny, sublo, subhi, boxlo, prd):
+    """Local brick of GFMDSolver::set_grid_size (gfmd_solver.cpp:95-135).
+
+    Returns (xlo_loc, xhi_loc, ylo_loc, yhi_loc, nxy_loc, gammai)."""
+    def rnd(v):  # C round(): half away from zero
+        return int(np.floor(abs(v) + 0.5) * np.sign(v)) if v != 0 else 0
+    xlo = rnd(nx * (sublo[0] - boxlo[0]) / prd[0])
+    xhi = rnd(nx * (subhi[0] - boxlo[0]) / prd[0]) - 1
+    ylo = rnd(ny * (sublo[1] - boxlo[1]) / prd[1])
+    yhi = rnd(ny * (subhi[1] - boxlo[1]) / prd[1]) - 1
+    nx_loc, ny_loc = xhi - xlo + 1, yhi - ylo + 1
+    gammai = -1
+    if xlo <= 0 <= xhi and ylo <= 0 <= yhi:
+        gammai = -xlo * ny_loc - ylo
+    return xlo, xhi, ylo, yhi, nx_loc * ny_loc, gammai
+
+
+def post_force(u, phi, linf, fft=None):
+    """GFMDSolverStatic::post_force on the full grid (single rank).
+
+    u    : [ndof, nx, ny] float64 (the reference's u_xy[idof][ix*ny+iy])
+    phi  : [nx*ny, ndof, ndof] complex128, already divided by nx*ny
+    linf : [ndof//3]
+    Returns f [ndof, nx, ny], epot, u0 [ndof].
+    """
+    if fft is None:
+        fft = np.fft
+    ndof, nx, ny = u.shape
+    nu = ndof // 3
+    linf = np.asarray(linf, dtype=np.float64)
+    uq = fft.fft2(u, axes=(1, 2))                       # exp(-i q r), unnormalised
+    q = np.ascontiguousarray(np.moveaxis(uq.reshape(ndof, nx * ny), 0, 1))  # [idq][idim]
+    u0 = q[0].real.copy()
+    epot = 0.0
+    for i in range(nu):
+        epot -= 2 * linf[i] * q[0, 3 * i + 2].real
+    F = np.einsum("qij,qj->qi", phi.reshape(nx * ny, ndof, ndof), q)
+    epot += float(np.sum((np.conj(F) * q).real))
+    q = -F
+    for i in range(nu):
+        q[0, 3 * i + 2] += linf[i]
+    epot *= 0.5
+    fq = np.moveaxis(q, 0, 1).reshape(ndof, nx, ny)
+    f = fft.ifft2(fq, axes=(1, 2)).real * (nx * ny)     # unnormalised backward
+    return np.ascontiguousarray(f), epot, u0
+
+
+def gather(x, xeq, gid, mask, groupbit, nx, ny, ndof, xprd, yprd,
+           dxshift=0, dyshift=0, xlo_loc=0, ylo_loc=0, nx_loc=None, ny_loc=None,
+           u_xy=None):
+    """FixGFMD::pre_force list->grid (fix_gfmd.cpp:734-803).  gid is updated in
+    place when shifted, as the reference does.  Vectorised; duplicates resolve
+    to the LAST atom in list order like the reference's sequential loop."""
+    nx_loc = nx if nx_loc is None else nx_loc
+    ny_loc = ny if ny_loc is None else ny_loc
+    if u_xy is None:
+        u_xy = np.zeros((ndof, nx_loc * ny_loc))
+    sel = (mask & groupbit) != 0
+    ix = gid[:, 0] - dxshift
+    iy = gid[:, 1] - dyshift
+    if dxshift != 0 or dyshift != 0:
+        ix = np.mod(ix, nx)
+        iy = np.mod(iy, ny)
+        gid[sel, 0] = ix[sel]
+        gid[sel, 1] = iy[sel]
+    ix = ix - xlo_loc
+    iy = iy - ylo_loc
+    inside = sel & (ix >= 0) & (ix < nx_loc) & (iy >= 0) & (iy < ny_loc)
+    d = x - xeq
+    ux, uy, uz = d[:, 0].copy(), d[:, 1].copy(), d[:, 2]
+    # while (ux > xprd_half) ux -= xprd; while (ux < -xprd_half) ux += xprd
+    for arr, prd in ((ux, xprd), (uy, yprd)):
+        half = 0.5 * prd
+        while True:
+            m = arr > half
+            if not m.any():
+                break
+            arr[m] -= prd
+        while True:
+            m = arr < -half
+            if not m.any():
+                break
+            arr[m] += prd
+    idx = np.nonzero(inside)[0]
+    iloc = ix[idx] * ny_loc + iy[idx]
+    idof = 3 * gid[idx, 2]
+    u_xy[idof, iloc] = ux[idx]
+    u_xy[idof + 1, iloc] = uy[idx]
+    u_xy[idof + 2, iloc] = uz[idx]
+    return u_xy, int(inside.sum())
+
+
+def scatter(f_xy, gid, mask, groupbit, f, nlocal=None, xlo_loc=0, xhi_loc=None,
+            ylo_loc=0, yhi_loc=None, nx=None, ny=None):
+    """grid_to_list + f += f_i (fix_gfmd.cpp:952-1010, :896-902)."""
+    xhi_loc = nx - 1 if xhi_loc is None else xhi_loc
+    yhi_loc = ny - 1 if yhi_loc is None else yhi_loc
+    ny_loc = yhi_loc - ylo_loc + 1
+    nall = gid.shape[0]
+    nlocal = nall if nlocal is None else nlocal
+    sel = (mask & groupbit) != 0
+    ix, iy = gid[:, 0], gid[:, 1]
+    known = sel & (ix >= xlo_loc) & (ix <= xhi_loc) & (iy >= ylo_loc) & (iy <= yhi_loc)
+    idx = np.nonzero(known)[0]
+    iloc = (ix[idx] - xlo_loc) * ny_loc + (iy[idx] - ylo_loc)
+    idof = 3 * gid[idx, 2]
+    fi = np.stack([f_xy[idof, iloc], f_xy[idof + 1, iloc], f_xy[idof + 2, iloc]], axis=1)
+    f[idx] += fi
+    loc = idx < nlocal
+    fsum = fi[loc].sum(axis=0)
+    return f, fsum, int(known.sum())
+
+
+# --------------------------------------------------------------------------
+# Slab-decomposed restatement (used by the gloo tests of the multi-GPU plan):
+# the same arithmetic split at the points where the B200 path exchanges data.
+# --------------------------------------------------------------------------
+
+def rows_forward(u_slab):
+    """Row (y) real-to-complex transforms of one x-slab: [d, nx_loc, ny] ->
+    half spectrum transposed [d, nyh, nx_loc]."""
+    return np.ascontiguousarray(np.swapaxes(np.fft.rfft(u_slab, axis=2), 1, 2))
+
+
+def columns_contract(ut_cols, phi_cols, linf, ky0, weights):
+    """Column (x) transforms + contraction on a ky-slab.
+
+    ut_cols  : [d, nky, nx] complex (x complete)
+    phi_cols : [nky, nx, d, d] complex, normalised, phi(kx, ky0+k)
+    weights  : [nky] multiplicity of each ky in the full spectrum (1 or 2)
+    Returns (ft_cols [d, nky, nx], epot contribution (before the 0.5), u0 or None)."""
+    d = ut_cols.shape[0]
+    uq = np.fft.fft(ut_cols, axis=2)
+    F = np.einsum("kxij,jkx->ikx", phi_cols, uq)
+    e = float(np.sum(weights[None, :, None] * (np.conj(F) * uq).real))
+    u0 = None
+    Fq = -F
+    if ky0 == 0:
+        u0 = uq[:, 0, 0].real.copy()
+        for i in range(d // 3):
+            e -= 2 * linf[i] * uq[3 * i + 2, 0, 0].real
+            Fq[3 * i + 2, 0, 0] += linf[i]
+    ft = np.fft.ifft(Fq, axis=2) * uq.shape[2]
+    return ft, e, u0
+
+
+def rows_inverse(ft_slab, ny):
+    """[d, nyh, nx_loc] half spectrum -> real forces [d, nx_loc, ny] (unnormalised)."""
+    return np.fft.irfft(np.swapaxes(ft_slab, 1, 2), n=ny, axis=2) * ny
+
+
+# --------------------------------------------------------------------------
+# ctypes: plain-C restatement
+# --------------------------------------------------------------------------
+
+_clib = None
+
+
+def clib():
+    global _clib
+    if _clib is None:
+        path = os.path.join(_REF_DIR, "libgfmd_oracle.so")
+        lib = ctypes.CDLL(path)
+        lib.gfmd_oracle_post_force.restype = ctypes.c_double
+        lib.gfmd_oracle_post_force.argtypes = [
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
+            c_double_p, c_double_p, c_double_p, ctypes.c_int]
+        lib.gfmd_oracle_gather.restype = ctypes.c_int
+        lib.gfmd_oracle_gather.argtypes = [
+            ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_int_p, c_int_p,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+            ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+            ctypes.c_int, ctypes.c_int, c_double_p]
+        lib.gfmd_oracle_scatter.restype = ctypes.c_int
+        lib.gfmd_oracle_scatter.argtypes = [
+            ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, ctypes.c_int,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+            c_double_p, c_double_p]
+        _clib = lib
+    return _clib
+
+
+def c_post_force(u, phi, linf, fft_backend=1):
+    ndof, nx, ny = u.shape
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    phi = np.ascontiguousarray(phi, dtype=np.complex128)
+    linf = np.ascontiguousarray(linf, dtype=np.float64)
+    f = np.empty_like(u)
+    u0 = np.empty(ndof)
+    e = clib().gfmd_oracle_post_force(nx, ny, ndof, _dp(phi.view(np.float64)), _dp(linf),
+                                      _dp(u), _dp(f), _dp(u0), fft_backend)
+    return f, e, u0
+
+
+def c_gather(x, xeq, gid, mask, groupbit, nx, ny, ndof, xprd, yprd, dxshift=0, dyshift=0,
+             u_xy=None):
+    nall = x.shape[0]
+    if u_xy is None:
+        u_xy = np.zeros((ndof, nx * ny))
+    gid = np.ascontiguousarray(gid, dtype=np.int32)
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    n = clib().gfmd_oracle_gather(nall, nall, _dp(np.ascontiguousarray(x)),
+                                  _dp(np.ascontiguousarray(xeq)), _ip(gid), _ip(mask),
+                                  groupbit, nx, ny, 0, 0, nx, ny, xprd, yprd, dxshift,
+                                  dyshift, _dp(u_xy))
+    return u_xy, n, gid
+
+
+def c_scatter(f_xy, gid, mask, groupbit, f, nx, ny):
+    nall = gid.shape[0]
+    gid = np.ascontiguousarray(gid, dtype=np.int32)
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    fsum = np.zeros(3)
+    n = clib().gfmd_oracle_scatter(nall, nall, _ip(gid), _ip(mask), groupbit, 0, nx - 1, 0,
+                                   ny - 1, _dp(np.ascontiguousarray(f_xy)), _dp(f), _dp(fsum))
+    return f, fsum, n
+
+
+# --------------------------------------------------------------------------
+# ctypes: the reference's own sources (oracle/_ref/libgfmd_ref.so)
+# --------------------------------------------------------------------------
+
+_rlib = None
+
+
+def ref_available():
+    return os.path.exists(os.path.join(_REF_DIR, "libgfmd_ref.so"))
+
+
+def rlib():
+    global _rlib
+    if _rlib is None:
+        lib = ctypes.CDLL(os.path.join(_REF_DIR, "libgfmd_ref.so"))
+        lib.ref_kernel_create.restype = ctypes.c_void_p
+        lib.ref_kernel_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        lib.ref_kernel_ndof.argtypes = [ctypes.c_void_p]
+        lib.ref_kernel_nu.argtypes = [ctypes.c_void_p]
+        lib.ref_fill_phi.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p,
+                                     ctypes.c_int]
+        lib.ref_phi_at.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                   ctypes.c_double, c_double_p]
+        lib.ref_get_linf.argtypes = [ctypes.c_void_p, c_double_p]
+        lib.ref_kernel_destroy.argtypes = [ctypes.c_void_p]
+        lib.ref_solver_create.restype = ctypes.c_void_p
+        lib.ref_solver_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.ref_solver_set_kernel.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.ref_solver_set_phi.argtypes = [ctypes.c_void_p, c_double_p, c_double_p]
+        lib.ref_solver_post_force.restype = ctypes.c_double
+        lib.ref_solver_post_force.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
+        lib.ref_solver_destroy.argtypes = [ctypes.c_void_p]
+        lib.ref_set_fft_backend.argtypes = [ctypes.c_int]
+        _rlib = lib
+    return _rlib
+
+
+class RefKernel:
+    """A stiffness-kernel plugin of the reference, e.g.
+    RefKernel("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height 128")."""
+
+    def __init__(self, kernel_string, invariant=False):
+        self.h = rlib().ref_kernel_create(kernel_string.encode(), int(invariant))
+        if not self.h:
+            raise ValueError("unknown stiffness kernel: " + kernel_string)
+        self.ndof = rlib().ref_kernel_ndof(self.h)
+        self.nu = self.ndof // 3
+
+    def phi(self, nx, ny, normalize=True):
+        """fill_phi_buffer (gfmd_misc.cpp:32-101): [nx*ny, ndof, ndof] complex128."""
+        out = np.empty((nx * ny, self.ndof, self.ndof), dtype=np.complex128)
+        rlib().ref_fill_phi(self.h, nx, ny, _dp(out.view(np.float64)), int(normalize))
+        return out
+
+    def phi_at(self, nx, ny, qx, qy):
+        out = np.empty((self.ndof, self.ndof), dtype=np.complex128)
+        rlib().ref_phi_at(self.h, nx, ny, qx, qy, _dp(out.view(np.float64)))
+        return out
+
+    def linf(self):
+        out = np.zeros(max(self.nu, 1))
+        rlib().ref_get_linf(self.h, _dp(out))
+        return out
+
+    def close(self):
+        if self.h:
+            rlib().ref_kernel_destroy(self.h)
+            self.h = None
+
+
+class RefSolver:
+    """The reference's GFMDSolverStatic (from gfmd_solver_factory("static")),
+    single rank, FFT3d replaced by the shim.  fft_backend 0 = long-double DFT."""
+
+    def __init__(self, nx, ny, ndof, fft_backend=0):
+        self.nx, self.ny, self.ndof = nx, ny, ndof
+        rlib().ref_set_fft_backend(fft_backend)
+        self.backend = fft_backend
+        self.h = rlib().ref_solver_create(nx, ny, ndof)
+
+    def set_kernel(self, kernel, normalize=True):
+        rlib().ref_solver_set_kernel(self.h, kernel.h, int(normalize))
+
+    def set_phi(self, phi, linf):
+        phi = np.ascontiguousarray(phi, dtype=np.complex128)
+        linf = np.ascontiguousarray(linf, dtype=np.float64)
+        rlib().ref_solver_set_phi(self.h, _dp(phi.view(np.float64)), _dp(linf))
+
+    def post_force(self, u):
+        rlib().ref_set_fft_backend(self.backend)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        f = np.empty_like(u)
+        u0 = np.empty(self.ndof)
+        e = rlib().ref_solver_post_force(self.h, _dp(u), _dp(f), _dp(u0))
+        return f.reshape(self.ndof, self.nx, self.ny), e, u0
+
+    def close(self):
+        if self.h:
+            rlib().ref_solver_destroy(self.h)
+            self.h = None
