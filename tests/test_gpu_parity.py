@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the golden
+vectors the reference's own sources produced (tests/golden) and against the
+oracle on fresh seeded inputs.  Tolerance: BASELINE.json north_star, <= 1e-11
+relative (forces: max-norm relative to max|f|; energy relative)."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, golden_names, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def B():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import gfmd_b200
+    gfmd_b200.load_library()          # raises if the CUDA library is missing: no fallback
+    return gfmd_b200
+
+
+def run_host(B, nx, ny, d, phi, linf, u):
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(phi, linf)
+    u = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(u, np.nan)
+    e = s.post_force(u, f)
+    u0 = s.get_u0().copy()
+    assert s.launch_count() >= 4
+    s.close()
+    return f.reshape(d, nx, ny), e, u0
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors(B, name):
+    g = load_golden(name)
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    herm, conj = s.phi_deviation()
+    assert herm < 1e-12 and conj < 1e-12
+    for c in golden_cases(g):
+        u = np.ascontiguousarray(g["u_" + c].reshape(d, nx * ny))
+        f = np.full_like(u, np.nan)
+        e = s.post_force(u, f)
+        assert rel_err(f.reshape(d, nx, ny), g["f_" + c]) < TOL, (name, c)
+        eref = float(g["epot_" + c])
+        assert abs(e - eref) <= TOL * max(abs(eref), 1e-300), (name, c, e, eref)
+        u0ref = g["u0_" + c]
+        assert np.abs(s.get_u0() - u0ref).max() <= TOL * max(1.0, np.abs(u0ref).max())
+    s.close()
+
+
+SIZES = [
+    # nx, ny, ndof : every radix, odd/even/prime rows and columns, Bluestein both ways
+    (1, 1, 3), (1, 2, 3), (2, 1, 3), (3, 5, 3), (7, 9, 6), (16, 16, 3), (10, 10, 6),
+    (37, 64, 3), (64, 37, 6), (74, 22, 3), (30, 42, 9), (35, 25, 12), (128, 96, 3),
+    (11, 13, 15), (256, 512, 3), (243, 250, 3), (1024, 64, 3), (64, 2048, 6),
+]
+
+
+@pytest.mark.parametrize("nx,ny,d", SIZES)
+def test_random_tables_against_oracle(B, nx, ny, d, oracle_libs):
+    """Synthetic Hermitian, conj-symmetric Phi and nonzero linf on many grid shapes."""
+    O = oracle_libs
+    rng = np.random.default_rng(1000 * nx + ny + d)
+    # real-space force-constant matrices D(R) real => Phi(q) = FFT(D) obeys Phi(-q) = conj Phi(q);
+    # symmetrise so that Phi(q) is Hermitian: D(-R) = D(R)^T
+    Dr = rng.standard_normal((nx, ny, d, d)) * np.exp(-0.3 * rng.random((nx, ny, 1, 1)) * 10)
+    Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+    Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+    phi = np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+    linf = rng.standard_normal(d // 3)
+    u = rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    f, e, u0 = run_host(B, nx, ny, d, phi, linf, u)
+    assert rel_err(f, f_ref) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(u0 - u0_ref).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+
+
+def test_linearity_and_energy_identity_4096(B):
+    """Size-independent properties at the benchmark size (4096 x 4096, ndof 3):
+    f is linear in u, E = -1/2 sum f.u for linf = 0, a pure translation (q = 0)
+    yields f = -Phi(0) u0 on every cell, and zero displacement gives zero force."""
+    import torch
+    nx = ny = 4096
+    d = 3
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    # closed-form isotropic-like table, built column block by column block
+    qx = 2 * np.pi * np.fft.fftfreq(nx)
+    for k0 in range(0, s.nky, 256):
+        nk = min(256, s.nky - k0)
+        qy = 2 * np.pi * np.arange(k0, k0 + nk) / ny
+        QX, QY = np.meshgrid(qx, qy, indexing="ij")
+        P = np.zeros((nx, nk, d, d), dtype=np.complex128)
+        cx, cy = 2 - 2 * np.cos(QX), 2 - 2 * np.cos(QY)
+        P[..., 0, 0] = cx + 0.5 * cy + 0.05
+        P[..., 1, 1] = cy + 0.5 * cx + 0.05
+        P[..., 2, 2] = 0.7 * (cx + cy) + 0.05
+        P[..., 0, 1] = 0.5 * np.sin(QX) * np.sin(QY)
+        P[..., 1, 0] = P[..., 0, 1]
+        P[..., 0, 2] = 0.3j * np.sin(QX)
+        P[..., 2, 0] = -0.3j * np.sin(QX)
+        P[..., 1, 2] = 0.3j * np.sin(QY)
+        P[..., 2, 1] = -0.3j * np.sin(QY)
+        s.set_kernel_columns(P, k0, normalized=False)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    n = nx * ny
+    u1 = torch.rand((d, n), generator=gen, device="cuda", dtype=torch.float64) - 0.5
+    u2 = torch.rand((d, n), generator=gen, device="cuda", dtype=torch.float64) - 0.5
+    f1, f2, f3 = (torch.empty_like(u1) for _ in range(3))
+    s.post_force_device(u1, f1)
+    e1 = s.results()["epot"]
+    s.post_force_device(u2, f2)
+    e2 = s.results()["epot"]
+    u3 = 2.0 * u1 - 3.0 * u2
+    s.post_force_device(u3, f3)
+    e3 = s.results()["epot"]
+    scale = f3.abs().max().item()
+    assert (f3 - (2.0 * f1 - 3.0 * f2)).abs().max().item() < TOL * scale
+    for u, f, e in ((u1, f1, e1), (u2, f2, e2), (u3, f3, e3)):
+        ed = -0.5 * torch.sum(f * u).item()
+        assert abs(e - ed) <= 1e-11 * abs(e)
+    # translation: only q = 0 contributes; Phi(0) = 0.05 * identity (unnormalised)
+    ut = torch.zeros_like(u1)
+    ut[0] = 0.25
+    ut[2] = -1.5
+    s.post_force_device(ut, f1)
+    r = s.results()
+    assert abs(r["u0"][0] - 0.25 * n) < 1e-9 * n and abs(r["u0"][2] + 1.5 * n) < 1e-9 * n
+    assert (f1[0] + 0.05 * 0.25).abs().max().item() < 1e-12
+    assert (f1[2] - 0.05 * 1.5).abs().max().item() < 1e-12
+    assert f1[1].abs().max().item() < 1e-12
+    s.post_force_device(torch.zeros_like(u1), f1)
+    assert f1.abs().max().item() == 0.0 and s.results()["epot"] == 0.0
+    s.close()
+
+
+def make_atoms(nx, ny, nu, rng, nghost_frac=0.0):
+    n = nx * ny * nu
+    gid = np.array([(ix, iy, iu) for ix in range(nx) for iy in range(ny) for iu in range(nu)],
+                   dtype=np.int32)
+    gid = gid[rng.permutation(n)]
+    xeq = np.stack([gid[:, 0] + 0.5, gid[:, 1] + 0.5, -gid[:, 2].astype(float)], axis=1)
+    x = xeq + rng.uniform(-0.3, 0.3, size=(n, 3))
+    x[:, 0] = np.mod(x[:, 0], nx)
+    x[:, 1] = np.mod(x[:, 1], ny)
+    mask = np.where(rng.random(n) < 0.95, 3, 1).astype(np.int32)
+    return x, xeq, gid, mask
+
+
+@pytest.mark.parametrize("nx,ny,nu,shift", [(6, 5, 2, (0, 0)), (37, 16, 1, (3, -2)), (64, 64, 2, (0, 0))])
+def test_gather_scatter_against_oracle(B, nx, ny, nu, shift, oracle_libs):
+    import torch
+    O = oracle_libs
+    rng = np.random.default_rng(11)
+    d = 3 * nu
+    x, xeq, gid, mask = make_atoms(nx, ny, nu, rng)
+    n = x.shape[0]
+    g_ref = gid.copy()
+    u_ref, n_ref = O.gather(x, xeq, g_ref, mask, 2, nx, ny, d, float(nx), float(ny), *shift)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    dx, dxeq = torch.tensor(x, device="cuda"), torch.tensor(xeq, device="cuda")
+    dgid, dmask = torch.tensor(gid, device="cuda"), torch.tensor(mask, device="cuda")
+    du = torch.zeros((d, nx * ny), device="cuda", dtype=torch.float64)
+    s.gather(dx, dxeq, dgid, dmask, 2, n, float(nx), float(ny), shift[0], shift[1], du)
+    r = s.results()
+    assert r["natoms_gathered"] == n_ref and r["n_out_of_range"] == 0
+    assert np.array_equal(du.cpu().numpy(), u_ref)            # bit-exact: same subtractions
+    assert np.array_equal(dgid.cpu().numpy(), g_ref)          # shifted gid written back
+    fxy = rng.standard_normal((d, nx * ny))
+    f0 = rng.standard_normal((n, 3))
+    nlocal = n - n // 7
+    f_ref, fsum_ref, k_ref = O.scatter(fxy, g_ref, mask, 2, f0.copy(), nlocal=nlocal, nx=nx, ny=ny)
+    df = torch.tensor(f0, device="cuda")
+    s.scatter(dgid, dmask, 2, n, nlocal, df, torch.tensor(fxy, device="cuda"))
+    r = s.results()
+    assert r["natoms_scattered"] == k_ref
+    assert np.array_equal(df.cpu().numpy(), f_ref)
+    assert np.abs(r["fsum"] - fsum_ref).max() <= 1e-12 * max(1.0, np.abs(fsum_ref).max())
+    s.close()
+
+
+def test_full_step_device_resident(B, oracle_libs):
+    """gather -> solver -> scatter on device-resident atoms vs. the oracle chain."""
+    import torch
+    O = oracle_libs
+    g = load_golden("C1_sc100_128x128")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    rng = np.random.default_rng(5)
+    x, xeq, gid, mask = make_atoms(nx, ny, 1, rng)
+    mask[:] = 3
+    n = x.shape[0]
+    u_ref, _ = O.gather(x, xeq, gid.copy(), mask, 2, nx, ny, d, float(nx), float(ny))
+    f_ref, e_ref, u0_ref = O.post_force(u_ref.reshape(d, nx, ny), g["phi"], g["linf"])
+    fa_ref, fsum_ref, _ = O.scatter(f_ref.reshape(d, nx * ny), gid, mask, 2, np.zeros((n, 3)), nx=nx, ny=ny)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    for graph in (False, True):
+        s.use_graph(graph)
+        for _ in range(2):
+            df = torch.zeros((n, 3), device="cuda", dtype=torch.float64)
+            s.full_step(torch.tensor(x, device="cuda"), torch.tensor(xeq, device="cuda"),
+                        torch.tensor(gid, device="cuda"), torch.tensor(mask, device="cuda"), 2, n, n,
+                        float(nx), float(ny), df)
+            r = s.results()
+            assert rel_err(df.cpu().numpy(), fa_ref) < TOL
+            assert abs(r["epot"] - e_ref) <= TOL * abs(e_ref)
+            assert np.abs(r["fsum"] - fsum_ref).max() <= 1e-9
+    s.close()
+
+
+def test_async_pre_force_and_errors(B):
+    g = load_golden("small_sc100_16x12")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    u = np.ascontiguousarray(g["u_uniform"].reshape(d, nx * ny))
+    f = np.zeros_like(u)
+    with pytest.raises(B.GFMDError) as ei:          # post_force before set_kernel
+        s.post_force(u, f)
+    assert ei.value.code == 6
+    bad = g["phi"].copy()
+    bad[5, 0, 1] += 0.1                              # break Hermiticity
+    with pytest.raises(B.GFMDError) as ei:
+        s.set_kernel(bad, g["linf"])
+    assert ei.value.code == 7
+    s.set_kernel(g["phi"], g["linf"])
+    s.pin_host_buffers(True)
+    s.pre_force(u, f)                                # asynchronous start, then collect
+    e = s.post_force(u, f)
+    assert rel_err(f.reshape(d, nx, ny), g["f_uniform"]) < TOL
+    assert abs(e - float(g["epot_uniform"])) <= TOL * abs(e)
+    prof = None
+    s.profile(True)
+    s.post_force(u, f)
+    prof = s.stage_times()
+    assert prof["cols_fused"][1] == 1 and prof["cols_fused"][0] > 0
+    s.close()

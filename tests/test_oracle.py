@@ -1,0 +1,125 @@
+"""CPU tests: pin the oracle restatements (numpy, plain C) against the golden
+vectors produced by the reference's own sources, and -- where oracle/_ref was
+built -- against those sources directly."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, golden_names, load_golden, rel_err
+
+TOL = 1e-13   # restatements differ from the reference arithmetic only by FFT rounding
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_numpy_oracle_matches_golden(name, oracle_libs):
+    O = oracle_libs
+    g = load_golden(name)
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    for c in golden_cases(g):
+        f, e, u0 = O.post_force(g["u_" + c], g["phi"], g["linf"])
+        assert rel_err(f, g["f_" + c]) < TOL
+        assert abs(e - g["epot_" + c]) <= TOL * max(1.0, abs(g["epot_" + c]))
+        assert np.abs(u0 - g["u0_" + c]).max() <= TOL * max(1.0, np.abs(g["u0_" + c]).max())
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("backend", [0, 1])
+def test_c_oracle_matches_golden(name, backend, oracle_libs):
+    O = oracle_libs
+    g = load_golden(name)
+    if backend == 0 and int(g["nx"]) * int(g["ny"]) > 4096:
+        pytest.skip("long-double DFT backend only exercised on small grids")
+    for c in golden_cases(g):
+        f, e, u0 = O.c_post_force(g["u_" + c], g["phi"], g["linf"], backend)
+        tol = 0.0 if backend == 0 else TOL     # same DFT as the golden run -> bit-exact
+        assert rel_err(f, g["f_" + c]) <= tol
+        assert abs(e - g["epot_" + c]) <= tol * max(1.0, abs(g["epot_" + c]))
+
+
+def test_plain_fft_all_radices(oracle_libs):
+    """oracle/fft_plain.c (mixed radix + Bluestein) against numpy's pocketfft."""
+    import ctypes
+    lib = oracle_libs.clib()
+    lib.fftp_plan_2d.restype = ctypes.c_void_p
+    lib.fftp_plan_2d.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.fftp_exec_2d.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.fftp_destroy.argtypes = [ctypes.c_void_p]
+    rng = np.random.default_rng(5)
+    for nx, ny in [(1, 1), (2, 3), (4, 8), (5, 7), (12, 30), (37, 64), (64, 37), (74, 11), (105, 128),
+                   (13, 26), (256, 6)]:
+        a = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+        p = lib.fftp_plan_2d(nx, ny)
+        b = a.copy()
+        lib.fftp_exec_2d(p, b.ctypes.data, -1)
+        assert rel_err(b, np.fft.fft2(a)) < 1e-13, (nx, ny)
+        lib.fftp_exec_2d(p, b.ctypes.data, +1)
+        assert rel_err(b / (nx * ny), a) < 1e-13, (nx, ny)
+        lib.fftp_destroy(p)
+
+
+def test_reference_build_matches_golden(oracle_libs):
+    """The reference's own solver sources (when built here) reproduce the
+    committed golden vectors bit for bit, and the plugin tables too."""
+    O = oracle_libs
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built (no /root/reference)")
+    for name in ["small_sc100_16x12", "C3_fcc100_two_layers_10x10"]:
+        g = load_golden(name)
+        nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+        k = O.RefKernel(str(g["kernel"]))
+        assert k.ndof == d
+        phi = k.phi(nx, ny)
+        assert np.array_equal(phi, g["phi"])
+        s = O.RefSolver(nx, ny, d, fft_backend=0)
+        s.set_kernel(k)
+        for c in golden_cases(g):
+            f, e, u0 = s.post_force(g["u_" + c])
+            assert np.array_equal(f, g["f_" + c])
+            assert e == g["epot_" + c]
+        s.close()
+        k.close()
+
+
+def test_phi_symmetries(oracle_libs):
+    """Phi Hermitian and Phi(-q) = conj Phi(q): what the half-spectrum,
+    Hermitian-packed device table relies on."""
+    for name in golden_names():
+        g = load_golden(name)
+        nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+        P = g["phi"].reshape(nx, ny, d, d)
+        scale = np.abs(P).max()
+        assert np.abs(P - np.conj(np.swapaxes(P, 2, 3))).max() < 1e-14 * scale
+        Pm = P[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+        assert np.abs(P - np.conj(Pm)).max() < 1e-14 * scale
+
+
+def test_energy_identity(oracle_libs):
+    """E = -1/2 sum_r f.u when linf = 0 (SURVEY 8a restatement)."""
+    g = load_golden("small_sc100_16x12")
+    f, e, _ = oracle_libs.post_force(g["u_uniform"], g["phi"], g["linf"])
+    assert abs(e + 0.5 * np.sum(f * g["u_uniform"])) < 1e-12 * abs(e)
+
+
+def test_gather_scatter_oracles_agree(oracle_libs):
+    O = oracle_libs
+    rng = np.random.default_rng(3)
+    nx, ny, nu = 6, 5, 2
+    d = 3 * nu
+    n = nx * ny * nu
+    gid = np.array([(ix, iy, iu) for ix in range(nx) for iy in range(ny) for iu in range(nu)],
+                   dtype=np.int32)
+    perm = rng.permutation(n)
+    gid = gid[perm]
+    xeq = np.stack([gid[:, 0] + 0.5, gid[:, 1] + 0.5, -gid[:, 2].astype(float)], axis=1)
+    x = xeq + rng.uniform(-0.3, 0.3, size=(n, 3))
+    x[:, 0] = np.mod(x[:, 0], nx)     # wrapped positions -> minimum image needed
+    x[:, 1] = np.mod(x[:, 1], ny)
+    mask = np.where(rng.random(n) < 0.9, 3, 1).astype(np.int32)
+    for shift in [(0, 0), (2, -1)]:
+        u1, n1 = O.gather(x, xeq, gid.copy(), mask, 2, nx, ny, d, float(nx), float(ny), *shift)
+        u2, n2, _ = O.c_gather(x, xeq, gid.copy(), mask, 2, nx, ny, d, float(nx), float(ny), *shift)
+        assert n1 == n2 and np.array_equal(u1, u2)
+        assert np.abs(u1).max() <= 0.3 + 1e-12
+    fxy = rng.standard_normal((d, nx * ny))
+    f1, s1, k1 = O.scatter(fxy, gid, mask, 2, np.zeros((n, 3)), nx=nx, ny=ny)
+    f2, s2, k2 = O.c_scatter(fxy, gid, mask, 2, np.zeros((n, 3)), nx, ny)
+    assert k1 == k2 and np.array_equal(f1, f2) and np.allclose(s1, s2, rtol=0, atol=1e-12)

@@ -1,0 +1,1092 @@
+// libgfmd_b200: C ABI (include/gfmd_b200.h) + orchestration of the CUDA kernels.
+// No CPU fallback anywhere in this file: every compute entry point launches
+// kernels on the handle's device or fails with an error code.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gfmd_b200.h"
+#include "fft_engine.cuh"
+#include "kernels_generic.cuh"
+#include "kernels_fast.cuh"
+
+using namespace gfmd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in dynamic shared memory per CTA
+
+// ------------------------------------------------------------------- NCCL ---
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+
+NcclApi &nccl()
+{
+  static NcclApi api;
+  return api;
+}
+
+bool nccl_load()
+{
+  NcclApi &a = nccl();
+  if (a.lib) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) {
+    a.err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+    return false;
+  }
+#define LOAD(sym)                                                       \
+  a.sym = reinterpret_cast<decltype(a.sym)>(dlsym(a.lib, "nccl" #sym)); \
+  if (!a.sym) {                                                         \
+    a.err = "libnccl lacks nccl" #sym;                                  \
+    a.lib = nullptr;                                                    \
+    return false;                                                       \
+  }
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(AllReduce)
+  LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
+#undef LOAD
+  return true;
+}
+
+// --------------------------------------------------------------- FFT plans ---
+
+struct DevFft {
+  FftDesc desc;
+  std::vector<void *> allocs;
+  size_t bytes = 0;
+};
+
+void fill_tw(std::vector<double2> &tw, int n)
+{
+  const long double pi = 3.141592653589793238462643383279502884L;
+  tw.resize(n);
+  for (int k = 0; k < n; ++k) {
+    // exact octant symmetry is not needed: long double gives < 1 ulp double error
+    long double a = -2.0L * pi * (long double) k / (long double) n;
+    tw[k] = make_double2((double) cosl(a), (double) sinl(a));
+  }
+}
+
+bool factor_smooth(int n, FftCore &c)
+{
+  c.len = n;
+  c.npass = 0;
+  int rem = n;
+  const int rad[] = {8, 4, 2, 3, 5, 7};
+  for (int r : rad)
+    while (rem % r == 0 && c.npass < kMaxPass) {
+      c.radix[c.npass++] = r;
+      rem /= r;
+    }
+  return rem == 1;
+}
+
+cudaError_t upload(const void *src, size_t bytes, void **dst, DevFft &f)
+{
+  cudaError_t e = cudaMalloc(dst, bytes);
+  if (e != cudaSuccess) return e;
+  f.allocs.push_back(*dst);
+  f.bytes += bytes;
+  return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+}
+
+// host-side complex FFT by definition-free recursion is not needed: the chirp
+// filter spectrum is computed with a simple O(m log m) radix-2 in long double.
+void host_fft_pow2(std::vector<long double> &re, std::vector<long double> &im, int sign)
+{
+  const int n = (int) re.size();
+  const long double pi = 3.141592653589793238462643383279502884L;
+  for (int i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        long double a = sign * 2.0L * pi * k / len;
+        long double wr = cosl(a), wi = sinl(a);
+        long double xr = re[i + k + len / 2] * wr - im[i + k + len / 2] * wi;
+        long double xi = re[i + k + len / 2] * wi + im[i + k + len / 2] * wr;
+        re[i + k + len / 2] = re[i + k] - xr;
+        im[i + k + len / 2] = im[i + k] - xi;
+        re[i + k] += xr;
+        im[i + k] += xi;
+      }
+  }
+}
+
+cudaError_t build_fft(int n, DevFft &out)
+{
+  memset(&out.desc, 0, sizeof(out.desc));
+  FftDesc &d = out.desc;
+  d.n = n;
+  std::vector<double2> tw;
+  if (factor_smooth(n, d.core)) {
+    d.bluestein = 0;
+    d.ld_min = n;
+    fill_tw(tw, n);
+    return upload(tw.data(), sizeof(double2) * n, (void **) &d.core.tw, out);
+  }
+  d.bluestein = 1;
+  int m = 1;
+  while (m < 2 * n - 1) m *= 2;
+  factor_smooth(m, d.core);
+  d.ld_min = m;
+  fill_tw(tw, m);
+  cudaError_t e = upload(tw.data(), sizeof(double2) * m, (void **) &d.core.tw, out);
+  if (e != cudaSuccess) return e;
+  const long double pi = 3.141592653589793238462643383279502884L;
+  std::vector<double2> chirp(n);
+  std::vector<long double> br(m, 0.0L), bi(m, 0.0L);
+  for (int k = 0; k < n; ++k) {
+    long long k2 = ((long long) k * k) % (2LL * n);
+    long double a = -pi * (long double) k2 / (long double) n;
+    long double c = cosl(a), s = sinl(a);
+    chirp[k] = make_double2((double) c, (double) s);
+    br[k] = c; bi[k] = -s;
+    if (k > 0) { br[m - k] = c; bi[m - k] = -s; }
+  }
+  host_fft_pow2(br, bi, -1);
+  std::vector<double2> bhat(m);
+  for (int k = 0; k < m; ++k) bhat[k] = make_double2((double) (br[k] / m), (double) (bi[k] / m));
+  e = upload(chirp.data(), sizeof(double2) * n, (void **) &d.chirp, out);
+  if (e != cudaSuccess) return e;
+  return upload(bhat.data(), sizeof(double2) * m, (void **) &d.bhat, out);
+}
+
+void free_fft(DevFft &f)
+{
+  for (void *p : f.allocs) cudaFree(p);
+  f.allocs.clear();
+}
+
+// threads needed so that every pass fits kEPT elements per thread
+int min_threads_for(const FftCore &c)
+{
+  int t = 32;
+  for (int p = 0; p < c.npass; ++p) {
+    const int R = c.radix[p];
+    const int U = kEPT / R;
+    const int need = (c.len / R + U - 1) / U;
+    if (need > t) t = need;
+  }
+  return t;
+}
+
+int round_up_pow2(int v)
+{
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------- handle ---
+
+struct gfmd_b200 {
+  int nx = 0, ny = 0, d = 0, device = 0;
+  GridDesc g{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  double *d_u = nullptr, *d_f = nullptr;
+  double2 *d_stage = nullptr, *d_stage2 = nullptr;
+  double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
+  int fsum_part_cap = 0;
+  StepResults *d_res = nullptr, *h_res = nullptr;
+  double2 *d_tw_ny = nullptr;
+  DevFft fft_rows, fft_cols;
+
+  // launch parameters
+  bool even = true;
+  int rows_RB = 1, rows_ld = 0, rows_T = 64;
+  size_t rows_smem = 0;
+  int cols_ld = 0, cols_T = 64;
+  size_t cols_smem = 0;
+  int fast_rows = 0, fast_cols = 0;   // specialised kernels selected
+
+  bool phi_set = false;
+  std::vector<char> phi_cols_set;
+  double herm_dev = 0.0, conj_dev = 0.0;
+
+  ncclComm_t comm = nullptr;
+
+  // CUDA graph of the solver step
+  bool want_graph = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  const double *graph_u = nullptr;
+  double *graph_f = nullptr;
+  long long graph_launches = 0;
+
+  // async host path
+  const double *pending_u = nullptr;
+  std::map<const void *, size_t> pinned;   // host ranges this handle page-locked
+  bool pin_host = false;
+
+  bool profiling = false;
+  cudaEvent_t ev[GFMD_B200_NSTAGES + 1] = {};
+  double stage_ms[GFMD_B200_NSTAGES] = {};
+  long long stage_cnt[GFMD_B200_NSTAGES] = {};
+
+  long long launches = 0;
+  double bytes = 0.0;
+  std::string err;
+  std::string desc;
+};
+
+namespace {
+
+int fail(gfmd_b200 *h, int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CU(h, call)                                                                     \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(h, GFMD_B200_ECUDA, "%s failed: %s (%s:%d)", #call,                   \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+  } while (0)
+
+#define NC(h, call)                                                                     \
+  do {                                                                                  \
+    ncclResult_t r__ = (call);                                                          \
+    if (r__ != ncclSuccess)                                                             \
+      return fail(h, GFMD_B200_ENCCL, "%s failed: %s", #call, nccl().GetErrorString(r__)); \
+  } while (0)
+
+template <typename T> cudaError_t dmalloc(gfmd_b200 *h, T **p, size_t count)
+{
+  size_t bytes = sizeof(T) * (count ? count : 1);
+  cudaError_t e = cudaMalloc((void **) p, bytes);
+  if (e == cudaSuccess) h->bytes += (double) bytes;
+  return e;
+}
+
+int set_device(gfmd_b200 *h)
+{
+  CU(h, cudaSetDevice(h->device));
+  return 0;
+}
+
+int plan(gfmd_b200 *h)
+{
+  const GridDesc &g = h->g;
+  // rows
+  h->even = (g.ny % 2 == 0);
+  const int nrow_len = h->even ? g.ny / 2 : g.ny;
+  CU(h, build_fft(nrow_len, h->fft_rows));
+  CU(h, build_fft(g.nx, h->fft_cols));
+  h->bytes += (double) (h->fft_rows.bytes + h->fft_cols.bytes);
+  {
+    std::vector<double2> tw;
+    fill_tw(tw, g.ny);
+    CU(h, dmalloc(h, &h->d_tw_ny, (size_t) g.ny));
+    CU(h, cudaMemcpy(h->d_tw_ny, tw.data(), sizeof(double2) * g.ny, cudaMemcpyHostToDevice));
+  }
+  int ld = h->fft_rows.desc.ld_min;
+  const int need = h->even ? g.ny / 2 + 1 : g.ny;
+  if (ld < need) ld = need;
+  if ((ld & 1) == 0) ld += 1;            // odd stride: transposed accesses spread over banks
+  h->rows_ld = ld;
+  int RB = 8192 / ld;
+  if (RB < 1) RB = 1;
+  if (RB > 32) RB = 32;
+  if (RB > g.nx_loc) RB = g.nx_loc;
+  while (RB > 1 && (size_t) RB * ld * sizeof(double2) > 200 * 1024) --RB;
+  h->rows_RB = RB;
+  h->rows_smem = (size_t) RB * ld * sizeof(double2);
+  if (h->rows_smem > kMaxSmem)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "ny = %d: one row (%zu B) exceeds shared memory", g.ny,
+                h->rows_smem);
+  int tmin = min_threads_for(h->fft_rows.desc.core);
+  if (tmin > 512)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "ny = %d: row transform of length %d too long for one CTA",
+                g.ny, h->fft_rows.desc.core.len);
+  int t = round_up_pow2(RB * h->fft_rows.desc.core.len / 8);
+  if (t < tmin) t = round_up_pow2(tmin);
+  if (t < 64) t = 64;
+  if (t > 512) t = 512;
+  h->rows_T = t;
+
+  // columns
+  int cld = h->fft_cols.desc.ld_min;
+  if (cld < g.nx) cld = g.nx;
+  h->cols_ld = cld;
+  h->cols_smem = (size_t) g.d * cld * sizeof(double2);
+  if (h->cols_smem > kMaxSmem)
+    return fail(h, GFMD_B200_EUNSUPPORTED,
+                "nx = %d with ndof = %d: a column set (%zu B) exceeds the %zu B of shared memory per "
+                "CTA (long-column path not available in this build)",
+                g.nx, g.d, h->cols_smem, kMaxSmem);
+  tmin = min_threads_for(h->fft_cols.desc.core);
+  if (tmin > 512)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d: column transform too long for one CTA", g.nx);
+  t = round_up_pow2(g.d * h->fft_cols.desc.core.len / 8);
+  if (t < tmin) t = round_up_pow2(tmin);
+  if (t < 64) t = 64;
+  if (t > 512) t = 512;
+  h->cols_T = t;
+
+#define SET_SMEM(k, bytes) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)))
+  if (h->even) {
+    SET_SMEM(k_rows_fwd<true>, h->rows_smem);
+    SET_SMEM(k_rows_inv<true>, h->rows_smem);
+  } else {
+    SET_SMEM(k_rows_fwd<false>, h->rows_smem);
+    SET_SMEM(k_rows_inv<false>, h->rows_smem);
+  }
+  switch (g.d) {
+    case 3: SET_SMEM(k_cols_fused<3>, h->cols_smem); break;
+    case 6: SET_SMEM(k_cols_fused<6>, h->cols_smem); break;
+    case 9: SET_SMEM(k_cols_fused<9>, h->cols_smem); break;
+    case 12: SET_SMEM(k_cols_fused<12>, h->cols_smem); break;
+    default: SET_SMEM(k_cols_fused<0>, h->cols_smem); break;
+  }
+#undef SET_SMEM
+  int rc = fast_plan(h->g, h->fast_rows, h->fast_cols);
+  if (rc) return fail(h, GFMD_B200_ECUDA, "fast kernel setup failed");
+  return 0;
+}
+
+int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int rank, int nranks)
+{
+  if (!out) return fail(nullptr, GFMD_B200_EINVAL, "null handle pointer");
+  *out = nullptr;
+  if (nx < 1 || ny < 1) return fail(nullptr, GFMD_B200_EINVAL, "grid %d x %d invalid", nx, ny);
+  if (ndof < 3 || ndof % 3 != 0 || ndof > GFMD_B200_MAX_NDOF)
+    return fail(nullptr, GFMD_B200_EINVAL, "ndof = %d must be a multiple of 3 in [3, %d]", ndof,
+                GFMD_B200_MAX_NDOF);
+  if (nranks < 1 || rank < 0 || rank >= nranks)
+    return fail(nullptr, GFMD_B200_EINVAL, "rank %d of %d invalid", rank, nranks);
+  if (nx % nranks != 0)
+    return fail(nullptr, GFMD_B200_EUNSUPPORTED, "nx = %d not divisible by %d slab ranks", nx, nranks);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, GFMD_B200_ENOGPU, "no CUDA device: %s (this library has no CPU fallback)",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev)
+    return fail(nullptr, GFMD_B200_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+
+  gfmd_b200 *h = new gfmd_b200;
+  h->nx = nx; h->ny = ny; h->d = ndof; h->device = device;
+  GridDesc &g = h->g;
+  g.nx = nx; g.ny = ny; g.nyh = ny / 2 + 1; g.d = ndof;
+  g.P = nranks; g.rank = rank;
+  g.nx_loc = nx / nranks; g.x0 = rank * g.nx_loc;
+  g.kyb = (g.nyh + nranks - 1) / nranks;
+  g.ky0 = rank * g.kyb;
+  g.nky_loc = g.nyh - g.ky0;
+  if (g.nky_loc > g.kyb) g.nky_loc = g.kyb;
+  if (g.nky_loc < 0) g.nky_loc = 0;
+
+  int rc = 0;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    gfmd_b200_destroy(h);
+    return code;
+  };
+  if ((rc = set_device(h))) return bail(rc);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->err = "cudaStreamCreate failed";
+    return bail(GFMD_B200_ECUDA);
+  }
+  h->own_stream = true;
+  if ((rc = plan(h))) return bail(rc);
+
+  const size_t nxy = (size_t) g.nx_loc * g.ny;
+  const size_t nstage = (size_t) g.P * g.d * g.kyb * g.nx_loc;
+  const size_t nphi = (size_t) g.nky_loc * g.d * g.d * g.nx;
+  cudaError_t ce = cudaSuccess;
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_u, nxy * g.d);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_f, nxy * g.d);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_stage, nstage);
+  if (ce == cudaSuccess && g.P > 1) ce = dmalloc(h, &h->d_stage2, nstage);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_phi, nphi);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_linf, (size_t) GFMD_B200_MAX_NDOF);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_epart, (size_t) g.kyb + 1);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_res, (size_t) 1);
+  if (ce == cudaSuccess) ce = cudaMallocHost((void **) &h->h_res, sizeof(StepResults));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_u, 0, sizeof(double) * nxy * g.d);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_f, 0, sizeof(double) * nxy * g.d);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_stage, 0, sizeof(double2) * nstage);
+  if (ce == cudaSuccess && g.P > 1) ce = cudaMemset(h->d_stage2, 0, sizeof(double2) * nstage);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_linf, 0, sizeof(double) * GFMD_B200_MAX_NDOF);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_res, 0, sizeof(StepResults));
+  if (ce != cudaSuccess) {
+    h->err = std::string("device allocation failed: ") + cudaGetErrorString(ce);
+    return bail(GFMD_B200_ECUDA);
+  }
+  memset(h->h_res, 0, sizeof(StepResults));
+  h->phi_cols_set.assign(g.nky_loc > 0 ? g.nky_loc : 0, 0);
+  for (int i = 0; i <= GFMD_B200_NSTAGES; ++i) cudaEventCreate(&h->ev[i]);
+
+  char buf[512];
+  snprintf(buf, sizeof(buf),
+           "grid %dx%d ndof %d rank %d/%d | rows: %s len %d%s RB %d T %d smem %zu%s | cols: len %d%s T %d "
+           "smem %zu%s",
+           nx, ny, ndof, rank, nranks, h->even ? "half-length" : "full-length", h->fft_rows.desc.n,
+           h->fft_rows.desc.bluestein ? " (bluestein)" : "", h->rows_RB, h->rows_T, h->rows_smem,
+           h->fast_rows ? " [fast]" : "", h->fft_cols.desc.n, h->fft_cols.desc.bluestein ? " (bluestein)" : "",
+           h->cols_T, h->cols_smem, h->fast_cols ? " [fast]" : "");
+  h->desc = buf;
+  *out = h;
+  return 0;
+}
+
+void drop_graph(gfmd_b200 *h)
+{
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+}
+
+inline void stage_mark(gfmd_b200 *h, int i)
+{
+  if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
+}
+
+int exchange(gfmd_b200 *h, const double2 *src, double2 *dst)
+{
+  const GridDesc &g = h->g;
+  if (!h->comm) return fail(h, GFMD_B200_ESTATE, "slab handle used before gfmd_b200_comm_init");
+  const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;   // complex elements per peer block
+  NcclApi &a = nccl();
+  NC(h, a.GroupStart());
+  for (int r = 0; r < g.P; ++r) {
+    NC(h, a.Send(src + r * blk, blk * 2, ncclDouble, r, h->comm, h->stream));
+    NC(h, a.Recv(dst + r * blk, blk * 2, ncclDouble, r, h->comm, h->stream));
+  }
+  NC(h, a.GroupEnd());
+  return 0;
+}
+
+// the kernels of one solver step, enqueued on h->stream
+int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
+{
+  const GridDesc &g = h->g;
+  const int nrow_blocks = g.d * ((g.nx_loc + h->rows_RB - 1) / h->rows_RB);
+  double2 *A = h->d_stage;
+  double2 *B = g.P > 1 ? h->d_stage2 : h->d_stage;
+
+  CU(h, cudaMemsetAsync(&h->d_res->epot, 0, offsetof(StepResults, fsum), h->stream));
+
+  stage_mark(h, 1);
+  if (h->fast_rows) {
+    int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
+  } else {
+    if (h->even)
+      k_rows_fwd<true><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(
+          d_u, A, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
+    else
+      k_rows_fwd<false><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(
+          d_u, A, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
+    h->launches++;
+  }
+  stage_mark(h, 2);
+  if (g.P > 1) {
+    int rc = exchange(h, A, B);
+    if (rc) return rc;
+  }
+  stage_mark(h, 3);
+  if (g.nky_loc > 0) {
+    if (h->fast_cols) {
+      int rc = fast_cols_fused(h->fast_cols, B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart,
+                               h->d_res, h->stream, &h->launches);
+      if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+    } else {
+#define LAUNCH_COLS(DT)                                                                          \
+  k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
+      B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
+      switch (g.d) {
+        case 3: LAUNCH_COLS(3); break;
+        case 6: LAUNCH_COLS(6); break;
+        case 9: LAUNCH_COLS(9); break;
+        case 12: LAUNCH_COLS(12); break;
+        default: LAUNCH_COLS(0); break;
+      }
+#undef LAUNCH_COLS
+      h->launches++;
+    }
+  }
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc, h->d_res);
+  h->launches++;
+  stage_mark(h, 4);
+  if (g.P > 1) {
+    int rc = exchange(h, A, B);
+    if (rc) return rc;
+    NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
+                           h->stream));
+  }
+  stage_mark(h, 5);
+  if (h->fast_rows) {
+    int rc = fast_rows_inv(h->fast_rows, B, d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_inv launch failed");
+  } else {
+    if (h->even)
+      k_rows_inv<true><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(
+          B, d_f, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
+    else
+      k_rows_inv<false><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(
+          B, d_f, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
+    h->launches++;
+  }
+  stage_mark(h, 6);
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+void accumulate_stage_times(gfmd_b200 *h, int first, int last)
+{
+  // events first..last+1 were recorded; requires a stream sync by the caller
+  for (int s = first; s <= last; ++s) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]) == cudaSuccess) {
+      h->stage_ms[s] += ms;
+      h->stage_cnt[s]++;
+    }
+  }
+}
+
+int solver_step(gfmd_b200 *h, const double *d_u, double *d_f)
+{
+  if (!h->phi_set) return fail(h, GFMD_B200_ESTATE, "post_force before set_phi (set_kernel)");
+  if (d_u == d_f) return fail(h, GFMD_B200_EINVAL, "u and f must be different buffers");
+  const bool graph_ok = h->want_graph && h->g.P == 1 && !h->profiling;
+  if (!graph_ok) {
+    int rc = enqueue_solver(h, d_u, d_f);
+    if (rc) return rc;
+    if (h->profiling) {
+      CU(h, cudaStreamSynchronize(h->stream));
+      accumulate_stage_times(h, 1, 5);
+    }
+    return 0;
+  }
+  if (!h->graph_exec || h->graph_u != d_u || h->graph_f != d_f) {
+    drop_graph(h);
+    cudaGraph_t graph = nullptr;
+    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = h->launches;
+    int rc = enqueue_solver(h, d_u, d_f);
+    h->graph_launches = h->launches - before;
+    h->launches = before;
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    CU(h, ce);
+    ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CU(h, ce);
+    h->graph_u = d_u;
+    h->graph_f = d_f;
+  }
+  CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
+  h->launches += h->graph_launches;
+  return 0;
+}
+
+int fetch_results(gfmd_b200 *h)
+{
+  CU(h, cudaMemcpyAsync(h->h_res, h->d_res, sizeof(StepResults), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void try_pin(gfmd_b200 *h, const void *p, size_t bytes)
+{
+  if (!h->pin_host) return;
+  auto it = h->pinned.find(p);
+  if (it != h->pinned.end() && it->second >= bytes) return;
+  if (it != h->pinned.end()) {
+    cudaHostUnregister(const_cast<void *>(p));
+    h->pinned.erase(it);
+  }
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered)
+    return;                 // already page-locked / managed by someone else
+  cudaGetLastError();
+  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+    h->pinned[p] = bytes;
+  else
+    cudaGetLastError();     // pageable copies still work
+}
+
+// Hermitian packing of one q: M = full d x d complex matrix (row-major), scale s.
+inline void pack_hermitian(const double *M, const double *Mneg, int d, double s, double *dst,
+                           size_t plane_stride, double &amax, double &hdev, double &cdev)
+{
+  // Phi_h = (Phi(q) + conj Phi(-q)) / 2 ; then its Hermitian part
+  auto elem = [&](int i, int j, double &re, double &im) {
+    const double *a = M + 2 * ((size_t) i * d + j);
+    if (Mneg) {
+      const double *b = Mneg + 2 * ((size_t) i * d + j);
+      re = 0.5 * (a[0] + b[0]);
+      im = 0.5 * (a[1] - b[1]);
+      double dr = a[0] - b[0], di = a[1] + b[1];
+      double dv = std::sqrt(dr * dr + di * di);
+      if (dv > cdev) cdev = dv;
+    } else {
+      re = a[0];
+      im = a[1];
+    }
+    double av = std::sqrt(a[0] * a[0] + a[1] * a[1]);
+    if (av > amax) amax = av;
+  };
+  int c = d;
+  for (int i = 0; i < d; ++i) {
+    double re, im;
+    elem(i, i, re, im);
+    if (std::fabs(im) > hdev) hdev = std::fabs(im);
+    dst[(size_t) i * plane_stride] = re * s;
+    for (int j = i + 1; j < d; ++j) {
+      double r1, i1, r2, i2;
+      elem(i, j, r1, i1);
+      elem(j, i, r2, i2);
+      double dr = r1 - r2, di = i1 + i2;
+      double dv = std::sqrt(dr * dr + di * di);
+      if (dv > hdev) hdev = dv;
+      dst[(size_t) c * plane_stride] = 0.5 * (r1 + r2) * s;
+      dst[(size_t) (c + 1) * plane_stride] = 0.5 * (i1 - i2) * s;
+      c += 2;
+    }
+  }
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------- ABI ---
+
+extern "C" {
+
+const char *gfmd_b200_version(void) { return "gfmd_b200 0.1 (sm_100a, fp64)"; }
+
+int gfmd_b200_create(gfmd_b200_t **h, int nx, int ny, int ndof, int device)
+{
+  return create_common(h, nx, ny, ndof, device, 0, 1);
+}
+
+int gfmd_b200_create_slab(gfmd_b200_t **h, int nx, int ny, int ndof, int device, int rank, int nranks)
+{
+  return create_common(h, nx, ny, ndof, device, rank, nranks);
+}
+
+int gfmd_b200_get_unique_id(char id[GFMD_B200_UNIQUE_ID_BYTES])
+{
+  if (!nccl_load()) return fail(nullptr, GFMD_B200_ENCCL, "%s", nccl().err.c_str());
+  ncclUniqueId uid;
+  static_assert(sizeof(ncclUniqueId) == GFMD_B200_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclResult_t r = nccl().GetUniqueId(&uid);
+  if (r != ncclSuccess) return fail(nullptr, GFMD_B200_ENCCL, "ncclGetUniqueId: %s", nccl().GetErrorString(r));
+  memcpy(id, &uid, sizeof(uid));
+  return 0;
+}
+
+int gfmd_b200_comm_init(gfmd_b200_t *h, const char id[GFMD_B200_UNIQUE_ID_BYTES])
+{
+  if (!h) return GFMD_B200_EINVAL;
+  if (h->g.P == 1) return 0;
+  if (!nccl_load()) return fail(h, GFMD_B200_ENCCL, "%s", nccl().err.c_str());
+  int rc = set_device(h);
+  if (rc) return rc;
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NC(h, nccl().CommInitRank(&h->comm, h->g.P, uid, h->g.rank));
+  return 0;
+}
+
+void gfmd_b200_destroy(gfmd_b200_t *h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graph(h);
+  if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
+  for (auto &kv : h->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+  cudaGetLastError();
+  cudaFree(h->d_u); cudaFree(h->d_f); cudaFree(h->d_stage); cudaFree(h->d_stage2);
+  cudaFree(h->d_phi); cudaFree(h->d_linf); cudaFree(h->d_epart); cudaFree(h->d_fsum_part);
+  cudaFree(h->d_res); cudaFree(h->d_tw_ny);
+  if (h->h_res) cudaFreeHost(h->h_res);
+  free_fft(h->fft_rows);
+  free_fft(h->fft_cols);
+  for (int i = 0; i <= GFMD_B200_NSTAGES; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *gfmd_b200_last_error(const gfmd_b200_t *h)
+{
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int gfmd_b200_get_brick(const gfmd_b200_t *h, int *xlo, int *xhi, int *ylo, int *yhi, int *nxy_loc,
+                        int *gammai)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  const GridDesc &g = h->g;
+  if (xlo) *xlo = g.x0;
+  if (xhi) *xhi = g.x0 + g.nx_loc - 1;
+  if (ylo) *ylo = 0;
+  if (yhi) *yhi = g.ny - 1;
+  if (nxy_loc) *nxy_loc = g.nx_loc * g.ny;
+  if (gammai) *gammai = g.x0 == 0 ? 0 : -1;
+  return 0;
+}
+
+int gfmd_b200_get_q_columns(const gfmd_b200_t *h, int *kylo, int *nky)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  if (kylo) *kylo = h->g.ky0;
+  if (nky) *nky = h->g.nky_loc;
+  return 0;
+}
+
+int gfmd_b200_set_linf(gfmd_b200_t *h, const double *linf)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  int rc = set_device(h);
+  if (rc) return rc;
+  double tmp[GFMD_B200_MAX_NDOF] = {0};
+  if (linf)
+    for (int i = 0; i < h->g.d / 3; ++i) tmp[i] = linf[i];
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(h->d_linf, tmp, sizeof(tmp), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised, const double *linf)
+{
+  if (!h || !phi) return fail(h, GFMD_B200_EINVAL, "set_phi: null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const GridDesc &g = h->g;
+  const int d = g.d, nx = g.nx, ny = g.ny;
+  const size_t dsq = (size_t) d * d;
+  const double s = already_normalised ? 1.0 : 1.0 / ((double) nx * (double) ny);
+  double amax = 0.0, hdev = 0.0, cdev = 0.0;
+  CU(h, cudaStreamSynchronize(h->stream));
+  // chunk over local ky to bound the host staging buffer
+  const int chunk = 64;
+  std::vector<double> buf((size_t) chunk * dsq * nx);
+  for (int k0 = 0; k0 < g.nky_loc; k0 += chunk) {
+    const int nk = g.nky_loc - k0 < chunk ? g.nky_loc - k0 : chunk;
+    for (int kl = 0; kl < nk; ++kl) {
+      const int ky = g.ky0 + k0 + kl;
+      const int kyn = (ny - ky) % ny;
+      for (int kx = 0; kx < nx; ++kx) {
+        const int kxn = (nx - kx) % nx;
+        const double *M = phi + 2 * dsq * ((size_t) kx * ny + ky);
+        const double *Mn = phi + 2 * dsq * ((size_t) kxn * ny + kyn);
+        pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + kx, (size_t) nx, amax, hdev,
+                       cdev);
+      }
+    }
+    CU(h, cudaMemcpy(h->d_phi + (size_t) k0 * dsq * nx, buf.data(), sizeof(double) * (size_t) nk * dsq * nx,
+                     cudaMemcpyHostToDevice));
+  }
+  h->herm_dev = amax > 0 ? hdev / amax : 0.0;
+  h->conj_dev = amax > 0 ? cdev / amax : 0.0;
+  if (h->herm_dev > 1e-6)
+    return fail(h, GFMD_B200_EPHI, "Phi table is not Hermitian: max |Phi - Phi^H| / max|Phi| = %g", h->herm_dev);
+  if (h->conj_dev > 1e-6)
+    return fail(h, GFMD_B200_EPHI, "Phi(-q) != conj Phi(q): relative deviation %g (complex u(r)?)", h->conj_dev);
+  std::fill(h->phi_cols_set.begin(), h->phi_cols_set.end(), 1);
+  h->phi_set = true;
+  return gfmd_b200_set_linf(h, linf);
+}
+
+int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, int nky, int already_normalised)
+{
+  if (!h || !phi) return fail(h, GFMD_B200_EINVAL, "set_phi_columns: null argument");
+  const GridDesc &g = h->g;
+  if (nky < 0 || ky_first < g.ky0 || ky_first + nky > g.ky0 + g.nky_loc)
+    return fail(h, GFMD_B200_EINVAL, "set_phi_columns: ky range [%d,%d) outside this handle's [%d,%d)",
+                ky_first, ky_first + nky, g.ky0, g.ky0 + g.nky_loc);
+  int rc = set_device(h);
+  if (rc) return rc;
+  const int d = g.d, nx = g.nx;
+  const size_t dsq = (size_t) d * d;
+  const double s = already_normalised ? 1.0 : 1.0 / ((double) nx * (double) g.ny);
+  double amax = 0.0, hdev = 0.0, cdev = 0.0;
+  CU(h, cudaStreamSynchronize(h->stream));
+  const int chunk = 64;
+  std::vector<double> buf((size_t) chunk * dsq * nx);
+  for (int k0 = 0; k0 < nky; k0 += chunk) {
+    const int nk = nky - k0 < chunk ? nky - k0 : chunk;
+    for (int kl = 0; kl < nk; ++kl)
+      for (int kx = 0; kx < nx; ++kx) {
+        const double *M = phi + 2 * dsq * ((size_t) kx * nky + k0 + kl);
+        pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + kx, (size_t) nx, amax, hdev,
+                       cdev);
+      }
+    CU(h, cudaMemcpy(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),
+                     sizeof(double) * (size_t) nk * dsq * nx, cudaMemcpyHostToDevice));
+  }
+  if (amax > 0 && hdev / amax > 1e-6)
+    return fail(h, GFMD_B200_EPHI, "Phi table is not Hermitian: relative deviation %g", hdev / amax);
+  for (int k = 0; k < nky; ++k) h->phi_cols_set[ky_first - g.ky0 + k] = 1;
+  bool all = true;
+  for (char c : h->phi_cols_set) all = all && c;
+  h->phi_set = all;
+  return 0;
+}
+
+int gfmd_b200_phi_deviation(const gfmd_b200_t *h, double *herm_dev, double *conj_dev)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  if (herm_dev) *herm_dev = h->herm_dev;
+  if (conj_dev) *conj_dev = h->conj_dev;
+  return 0;
+}
+
+int gfmd_b200_post_force_device(gfmd_b200_t *h, const double *d_u, double *d_f)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  int rc = set_device(h);
+  if (rc) return rc;
+  return solver_step(h, d_u ? d_u : h->d_u, d_f ? d_f : h->d_f);
+}
+
+int gfmd_b200_pre_force_async_host(gfmd_b200_t *h, const double *u)
+{
+  if (!h || !u) return fail(h, GFMD_B200_EINVAL, "pre_force_async_host: null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t) h->g.d * h->g.nx_loc * h->g.ny;
+  try_pin(h, u, bytes);
+  CU(h, cudaMemcpyAsync(h->d_u, u, bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = solver_step(h, h->d_u, h->d_f);
+  if (rc) return rc;
+  h->pending_u = u;
+  return 0;
+}
+
+int gfmd_b200_post_force_host(gfmd_b200_t *h, const double *u, double *f, double *epot, double *u0)
+{
+  if (!h || !u || !f) return fail(h, GFMD_B200_EINVAL, "post_force_host: null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t) h->g.d * h->g.nx_loc * h->g.ny;
+  if (h->pending_u != u) {
+    rc = gfmd_b200_pre_force_async_host(h, u);
+    if (rc) return rc;
+  }
+  h->pending_u = nullptr;
+  try_pin(h, f, bytes);
+  CU(h, cudaMemcpyAsync(f, h->d_f, bytes, cudaMemcpyDeviceToHost, h->stream));
+  rc = fetch_results(h);
+  if (rc) return rc;
+  if (epot) *epot = h->h_res->epot;
+  if (u0)
+    for (int i = 0; i < h->g.d; ++i) u0[i] = h->h_res->u0[i];
+  return 0;
+}
+
+int gfmd_b200_gather(gfmd_b200_t *h, const double *d_x, const double *d_xeq, int *d_gid, const int *d_mask,
+                     int groupbit, int nall, double xprd, double yprd, int dxshift, int dyshift, double *d_u)
+{
+  if (!h || !d_x || !d_xeq || !d_gid || !d_mask) return fail(h, GFMD_B200_EINVAL, "gather: null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(h, cudaMemsetAsync(&h->d_res->natoms_gathered, 0, sizeof(int), h->stream));
+  CU(h, cudaMemsetAsync(&h->d_res->n_out_of_range, 0, sizeof(int), h->stream));
+  stage_mark(h, 0);
+  if (nall > 0) {
+    k_gather<<<(nall + 255) / 256, 256, 0, h->stream>>>(d_x, d_xeq, d_gid, d_mask, groupbit, nall, h->g, xprd,
+                                                        yprd, dxshift, dyshift, d_u ? d_u : h->d_u, h->d_res);
+    h->launches++;
+  }
+  if (h->profiling) {
+    cudaEventRecord(h->ev[1], h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+    accumulate_stage_times(h, 0, 0);
+  }
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+int gfmd_b200_scatter(gfmd_b200_t *h, const double *d_fgrid, const int *d_gid, const int *d_mask, int groupbit,
+                      int nall, int nlocal, double *d_f)
+{
+  if (!h || !d_gid || !d_mask || !d_f) return fail(h, GFMD_B200_EINVAL, "scatter: null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const int nblk = (nall + 255) / 256;
+  if (nblk > h->fsum_part_cap) {
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_fsum_part);
+    h->d_fsum_part = nullptr;
+    CU(h, dmalloc(h, &h->d_fsum_part, (size_t) 3 * nblk));
+    h->fsum_part_cap = nblk;
+  }
+  CU(h, cudaMemsetAsync(&h->d_res->natoms_scattered, 0, sizeof(int), h->stream));
+  if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
+  if (nall > 0) {
+    k_scatter<<<nblk, 256, 0, h->stream>>>(d_fgrid ? d_fgrid : h->d_f, d_gid, d_mask, groupbit, nall, nlocal,
+                                           h->g, d_f, h->d_fsum_part, h->d_res);
+    k_sum_partials<<<1, 256, 0, h->stream>>>(h->d_fsum_part, nblk, 3, h->d_res->fsum);
+    h->launches += 2;
+  } else {
+    CU(h, cudaMemsetAsync(h->d_res->fsum, 0, 3 * sizeof(double), h->stream));
+  }
+  if (h->profiling) {
+    cudaEventRecord(h->ev[7], h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+    accumulate_stage_times(h, 6, 6);
+  }
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+int gfmd_b200_full_step(gfmd_b200_t *h, const double *d_x, const double *d_xeq, int *d_gid, const int *d_mask,
+                        int groupbit, int nall, int nlocal, double xprd, double yprd, double *d_f)
+{
+  int rc = gfmd_b200_gather(h, d_x, d_xeq, d_gid, d_mask, groupbit, nall, xprd, yprd, 0, 0, nullptr);
+  if (rc) return rc;
+  rc = solver_step(h, h->d_u, h->d_f);
+  if (rc) return rc;
+  return gfmd_b200_scatter(h, nullptr, d_gid, d_mask, groupbit, nall, nlocal, d_f);
+}
+
+int gfmd_b200_get_results(gfmd_b200_t *h, double *epot, double *u0, double fsum[3], int counters[3])
+{
+  if (!h) return GFMD_B200_EINVAL;
+  int rc = set_device(h);
+  if (rc) return rc;
+  rc = fetch_results(h);
+  if (rc) return rc;
+  if (epot) *epot = h->h_res->epot;
+  if (u0)
+    for (int i = 0; i < h->g.d; ++i) u0[i] = h->h_res->u0[i];
+  if (fsum)
+    for (int i = 0; i < 3; ++i) fsum[i] = h->h_res->fsum[i];
+  if (counters) {
+    counters[0] = h->h_res->natoms_gathered;
+    counters[1] = h->h_res->natoms_scattered;
+    counters[2] = h->h_res->n_out_of_range;
+  }
+  return 0;
+}
+
+double *gfmd_b200_device_u(gfmd_b200_t *h) { return h ? h->d_u : nullptr; }
+double *gfmd_b200_device_f(gfmd_b200_t *h) { return h ? h->d_f : nullptr; }
+void *gfmd_b200_stream(gfmd_b200_t *h) { return h ? (void *) h->stream : nullptr; }
+
+int gfmd_b200_set_stream(gfmd_b200_t *h, void *s)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  drop_graph(h);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t) s;
+  h->own_stream = false;
+  return 0;
+}
+
+int gfmd_b200_synchronize(gfmd_b200_t *h)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gfmd_b200_pin_host_buffers(gfmd_b200_t *h, int on)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  h->pin_host = on != 0;
+  if (!on) {
+    for (auto &kv : h->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+    cudaGetLastError();
+    h->pinned.clear();
+  }
+  return 0;
+}
+
+int gfmd_b200_use_graph(gfmd_b200_t *h, int on)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  h->want_graph = on != 0;
+  if (!on) drop_graph(h);
+  return 0;
+}
+
+long long gfmd_b200_launch_count(const gfmd_b200_t *h) { return h ? h->launches : 0; }
+
+int gfmd_b200_profile(gfmd_b200_t *h, int on)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  h->profiling = on != 0;
+  if (on) {
+    for (int i = 0; i < GFMD_B200_NSTAGES; ++i) {
+      h->stage_ms[i] = 0.0;
+      h->stage_cnt[i] = 0;
+    }
+  }
+  return 0;
+}
+
+int gfmd_b200_get_stage_times(gfmd_b200_t *h, double ms[GFMD_B200_NSTAGES], long long counts[GFMD_B200_NSTAGES])
+{
+  if (!h) return GFMD_B200_EINVAL;
+  for (int i = 0; i < GFMD_B200_NSTAGES; ++i) {
+    if (ms) ms[i] = h->stage_ms[i];
+    if (counts) counts[i] = h->stage_cnt[i];
+  }
+  return 0;
+}
+
+const char *gfmd_b200_describe(gfmd_b200_t *h) { return h ? h->desc.c_str() : ""; }
+
+double gfmd_b200_memory_usage(const gfmd_b200_t *h) { return h ? h->bytes : 0.0; }
+
+}  // extern "C"

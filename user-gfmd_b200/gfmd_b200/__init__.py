@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's solver plugin interface on top of the
+C ABI of ``libgfmd_b200.so`` (``include/gfmd_b200.h``).
+
+``GFMDSolverB200`` follows ``class GFMDSolver`` (reference
+``src/main/gfmd_solver.h:34-123``) member for member -- ``set_grid_size``,
+``set_kernel``, ``pre_force``, ``post_force``, ``get_u0``, ``get_xlo_loc`` ... --
+so the parity tests read like drivers of the reference's own
+``GFMDSolverStatic``.  Inside LAMMPS the same ABI is bound from C++
+(``user-gfmd_b200/host/gfmd_solver_b200.{h,cpp}``).
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is usable,
+loading / creating raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgfmd_b200.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+NSTAGES = 7
+STAGE_NAMES = ("gather", "rows_fwd", "exchange_fwd", "cols_fused", "exchange_inv", "rows_inv",
+               "scatter")
+UNIQUE_ID_BYTES = 128
+
+# every symbol include/gfmd_b200.h declares: (restype, argtypes)
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_d = ctypes.c_double
+ABI = {
+    "gfmd_b200_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i]),
+    "gfmd_b200_create_slab": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
+    "gfmd_b200_get_unique_id": (_i, [ctypes.c_char_p]),
+    "gfmd_b200_comm_init": (_i, [_vp, ctypes.c_char_p]),
+    "gfmd_b200_destroy": (None, [_vp]),
+    "gfmd_b200_last_error": (ctypes.c_char_p, [_vp]),
+    "gfmd_b200_get_brick": (_i, [_vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gfmd_b200_get_q_columns": (_i, [_vp, c_int_p, c_int_p]),
+    "gfmd_b200_set_phi": (_i, [_vp, _vp, _i, _vp]),
+    "gfmd_b200_set_phi_columns": (_i, [_vp, _vp, _i, _i, _i]),
+    "gfmd_b200_set_linf": (_i, [_vp, _vp]),
+    "gfmd_b200_phi_deviation": (_i, [_vp, c_double_p, c_double_p]),
+    "gfmd_b200_post_force_host": (_i, [_vp, _vp, _vp, c_double_p, _vp]),
+    "gfmd_b200_pre_force_async_host": (_i, [_vp, _vp]),
+    "gfmd_b200_post_force_device": (_i, [_vp, _vp, _vp]),
+    "gfmd_b200_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i, _vp]),
+    "gfmd_b200_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gfmd_b200_full_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
+    "gfmd_b200_get_results": (_i, [_vp, c_double_p, _vp, _vp, _vp]),
+    "gfmd_b200_device_u": (_vp, [_vp]),
+    "gfmd_b200_device_f": (_vp, [_vp]),
+    "gfmd_b200_stream": (_vp, [_vp]),
+    "gfmd_b200_set_stream": (_i, [_vp, _vp]),
+    "gfmd_b200_synchronize": (_i, [_vp]),
+    "gfmd_b200_pin_host_buffers": (_i, [_vp, _i]),
+    "gfmd_b200_use_graph": (_i, [_vp, _i]),
+    "gfmd_b200_launch_count": (ctypes.c_longlong, [_vp]),
+    "gfmd_b200_profile": (_i, [_vp, _i]),
+    "gfmd_b200_get_stage_times": (_i, [_vp, _vp, _vp]),
+    "gfmd_b200_describe": (ctypes.c_char_p, [_vp]),
+    "gfmd_b200_memory_usage": (_d, [_vp]),
+    "gfmd_b200_version": (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+class GFMDError(RuntimeError):
+    """Mirrors LAMMPS error->one(FLERR, msg): the reference's only error path."""
+
+    def __init__(self, code, msg):
+        super().__init__("gfmd_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library(path=None):
+    """Loads libgfmd_b200.so; raises (no fallback) if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(user-gfmd_b200/csrc/build.sh). There is no CPU fallback." % p)
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)      # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Raw address of a numpy array, torch tensor (host or device) or int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError("cannot take the address of %r" % type(a))
+
+
+def get_unique_id():
+    buf = ctypes.create_string_buffer(UNIQUE_ID_BYTES)
+    rc = load_library().gfmd_b200_get_unique_id(buf)
+    if rc:
+        raise GFMDError(rc, load_library().gfmd_b200_last_error(None).decode())
+    return buf.raw
+
+
+class GFMDSolverB200:
+    """``static/b200``: drop-in for ``GFMDSolverStatic`` behind ``GFMDSolver``.
+
+    Reference interface (gfmd_solver.h) -> here:
+      GFMDSolver(LAMMPS*)                 -> GFMDSolverB200(device=0, rank=0, nranks=1)
+      set_grid_size(nx, ny, ndof)  (:41)  -> set_grid_size
+      set_kernel(kernel, normalize) (:42) -> set_kernel(phi_table, linf, normalized)
+                                             (the table fill_phi_buffer produced)
+      pre_force(u, f)              (:50)  -> pre_force   (asynchronous launch)
+      post_force(u, f, dump_prefix) (:51) -> post_force  -> epot of this rank
+      get_u0 / get_xlo_loc ...     (:72-90)
+      get_name                     (:92)  -> "static/b200"
+      memory_usage                 (:96)
+    """
+
+    name = "static/b200"
+
+    def __init__(self, device=0, rank=0, nranks=1, unique_id=None):
+        self.lib = load_library()
+        self.h = None
+        self.device, self.rank, self.nranks = device, rank, nranks
+        self._unique_id = unique_id
+        self.u0 = None
+
+    # -- reference interface ------------------------------------------------
+    def get_name(self):
+        return self.name
+
+    def set_grid_size(self, nx, ny, ndof):
+        if self.h:
+            self.close()
+        h = ctypes.c_void_p()
+        if self.nranks == 1:
+            rc = self.lib.gfmd_b200_create(ctypes.byref(h), nx, ny, ndof, self.device)
+        else:
+            rc = self.lib.gfmd_b200_create_slab(ctypes.byref(h), nx, ny, ndof, self.device,
+                                                self.rank, self.nranks)
+        if rc:
+            raise GFMDError(rc, self.lib.gfmd_b200_last_error(None).decode())
+        self.h = h
+        self.nx, self.ny, self.ndof = nx, ny, ndof
+        self.u0 = np.zeros(ndof)
+        if self.nranks > 1:
+            if self._unique_id is None:
+                raise GFMDError(6, "slab solver needs the NCCL unique id of rank 0")
+            self._check(self.lib.gfmd_b200_comm_init(self.h, self._unique_id))
+        v = [ctypes.c_int() for _ in range(6)]
+        self._check(self.lib.gfmd_b200_get_brick(self.h, *[ctypes.byref(x) for x in v]))
+        (self.xlo_loc, self.xhi_loc, self.ylo_loc, self.yhi_loc, self.nxy_loc,
+         self.gammai) = [x.value for x in v]
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.gfmd_b200_get_q_columns(self.h, ctypes.byref(a), ctypes.byref(b)))
+        self.kylo, self.nky = a.value, b.value
+
+    def init(self):
+        pass
+
+    def set_kernel(self, phi, linf=None, normalized=True):
+        """phi: the table fill_phi_buffer produced for the whole grid,
+        [nx*ny, ndof, ndof] complex128 (gfmd_misc.cpp:32-101)."""
+        phi = np.ascontiguousarray(phi, dtype=np.complex128)
+        if phi.size != self.nx * self.ny * self.ndof * self.ndof:
+            raise GFMDError(1, "phi table has %d entries, expected %d" %
+                            (phi.size, self.nx * self.ny * self.ndof ** 2))
+        lp = None
+        if linf is not None:
+            linf = np.ascontiguousarray(linf, dtype=np.float64)
+            lp = linf.ctypes.data
+        self._check(self.lib.gfmd_b200_set_phi(self.h, phi.ctypes.data, int(normalized), lp))
+
+    def set_kernel_columns(self, phi_cols, ky_first, normalized=True):
+        """phi_cols: [nx, nky, ndof, ndof] as fill_phi_buffer(ndof, nx, 0, nx-1, ny,
+        ky_first, ky_first+nky-1) lays it out."""
+        phi_cols = np.ascontiguousarray(phi_cols, dtype=np.complex128)
+        nky = phi_cols.size // (self.nx * self.ndof * self.ndof)
+        self._check(self.lib.gfmd_b200_set_phi_columns(self.h, phi_cols.ctypes.data, ky_first, nky,
+                                                       int(normalized)))
+
+    def set_linf(self, linf):
+        linf = np.ascontiguousarray(linf, dtype=np.float64)
+        self._check(self.lib.gfmd_b200_set_linf(self.h, linf.ctypes.data))
+
+    def pre_force(self, u, f=None):
+        """Asynchronous start (gfmd_solver.h:44-50).  u: host [ndof, nxy_loc]."""
+        self._check(self.lib.gfmd_b200_pre_force_async_host(self.h, _ptr(u)))
+
+    def post_force(self, u, f, dump_prefix=None):
+        """u, f: HOST arrays [ndof, nxy_loc] (numpy or pinned torch).  Fills f and
+        u0, returns this rank's potential energy (gfmd_solver_static.cpp:145-249)."""
+        if dump_prefix is not None:
+            raise GFMDError(4, "q-space dumps are written by the host shim, not by this binding")
+        for a in (u, f):
+            if isinstance(a, np.ndarray) and (a.dtype != np.float64 or not a.flags.c_contiguous):
+                raise GFMDError(1, "u and f must be C-contiguous float64")
+        e = ctypes.c_double()
+        self._check(self.lib.gfmd_b200_post_force_host(self.h, _ptr(u), _ptr(f), ctypes.byref(e),
+                                                       self.u0.ctypes.data))
+        return e.value
+
+    def get_u0(self):
+        return self.u0
+
+    def get_xlo_loc(self):
+        return self.xlo_loc
+
+    def get_xhi_loc(self):
+        return self.xhi_loc
+
+    def get_ylo_loc(self):
+        return self.ylo_loc
+
+    def get_yhi_loc(self):
+        return self.yhi_loc
+
+    def get_nxy_loc(self):
+        return self.nxy_loc
+
+    def memory_usage(self):
+        return self.lib.gfmd_b200_memory_usage(self.h)
+
+    # -- device-resident path -------------------------------------------------
+    def post_force_device(self, d_u=None, d_f=None):
+        self._check(self.lib.gfmd_b200_post_force_device(self.h, _ptr(d_u), _ptr(d_f)))
+
+    def gather(self, d_x, d_xeq, d_gid, d_mask, groupbit, nall, xprd, yprd, dxshift=0, dyshift=0,
+               d_u=None):
+        self._check(self.lib.gfmd_b200_gather(self.h, _ptr(d_x), _ptr(d_xeq), _ptr(d_gid),
+                                              _ptr(d_mask), groupbit, nall, xprd, yprd, dxshift,
+                                              dyshift, _ptr(d_u)))
+
+    def scatter(self, d_gid, d_mask, groupbit, nall, nlocal, d_f, d_fgrid=None):
+        self._check(self.lib.gfmd_b200_scatter(self.h, _ptr(d_fgrid), _ptr(d_gid), _ptr(d_mask),
+                                               groupbit, nall, nlocal, _ptr(d_f)))
+
+    def full_step(self, d_x, d_xeq, d_gid, d_mask, groupbit, nall, nlocal, xprd, yprd, d_f):
+        self._check(self.lib.gfmd_b200_full_step(self.h, _ptr(d_x), _ptr(d_xeq), _ptr(d_gid),
+                                                 _ptr(d_mask), groupbit, nall, nlocal, xprd, yprd,
+                                                 _ptr(d_f)))
+
+    def results(self):
+        """Synchronises; returns dict(epot, u0, fsum, natoms_gathered, natoms_scattered,
+        n_out_of_range)."""
+        e = ctypes.c_double()
+        fsum = np.zeros(3)
+        cnt = np.zeros(3, dtype=np.int32)
+        self._check(self.lib.gfmd_b200_get_results(self.h, ctypes.byref(e), self.u0.ctypes.data,
+                                                   fsum.ctypes.data, cnt.ctypes.data))
+        return dict(epot=e.value, u0=self.u0.copy(), fsum=fsum, natoms_gathered=int(cnt[0]),
+                    natoms_scattered=int(cnt[1]), n_out_of_range=int(cnt[2]))
+
+    # -- plumbing ---------------------------------------------------------------
+    def device_u(self):
+        return self.lib.gfmd_b200_device_u(self.h)
+
+    def device_f(self):
+        return self.lib.gfmd_b200_device_f(self.h)
+
+    def stream(self):
+        return self.lib.gfmd_b200_stream(self.h)
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.gfmd_b200_set_stream(self.h, cuda_stream))
+
+    def synchronize(self):
+        self._check(self.lib.gfmd_b200_synchronize(self.h))
+
+    def pin_host_buffers(self, on=True):
+        self._check(self.lib.gfmd_b200_pin_host_buffers(self.h, int(on)))
+
+    def use_graph(self, on=True):
+        self._check(self.lib.gfmd_b200_use_graph(self.h, int(on)))
+
+    def launch_count(self):
+        return self.lib.gfmd_b200_launch_count(self.h)
+
+    def profile(self, on=True):
+        self._check(self.lib.gfmd_b200_profile(self.h, int(on)))
+
+    def stage_times(self):
+        ms = np.zeros(NSTAGES)
+        cnt = np.zeros(NSTAGES, dtype=np.int64)
+        self._check(self.lib.gfmd_b200_get_stage_times(self.h, ms.ctypes.data, cnt.ctypes.data))
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(STAGE_NAMES)}
+
+    def describe(self):
+        return self.lib.gfmd_b200_describe(self.h).decode()
+
+    def phi_deviation(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._check(self.lib.gfmd_b200_phi_deviation(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if self.h:
+            self.lib.gfmd_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise GFMDError(rc, self.lib.gfmd_b200_last_error(self.h).decode())
+
+
+def gfmd_solver_factory(keyword=None, **kw):
+    """Mirror of gfmd_solver_factory (src/main/gfmd_solver.cpp:209-257): only the
+    B200 solver exists here; the name check of :244-253 is kept."""
+    name = keyword or "static/b200"
+    if name not in ("static/b200", "b200"):
+        raise GFMDError(1, "Unknown solver name encountered.")
+    return GFMDSolverB200(**kw)
