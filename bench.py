@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""GFMD force-evaluation throughput benchmark (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU solver
+
+A "step" is one elastic-force evaluation of `fix gfmd` on a synthetic sc100-type
+surface (ndof 3): gather (atoms -> grid), forward 2-D FFT, Phi(q).u(q) contraction
+with energy and gamma point, inverse FFT, scatter (grid -> atoms).
+
+  value   steps/s with atoms and grids resident in HBM (gfmd_b200_full_step)
+  e2e     steps/s through the solver-plugin boundary GFMDSolver::post_force with HOST
+          u_xy / f_xy arrays: H2D of u, the GPU step, D2H of f and of (epot, u0) inside
+          the timed region (gfmd_b200_post_force_host)
+  roofline  the fused column kernel (x-FFT, Phi.u, x-IFFT): algorithmic bytes
+          (16 d + 4 d^2) per cell (stage S3) over its CUDA-event time
+  cpu_baseline  the reference's own solver sources (oracle/_ref, FFTW replaced by
+          oracle/fft_plain.c) on this box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "user-gfmd_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "gfmd_force_eval_steps_per_sec"
+UNIT = "steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=0, help="nx = ny (default 4096)")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    n = args.grid if args.grid > 0 else 4096
+    return n, n, 3
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ clocks ---
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------- reference ---
+
+def reference_run(nx, ny, d, steps, warmup, budget_s=150.0):
+    """Times the reference's GFMDSolverStatic::post_force (its own sources, FFT3d shim
+    backed by oracle/fft_plain.c with OpenMP) on host arrays.  Returns a dict."""
+    from oracle import gfmd_oracle as O
+    from gfmd_b200 import synthetic
+    kind = "reference" if O.ref_available() else "port"
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+
+    def one(nxs, nys, nrep, nwarm):
+        phi = synthetic.phi_full(nxs, nys)
+        u = synthetic.displacement_field(nxs, nys, seed=1, nwaves=8)
+        linf = np.zeros(1)
+        if kind == "reference":
+            s = O.RefSolver(nxs, nys, d, fft_backend=1)
+            s.set_phi(phi, linf)
+            fn = lambda: s.post_force(u)
+        else:
+            fn = lambda: O.c_post_force(u, phi, linf, 1)
+        t_first = time.perf_counter()
+        fn()
+        t_first = time.perf_counter() - t_first
+        for _ in range(max(nwarm - 1, 0)):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            fn()
+        dt = (time.perf_counter() - t0) / max(nrep, 1)
+        return dt, t_first
+
+    # choose the sample: the full grid if (steps + warmup) fit the budget, else shrink
+    nxs, nys = nx, ny
+    probe_n = min(nx, 1024)
+    dt_probe, _ = one(probe_n, probe_n, 1, 1)
+    est_full = dt_probe * (nx * ny) / float(probe_n * probe_n) * 1.3
+    while est_full * (steps + warmup) * (nxs * nys) / float(nx * ny) > budget_s and nxs > 256:
+        nxs //= 2
+        nys //= 2
+    dt, _ = one(nxs, nys, steps, warmup)
+    scale = (nxs * nys) / float(nx * ny)
+    value = scale / dt
+    sample = ("GFMDSolverStatic::post_force on host u_xy/f_xy, %dx%d ndof %d, %d timed steps"
+              % (nxs, nys, d, steps))
+    if scale != 1.0:
+        sample += ("; grid reduced from %dx%d to bound the run, steps/s scaled by the cell ratio %.4g"
+                   % (nx, ny, scale))
+    return {"value": value, "unit": UNIT, "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": kind,
+            "sample": sample + "; FFT = oracle/fft_plain.c (no FFTW/MPI on this box)",
+            "ms_per_step": 1e3 / value}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, d = workload(args)
+    r = reference_run(nx, ny, d, args.steps, args.warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d" % (nx, ny, d),
+                      "step": "GFMDSolver::post_force(u_xy, f_xy) on host arrays"},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# -------------------------------------------------------------------- b200 ---
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    import gfmd_b200
+    from gfmd_b200 import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        buf = torch.zeros(gfmd_b200.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(gfmd_b200.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    nx, ny, d = workload(args)
+    s = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world, unique_id=uid)
+    s.set_grid_size(nx, ny, d)
+    # stiffness table for this rank's q columns (closed form, see synthetic.phi_columns)
+    for k0 in range(s.kylo, s.kylo + s.nky, 128):
+        nk = min(128, s.kylo + s.nky - k0)
+        s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+    s.set_linf(np.zeros(d // 3))
+
+    nx_loc, x0 = nx // world, rank * (nx // world)
+    u = synthetic.displacement_field(nx, ny, x0, nx_loc, seed=1, nwaves=8)
+    x, xeq, gid, mask = synthetic.atoms_for_slab(nx, ny, x0, nx_loc, u)
+    nat = x.shape[0]
+    dx = torch.tensor(x, device=dev)
+    dxeq = torch.tensor(xeq, device=dev)
+    dgid = torch.tensor(gid, device=dev)
+    dmask = torch.tensor(mask, device=dev)
+    dfat = torch.zeros((nat, 3), device=dev, dtype=torch.float64)
+    stream = torch.cuda.Stream(device=dev)
+    s.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+
+    def step():
+        s.full_step(dx, dxeq, dgid, dmask, 1, nat, nat, float(nx), float(ny), dfat)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        # short sustained load so that the clock samples are taken under load
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            for _ in range(10):
+                step()
+            s.synchronize()
+        barrier()
+        l0 = s.launch_count()
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        t_wall1 = time.time()
+        ms = e0.elapsed_time(e1)
+        launches = s.launch_count() - l0
+        res = s.results()
+        t_tail = time.time() + 0.4
+        while time.time() < t_tail:
+            for _ in range(10):
+                step()
+            s.synchronize()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0 - 0.7, t_wall1 + 0.5) if sampler else None
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # solver only (device-resident grids), and per-stage times with CUDA events
+    with torch.cuda.stream(stream):
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            s.post_force_device()
+        e1.record(stream)
+        barrier()
+        ms_solver = e0.elapsed_time(e1) / args.steps
+        s.profile(True)
+        for _ in range(min(args.steps, 20)):
+            step()
+        s.profile(False)
+        barrier()
+    stages = s.stage_times()
+    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in stages.items()}
+
+    # roofline of the dominant kernel (fused columns): stage S3 bytes, this rank's cells
+    peaks, peak_src = measured_peaks()
+    cells_loc = nx * ny / world
+    alg_bytes = (16 * d + 4 * d * d) * cells_loc
+    t_cols = stage_ms["cols_fused"] * 1e-3
+    achieved = alg_bytes / t_cols / 1e9 if t_cols > 0 else 0.0
+    roofline = {"kernel": "k_cols_fused (x-FFT + Phi.u + energy + x-IFFT)", "bound": "hbm",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": stage_ms["cols_fused"],
+                "solver_bytes_per_step": (80 * d + 4 * d * d) * cells_loc,
+                "solver_frac": ((80 * d + 4 * d * d) * cells_loc / (ms_solver * 1e-3) / 1e9) / peaks["hbm_gbs"]}
+
+    # end to end through the plugin boundary with pinned host buffers
+    n_e2e = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, 10))
+    hu = torch.tensor(u.reshape(d, nx_loc * ny)).pin_memory()
+    hf = torch.empty_like(hu).pin_memory()
+    for _ in range(2):
+        s.post_force(hu, hf)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        s.post_force(hu, hf)
+    barrier()
+    dt_e2e = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t.item())
+    grid_bytes = d * nx_loc * ny * 8
+    e2e = {"value": 1.0 / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": grid_bytes,
+           "d2h_bytes_per_step": grid_bytes + 8 * (d + 1), "steps": n_e2e,
+           "call": "gfmd_b200_post_force_host (GFMDSolver::post_force boundary), pinned host u_xy/f_xy"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = reference_run(nx, ny, d, 3, 1, budget_s=25.0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d, 1 atom/cell" % (nx, ny, d),
+                          "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",
+                          "decomposition": "x-slabs over %d GPU(s), NCCL all-to-all transposes" % world,
+                          "l2": "inputs larger than L2 (%.0f MB of atoms+grids per step)" %
+                                ((nat * (48 + 16 + 24) + 2 * grid_bytes) / 1e6),
+                          "kernels": s.describe()},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+               "cpu_baseline": cpu,
+               "solver_only": {"value": 1e3 / ms_solver, "unit": UNIT, "ms_per_step": ms_solver},
+               "stage_ms": stage_ms, "epot": res["epot"]}
+        print(json.dumps(out))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

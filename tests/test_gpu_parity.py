@@ -115,13 +115,16 @@ def test_linearity_and_energy_identity_4096(B):
     u1 = torch.rand((d, n), generator=gen, device="cuda", dtype=torch.float64) - 0.5
     u2 = torch.rand((d, n), generator=gen, device="cuda", dtype=torch.float64) - 0.5
     f1, f2, f3 = (torch.empty_like(u1) for _ in range(3))
-    s.post_force_device(u1, f1)
-    e1 = s.results()["epot"]
-    s.post_force_device(u2, f2)
-    e2 = s.results()["epot"]
+
+    def run(u, f):
+        torch.cuda.synchronize()       # inputs were produced on torch's stream
+        s.post_force_device(u, f)
+        return s.results()["epot"]     # synchronises the library's stream
+
+    e1 = run(u1, f1)
+    e2 = run(u2, f2)
     u3 = 2.0 * u1 - 3.0 * u2
-    s.post_force_device(u3, f3)
-    e3 = s.results()["epot"]
+    e3 = run(u3, f3)
     scale = f3.abs().max().item()
     assert (f3 - (2.0 * f1 - 3.0 * f2)).abs().max().item() < TOL * scale
     for u, f, e in ((u1, f1, e1), (u2, f2, e2), (u3, f3, e3)):
@@ -131,14 +134,15 @@ def test_linearity_and_energy_identity_4096(B):
     ut = torch.zeros_like(u1)
     ut[0] = 0.25
     ut[2] = -1.5
-    s.post_force_device(ut, f1)
+    run(ut, f1)
     r = s.results()
     assert abs(r["u0"][0] - 0.25 * n) < 1e-9 * n and abs(r["u0"][2] + 1.5 * n) < 1e-9 * n
     assert (f1[0] + 0.05 * 0.25).abs().max().item() < 1e-12
     assert (f1[2] - 0.05 * 1.5).abs().max().item() < 1e-12
     assert f1[1].abs().max().item() < 1e-12
-    s.post_force_device(torch.zeros_like(u1), f1)
-    assert f1.abs().max().item() == 0.0 and s.results()["epot"] == 0.0
+    uz = torch.zeros_like(u1)
+    ez = run(uz, f1)
+    assert f1.abs().max().item() == 0.0 and ez == 0.0
     s.close()
 
 
@@ -170,6 +174,7 @@ def test_gather_scatter_against_oracle(B, nx, ny, nu, shift, oracle_libs):
     dx, dxeq = torch.tensor(x, device="cuda"), torch.tensor(xeq, device="cuda")
     dgid, dmask = torch.tensor(gid, device="cuda"), torch.tensor(mask, device="cuda")
     du = torch.zeros((d, nx * ny), device="cuda", dtype=torch.float64)
+    torch.cuda.synchronize()           # the library runs on its own stream
     s.gather(dx, dxeq, dgid, dmask, 2, n, float(nx), float(ny), shift[0], shift[1], du)
     r = s.results()
     assert r["natoms_gathered"] == n_ref and r["n_out_of_range"] == 0
@@ -208,9 +213,10 @@ def test_full_step_device_resident(B, oracle_libs):
         s.use_graph(graph)
         for _ in range(2):
             df = torch.zeros((n, 3), device="cuda", dtype=torch.float64)
-            s.full_step(torch.tensor(x, device="cuda"), torch.tensor(xeq, device="cuda"),
-                        torch.tensor(gid, device="cuda"), torch.tensor(mask, device="cuda"), 2, n, n,
-                        float(nx), float(ny), df)
+            dx, dxeq = torch.tensor(x, device="cuda"), torch.tensor(xeq, device="cuda")
+            dgid, dmask = torch.tensor(gid, device="cuda"), torch.tensor(mask, device="cuda")
+            torch.cuda.synchronize()   # the library runs on its own stream
+            s.full_step(dx, dxeq, dgid, dmask, 2, n, n, float(nx), float(ny), df)
             r = s.results()
             assert rel_err(df.cpu().numpy(), fa_ref) < TOL
             assert abs(r["epot"] - e_ref) <= TOL * abs(e_ref)

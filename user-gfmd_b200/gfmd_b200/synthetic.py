@@ -1,0 +1,74 @@
+"""Deterministic synthetic inputs for benchmarks and size-independent tests
+(configuration C4): a closed-form simple-cubic-like surface
+stiffness table and a displacement field made of random-phase plane waves."""
+import numpy as np
+
+
+def phi_columns(nx, ny, ky_first, nky):
+    """Closed-form 3x3 Hermitian stiffness, Phi(-q) = conj Phi(q), positive definite,
+    UNNORMALISED, for kx in [0, nx), ky in [ky_first, ky_first + nky) -- in the layout of
+    fill_phi_buffer(ndof, nx, 0, nx-1, ny, ky_first, ...): [nx, nky, 3, 3] complex128.
+
+    Nearest/next-nearest-neighbour simple-cubic surface layer (the U0 block of the
+    reference's sc100 kernel has this structure, src/stiffness_kernels/sc100_stiffness.cpp);
+    used where timing, not elasticity, is the point: the solver's work does not depend
+    on the table's values."""
+    qx = 2.0 * np.pi * np.fft.fftfreq(nx)
+    qy = 2.0 * np.pi * np.arange(ky_first, ky_first + nky) / ny
+    QX, QY = np.meshgrid(qx, qy, indexing="ij")
+    cx, cy, sx, sy = np.cos(QX), np.cos(QY), np.sin(QX), np.sin(QY)
+    P = np.zeros((nx, nky, 3, 3), dtype=np.complex128)
+    P[..., 0, 0] = 4.0 - 2.0 * cx * (1.0 + cy) + 0.02
+    P[..., 1, 1] = 4.0 - 2.0 * cy * (1.0 + cx) + 0.02
+    P[..., 2, 2] = 3.0 - cx - cy + 0.02
+    P[..., 0, 1] = 2.0 * sx * sy
+    P[..., 1, 0] = P[..., 0, 1]
+    P[..., 0, 2] = 1j * sx
+    P[..., 2, 0] = -1j * sx
+    P[..., 1, 2] = 1j * sy
+    P[..., 2, 1] = -1j * sy
+    return P
+
+
+def phi_full(nx, ny):
+    """Same table for the whole grid in the reference layout [nx*ny, 3, 3], normalised
+    by 1/(nx*ny) like fill_phi_buffer(normalize=true)."""
+    P = phi_columns(nx, ny, 0, ny)
+    return (P / (nx * ny)).reshape(nx * ny, 3, 3)
+
+
+def displacement_field(nx, ny, x0=0, nx_loc=None, seed=1, nwaves=64, amp=1e-3):
+    """Sum of `nwaves` random-phase plane waves of amplitude `amp` plus uniform noise of
+    the same size, on rows [x0, x0 + nx_loc): returns [3, nx_loc, ny] float64.  The wave
+    parameters depend on the seed only, so slabs of different ranks fit together."""
+    nx_loc = nx if nx_loc is None else nx_loc
+    rng = np.random.default_rng(seed)
+    kx = rng.integers(0, nx, size=(nwaves, 3))
+    ky = rng.integers(0, ny, size=(nwaves, 3))
+    ph = rng.uniform(0, 2 * np.pi, size=(nwaves, 3))
+    ix = np.arange(x0, x0 + nx_loc)[:, None]
+    iy = np.arange(ny)[None, :]
+    u = np.zeros((3, nx_loc, ny))
+    for c in range(3):
+        for w in range(nwaves):
+            u[c] += np.cos(2 * np.pi * (kx[w, c] * ix / nx + ky[w, c] * iy / ny) + ph[w, c])
+    u *= amp
+    noise = np.random.default_rng(seed + 1000 + x0).uniform(-amp, amp, size=u.shape)
+    return u + noise
+
+
+def atoms_for_slab(nx, ny, x0, nx_loc, u):
+    """One atom per cell at xeq = lattice site + 0.5, displaced by u: returns x, xeq
+    [n, 3] float64, gid [n, 3] int32 (ix, iy, 0), mask [n] int32 (group bit 1)."""
+    ix, iy = np.meshgrid(np.arange(x0, x0 + nx_loc), np.arange(ny), indexing="ij")
+    n = nx_loc * ny
+    gid = np.zeros((n, 3), dtype=np.int32)
+    gid[:, 0] = ix.ravel()
+    gid[:, 1] = iy.ravel()
+    xeq = np.empty((n, 3))
+    xeq[:, 0] = gid[:, 0] + 0.5
+    xeq[:, 1] = gid[:, 1] + 0.5
+    xeq[:, 2] = 0.5
+    x = xeq + np.moveaxis(u.reshape(3, n), 0, 1)
+    mask = np.ones(n, dtype=np.int32)
+    return x, xeq, gid, mask
