@@ -60,6 +60,9 @@ SIZES = [
     (1, 1, 3), (1, 2, 3), (2, 1, 3), (3, 5, 3), (7, 9, 6), (16, 16, 3), (10, 10, 6),
     (37, 64, 3), (64, 37, 6), (74, 22, 3), (30, 42, 9), (35, 25, 12), (128, 96, 3),
     (11, 13, 15), (256, 512, 3), (243, 250, 3), (1024, 64, 3), (64, 2048, 6),
+    # specialised power-of-two kernels: fused columns (nx 2048/4096, ndof 3), rows (ny 2048..16384)
+    (2048, 64, 3), (4096, 32, 3), (64, 2048, 3), (32, 4096, 3), (16, 8192, 3), (8, 16384, 3),
+    (2048, 2048, 3),
 ]
 
 
@@ -144,6 +147,44 @@ def test_linearity_and_energy_identity_4096(B):
     ez = run(uz, f1)
     assert f1.abs().max().item() == 0.0 and ez == 0.0
     s.close()
+
+
+def test_specialised_kernels_match_generic_4096(B):
+    """At the benchmark size the specialised power-of-two kernels and the generic
+    kernels (pinned against the oracle on the smaller grids above) must agree."""
+    import os
+    import torch
+    from gfmd_b200 import synthetic
+    nx = ny = 4096
+    d = 3
+    out = {}
+    for mode in ("fast", "generic"):
+        if mode == "generic":
+            os.environ["GFMD_B200_NO_FAST"] = "1"
+        try:
+            s = B.GFMDSolverB200()
+            s.set_grid_size(nx, ny, d)
+        finally:
+            os.environ.pop("GFMD_B200_NO_FAST", None)
+        assert ("[fast]" in s.describe()) == (mode == "fast"), s.describe()
+        for k0 in range(0, s.nky, 256):
+            nk = min(256, s.nky - k0)
+            s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+        s.set_linf(np.array([0.125]))
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        u = torch.rand((d, nx * ny), generator=gen, device="cuda", dtype=torch.float64) - 0.5
+        f = torch.empty_like(u)
+        torch.cuda.synchronize()
+        s.post_force_device(u, f)
+        r = s.results()
+        out[mode] = (f.cpu(), r["epot"], r["u0"])
+        s.close()
+    ff, ef, u0f = out["fast"]
+    fg, eg, u0g = out["generic"]
+    scale = fg.abs().max().item()
+    assert (ff - fg).abs().max().item() < TOL * scale
+    assert abs(ef - eg) <= TOL * abs(eg)
+    assert np.abs(u0f - u0g).max() <= TOL * np.abs(u0g).max()
 
 
 def make_atoms(nx, ny, nu, rng, nghost_frac=0.0):

@@ -235,6 +235,7 @@ struct gfmd_b200 {
   int cols_ld = 0, cols_T = 64;
   size_t cols_smem = 0;
   int fast_rows = 0, fast_cols = 0;   // specialised kernels selected
+  int num_sms = 148;
 
   bool phi_set = false;
   std::vector<char> phi_cols_set;
@@ -432,6 +433,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
     return bail(GFMD_B200_ECUDA);
   }
   h->own_stream = true;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   if ((rc = plan(h))) return bail(rc);
 
   const size_t nxy = (size_t) g.nx_loc * g.ny;
@@ -444,7 +446,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess && g.P > 1) ce = dmalloc(h, &h->d_stage2, nstage);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_phi, nphi);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_linf, (size_t) GFMD_B200_MAX_NDOF);
-  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_epart, (size_t) g.kyb + 1);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_epart, ((size_t) g.kyb + 1) * kColsNW);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_res, (size_t) 1);
   if (ce == cudaSuccess) ce = cudaMallocHost((void **) &h->h_res, sizeof(StepResults));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_u, 0, sizeof(double) * nxy * g.d);
@@ -452,7 +454,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess) ce = cudaMemset(h->d_stage, 0, sizeof(double2) * nstage);
   if (ce == cudaSuccess && g.P > 1) ce = cudaMemset(h->d_stage2, 0, sizeof(double2) * nstage);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_linf, 0, sizeof(double) * GFMD_B200_MAX_NDOF);
-  if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1) * kColsNW);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_res, 0, sizeof(StepResults));
   if (ce != cudaSuccess) {
     h->err = std::string("device allocation failed: ") + cudaGetErrorString(ce);
@@ -535,7 +537,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   if (g.nky_loc > 0) {
     if (h->fast_cols) {
       int rc = fast_cols_fused(h->fast_cols, B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart,
-                               h->d_res, h->stream, &h->launches);
+                               h->d_res, h->num_sms, h->stream, &h->launches);
       if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
     } else {
 #define LAUNCH_COLS(DT)                                                                          \
@@ -552,7 +554,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
       h->launches++;
     }
   }
-  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc, h->d_res);
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc * (h->fast_cols ? kColsNW : 1), h->d_res);
   h->launches++;
   stage_mark(h, 4);
   if (g.P > 1) {
@@ -809,6 +811,7 @@ int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised,
   const int d = g.d, nx = g.nx, ny = g.ny;
   const size_t dsq = (size_t) d * d;
   const double s = already_normalised ? 1.0 : 1.0 / ((double) nx * (double) ny);
+  const int lognx = ilog2_rt(nx);
   double amax = 0.0, hdev = 0.0, cdev = 0.0;
   CU(h, cudaStreamSynchronize(h->stream));
   // chunk over local ky to bound the host staging buffer
@@ -823,7 +826,8 @@ int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised,
         const int kxn = (nx - kx) % nx;
         const double *M = phi + 2 * dsq * ((size_t) kx * ny + ky);
         const double *Mn = phi + 2 * dsq * ((size_t) kxn * ny + kyn);
-        pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + kx, (size_t) nx, amax, hdev,
+        const int pos = h->fast_cols ? p2_freq_to_pos(lognx, kx) : kx;
+        pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + pos, (size_t) nx, amax, hdev,
                        cdev);
       }
     }
@@ -853,6 +857,7 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
   const int d = g.d, nx = g.nx;
   const size_t dsq = (size_t) d * d;
   const double s = already_normalised ? 1.0 : 1.0 / ((double) nx * (double) g.ny);
+  const int lognx = ilog2_rt(nx);
   double amax = 0.0, hdev = 0.0, cdev = 0.0;
   CU(h, cudaStreamSynchronize(h->stream));
   const int chunk = 64;
@@ -862,7 +867,8 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
     for (int kl = 0; kl < nk; ++kl)
       for (int kx = 0; kx < nx; ++kx) {
         const double *M = phi + 2 * dsq * ((size_t) kx * nky + k0 + kl);
-        pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + kx, (size_t) nx, amax, hdev,
+        const int pos = h->fast_cols ? p2_freq_to_pos(lognx, kx) : kx;
+        pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + pos, (size_t) nx, amax, hdev,
                        cdev);
       }
     CU(h, cudaMemcpy(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),

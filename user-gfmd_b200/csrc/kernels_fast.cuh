@@ -1,36 +1,414 @@
-// Specialised kernels for large power-of-two grids (selected by fast_plan when
-// the grid qualifies; otherwise the generic kernels of kernels_generic.cuh run).
+// Specialised kernels for large power-of-two grids, selected by fast_plan():
+//
+//   k_rows_fwd_p2   ny in {2048 .. 16384}: real rows -> half spectrum, transposed store
+//   k_cols_fused_p2 nx in {2048, 4096}, ndof 3: x-FFT + Phi(q).u(q) + energy +
+//                   gamma point + x-IFFT, one column set resident in shared memory,
+//                   the contraction done in registers between the last forward and the
+//                   first backward pass
+//   k_rows_inv_p2   half spectrum -> real rows
+//
+// Same data layout and same role as the generic kernels (kernels_generic.cuh); the
+// column spectrum is kept digit-reversed (see fft_pow2.cuh) and the Phi planes are
+// stored in that order by set_phi when this path is active.
 #pragma once
 
 #include "fft_engine.cuh"
+#include "fft_pow2.cuh"
 #include "kernels_generic.cuh"
 
 namespace gfmd {
 
+constexpr int kColsNW = 8;      // warps of the fused column kernel (epart has kColsNW slots per column)
+
+// ------------------------------------------------------------------ columns ---
+
+template <int D, int N, int T>
+__global__ void __launch_bounds__(T, 1)
+k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, int lnxl,
+                const double2 *__restrict__ tw, const double *__restrict__ phi,
+                const double *__restrict__ linf, double *__restrict__ epart, StepResults *res)
+{
+  constexpr int NW = T / 32;
+  static_assert(NW == kColsNW, "epart layout");
+  extern __shared__ double2 sm[];
+  double2 *tws = sm + D * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  p2_fill_tws<N>(tws, tw);
+  __syncthreads();
+
+  for (int kl = blockIdx.x; kl < g.nky_loc; kl += gridDim.x) {
+    const int ky = g.ky0 + kl;
+    const int xmask = (1 << lnxl) - 1;
+    auto addr = [&](int dof, int x) -> size_t {
+      const int p = x >> lnxl;
+      return ((((size_t) (p * D + dof)) * g.kyb + kl) << lnxl) + (x & xmask);
+    };
+
+    // ---- group A forward: pass 0 straight from global memory, all dofs in flight
+    {
+      using G = GA<N, 0, NW>;
+      constexpr int R = 1 << G::lr;
+#pragma unroll 1
+      for (int m = lane >> 2; m < G::M; m += 8) {
+        const int base = G::base(m, lane, warp);
+        double2 v[D][R];
+#pragma unroll
+        for (int dof = 0; dof < D; ++dof)
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[dof][r] = sin[addr(dof, base + (r << G::ls))];
+#pragma unroll
+        for (int dof = 0; dof < D; ++dof) {
+          Butterfly<R, -1>::run(v[dof]);
+          p2_twiddle<N, 0, -1>(v[dof], base, tw, tws);
+#pragma unroll
+          for (int r = 0; r < R; ++r) sm[dof * N + swz(base + (r << G::ls))] = v[dof][r];
+        }
+      }
+    }
+#pragma unroll
+    for (int dof = 0; dof < D; ++dof) p2_groupA_rest<N, NW, -1>(sm + dof * N, tw, tws, lane, warp);
+    __syncthreads();
+
+    // ---- group B forward, contraction in registers, group B backward
+#pragma unroll
+    for (int dof = 0; dof < D; ++dof)
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first_fwd<N>(sm + dof * N, tws, idx);
+    __syncwarp();
+
+    const double wgt = (ky == 0 || (2 * ky == g.ny)) ? 1.0 : 2.0;
+    const double *ph = phi + (size_t) kl * D * D * N;
+    double e = 0.0;
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < N / 8; idx += T) {
+      double2 u[D][8];
+#pragma unroll
+      for (int dof = 0; dof < D; ++dof) p2_last_fwd_load(sm + dof * N, idx, u[dof]);
+      const int pos = (idx >> 3) * 64 + 8 * (idx & 7);
+#pragma unroll
+      for (int rp = 0; rp < 4; ++rp) {
+        double2 pl[D * D];
+#pragma unroll
+        for (int c = 0; c < D * D; ++c)
+          pl[c] = __ldg(reinterpret_cast<const double2 *>(ph + (size_t) c * N + pos + 2 * rp));
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int r = 2 * rp + s;
+          double2 uv[D], F[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) uv[i] = u[i][r];
+          phi_matvec<D>(uv, F, [&](int c) { return s == 0 ? pl[c].x : pl[c].y; });
+          double eq = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            eq = fma(F[i].x, uv[i].x, fma(F[i].y, uv[i].y, eq));
+            F[i] = make_double2(-F[i].x, -F[i].y);
+          }
+          e = fma(wgt, eq, e);
+          if (ky == 0 && pos + r == 0) {            // gamma point: kx = 0 sits at position 0
+            double eg = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) res->u0[i] = uv[i].x;
+#pragma unroll
+            for (int a = 0; a < D / 3; ++a) {
+              eg -= 2.0 * linf[a] * uv[3 * a + 2].x;
+              F[3 * a + 2].x += linf[a];
+            }
+            res->egamma = eg;
+          }
+#pragma unroll
+          for (int i = 0; i < D; ++i) u[i][r] = F[i];
+        }
+      }
+#pragma unroll
+      for (int dof = 0; dof < D; ++dof) p2_last_inv_store(sm + dof * N, idx, u[dof]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int dof = 0; dof < D; ++dof)
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first_inv<N>(sm + dof * N, tws, idx);
+
+    // energy partial of this warp (fixed order -> deterministic)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    if (lane == 0) epart[(size_t) kl * NW + warp] = e;
+    __syncthreads();
+
+    // ---- group A backward, last pass straight to global memory
+#pragma unroll
+    for (int dof = 0; dof < D; ++dof) p2_groupA_rest<N, NW, +1>(sm + dof * N, tw, tws, lane, warp);
+#pragma unroll
+    for (int dof = 0; dof < D; ++dof)
+      p2_pass0_inv<N, NW>(sm + dof * N, tw, tws, lane, warp,
+                          [&](int pos, double2 v) { sout[addr(dof, pos)] = v; });
+    // no barrier: the next column's group A touches only what this warp owns
+  }
+}
+
+// --------------------------------------------------------------------- rows ---
+
+// RB rows (same dof) of ny = 2 NR reals per CTA.
+template <int NR, int RB, int T>
+__global__ void __launch_bounds__(T)
+k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
+              const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny)
+{
+  constexpr int NW = T / 32;
+  constexpr int LOG = P2<NR>::LOG;
+  extern __shared__ double2 sm[];
+  double2 *tws = sm + RB * NR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = g.nx_loc / RB;
+  const int dof = blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x - dof * nblk) * RB;
+  const int ny = 2 * NR;
+  p2_fill_tws<NR>(tws, tw);
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * ny);
+    p2_pass0_fwd<NR, NW>(sm + r * NR, tw, tws, lane, warp, [&](int pos) { return src[pos]; });
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) p2_groupA_rest<NR, NW, -1>(sm + r * NR, tw, tws, lane, warp);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_fwd<NR>(sm + r * NR, tws, idx);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
+      double2 v[8];
+      p2_last_fwd_load(sm + r * NR, idx, v);
+      const int base = (idx >> 3) * 64 + 8 * (idx & 7);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sm[r * NR + swz(base + q)] = v[q];
+    }
+  __syncthreads();
+
+  // un-mix the packed transform and store transposed: X[ky] = A - i w B
+  constexpr int h = NR;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < RB * (h + 1); i += T) {
+    const int r = i % RB, ky = i / RB;
+    const int ka = ky == h ? 0 : ky;
+    const int kb = ky == 0 ? 0 : h - ky;
+    const double2 zk = sm[r * NR + swz(p2_freq_to_pos(LOG, ka))];
+    const double2 zc = cconj(sm[r * NR + swz(p2_freq_to_pos(LOG, kb))]);
+    const double2 A = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
+    const double2 B = make_double2(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
+    const double2 t = cmul(__ldg(tw_ny + ky), B);
+    stage[stage_index(g, ky, dof, ix0 + r)] = make_double2(A.x + t.y, A.y - t.x);
+  }
+}
+
+template <int NR, int RB, int T>
+__global__ void __launch_bounds__(T)
+k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
+              const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny)
+{
+  constexpr int NW = T / 32;
+  constexpr int LOG = P2<NR>::LOG;
+  extern __shared__ double2 sm[];
+  double2 *tws = sm + RB * NR;
+  double2 *yh = tws + P2<NR>::TWS;          // Y[h] of each row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = g.nx_loc / RB;
+  const int dof = blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x - dof * nblk) * RB;
+  const int ny = 2 * NR;
+  constexpr int h = NR;
+  p2_fill_tws<NR>(tws, tw);
+
+#pragma unroll 1
+  for (int i = threadIdx.x; i < RB * (h + 1); i += T) {
+    const int r = i % RB, ky = i / RB;
+    const double2 y = stage[stage_index(g, ky, dof, ix0 + r)];
+    if (ky < h) sm[r * NR + swz(p2_freq_to_pos(LOG, ky))] = y;
+    else yh[r] = y;
+  }
+  __syncthreads();
+
+  // Z'[k] = (Y[k] + conj Y[h-k]) + i e^{+2 pi i k/ny} (Y[k] - conj Y[h-k]), in place pairwise
+  constexpr int np = h / 2 + 1;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < RB * np; i += T) {
+    const int r = i % RB, k = i / RB;
+    const int k2 = h - k;
+    const int pk = r * NR + swz(p2_freq_to_pos(LOG, k));
+    const int p2i = r * NR + swz(p2_freq_to_pos(LOG, k2 & (h - 1)));
+    const double2 yk = sm[pk];
+    const double2 y2 = k == 0 ? yh[r] : sm[p2i];
+    {
+      const double2 c2 = cconj(y2);
+      const double2 S = cadd(yk, c2), Dv = csub(yk, c2);
+      const double2 t = cmulc(Dv, __ldg(tw_ny + k));
+      sm[pk] = make_double2(S.x - t.y, S.y + t.x);
+    }
+    if (k2 != k && k2 < h) {
+      const double2 ck = cconj(yk);
+      const double2 S = cadd(y2, ck), Dv = csub(y2, ck);
+      const double2 t = cmulc(Dv, __ldg(tw_ny + k2));
+      sm[p2i] = make_double2(S.x - t.y, S.y + t.x);
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
+      const int base = (idx >> 3) * 64 + 8 * (idx & 7);
+      double2 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = sm[r * NR + swz(base + q)];
+      p2_last_inv_store(sm + r * NR, idx, v);
+    }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_inv<NR>(sm + r * NR, tws, idx);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RB; ++r) p2_groupA_rest<NR, NW, +1>(sm + r * NR, tw, tws, lane, warp);
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * ny);
+    p2_pass0_inv<NR, NW>(sm + r * NR, tw, tws, lane, warp, [&](int pos, double2 v) { dst[pos] = v; });
+  }
+}
+
+// ---------------------------------------------------------------- selection ---
+
+struct FastRowsCfg { int nr, rb, t; };
+
+inline bool fast_rows_cfg(int ny, FastRowsCfg &c)
+{
+  switch (ny) {
+    case 2048: c = {1024, 4, 128}; return true;
+    case 4096: c = {2048, 2, 256}; return true;
+    case 8192: c = {4096, 2, 256}; return true;
+    case 16384: c = {8192, 1, 512}; return true;
+    default: return false;
+  }
+}
+
+inline size_t fast_rows_smem(const FastRowsCfg &c)
+{
+  return sizeof(double2) * ((size_t) c.rb * c.nr + 504 + c.rb);
+}
+
+inline size_t fast_cols_smem(int d, int nx) { return sizeof(double2) * ((size_t) d * nx + 504); }
+
+inline int ilog2_rt(int n)
+{
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return l;
+}
+
+// returns 0 on success; fast_rows / fast_cols = 0 (generic kernels) or the variant id
 inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols)
 {
-  (void) g;
   fast_rows = 0;
   fast_cols = 0;
+  if (getenv("GFMD_B200_NO_FAST")) return 0;
+  FastRowsCfg rc;
+  if (fast_rows_cfg(g.ny, rc) && g.nx_loc % rc.rb == 0) {
+    fast_rows = g.ny;
+    cudaError_t e = cudaSuccess;
+#define ROWS_ATTR(NR, RB, T)                                                                              \
+  e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                           (int) fast_rows_smem(rc));                                                     \
+  if (e == cudaSuccess)                                                                                   \
+    e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                             (int) fast_rows_smem(rc));
+    switch (g.ny) {
+      case 2048: ROWS_ATTR(1024, 4, 128) break;
+      case 4096: ROWS_ATTR(2048, 2, 256) break;
+      case 8192: ROWS_ATTR(4096, 2, 256) break;
+      case 16384: ROWS_ATTR(8192, 1, 512) break;
+    }
+#undef ROWS_ATTR
+    if (e != cudaSuccess) return 1;
+  }
+  const bool p2ranks = (g.P & (g.P - 1)) == 0;
+  if (g.d == 3 && p2ranks && (g.nx == 2048 || g.nx == 4096) && g.nx_loc >= 64) {
+    fast_cols = g.nx;
+    cudaError_t e = cudaSuccess;
+#define COLS_ATTR(N)                                                                                      \
+  e = cudaFuncSetAttribute(k_cols_fused_p2<3, N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                           (int) fast_cols_smem(3, N));
+    switch (g.nx) {
+      case 2048: COLS_ATTR(2048) break;
+      case 4096: COLS_ATTR(4096) break;
+    }
+#undef COLS_ATTR
+    if (e != cudaSuccess) return 1;
+  }
   return 0;
 }
 
-inline int fast_rows_fwd(int, const double *, double2 *, const GridDesc &, const double2 *, const FftDesc &,
-                         cudaStream_t, long long *)
+inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const GridDesc &g, const double2 *tw_ny,
+                         const FftDesc &fd, cudaStream_t s, long long *launches)
 {
-  return 1;
+  FastRowsCfg rc;
+  if (!fast_rows_cfg(variant, rc)) return 1;
+  const int grid = g.d * (g.nx_loc / rc.rb);
+  const size_t smem = fast_rows_smem(rc);
+  switch (variant) {
+    case 2048: k_rows_fwd_p2<1024, 4, 128><<<grid, 128, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    case 4096: k_rows_fwd_p2<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    case 8192: k_rows_fwd_p2<4096, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    case 16384: k_rows_fwd_p2<8192, 1, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    default: return 1;
+  }
+  ++*launches;
+  return 0;
 }
 
-inline int fast_rows_inv(int, const double2 *, double *, const GridDesc &, const double2 *, const FftDesc &,
-                         cudaStream_t, long long *)
+inline int fast_rows_inv(int variant, const double2 *stage, double *f, const GridDesc &g, const double2 *tw_ny,
+                         const FftDesc &fd, cudaStream_t s, long long *launches)
 {
-  return 1;
+  FastRowsCfg rc;
+  if (!fast_rows_cfg(variant, rc)) return 1;
+  const int grid = g.d * (g.nx_loc / rc.rb);
+  const size_t smem = fast_rows_smem(rc);
+  switch (variant) {
+    case 2048: k_rows_inv_p2<1024, 4, 128><<<grid, 128, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    case 4096: k_rows_inv_p2<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    case 8192: k_rows_inv_p2<4096, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    case 16384: k_rows_inv_p2<8192, 1, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    default: return 1;
+  }
+  ++*launches;
+  return 0;
 }
 
-inline int fast_cols_fused(int, const double2 *, double2 *, const GridDesc &, const FftDesc &, const double *,
-                           const double *, double *, StepResults *, cudaStream_t, long long *)
+inline int fast_cols_fused(int variant, const double2 *sin, double2 *sout, const GridDesc &g, const FftDesc &fd,
+                           const double *phi, const double *linf, double *epart, StepResults *res,
+                           int num_sms, cudaStream_t s, long long *launches)
 {
-  return 1;
+  const int grid = g.nky_loc < num_sms ? g.nky_loc : num_sms;
+  const int lnxl = ilog2_rt(g.nx_loc);
+  const size_t smem = fast_cols_smem(3, variant);
+  switch (variant) {
+    case 2048:
+      k_cols_fused_p2<3, 2048, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, fd.core.tw, phi, linf, epart, res);
+      break;
+    case 4096:
+      k_cols_fused_p2<3, 4096, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, fd.core.tw, phi, linf, epart, res);
+      break;
+    default: return 1;
+  }
+  ++*launches;
+  return 0;
 }
 
 }  // namespace gfmd
