@@ -13,10 +13,16 @@
 // stored in the same permuted order (host: p2_freq_to_pos), so it never needs to
 // be un-permuted.
 //
-// Shared-memory addressing is XOR-swizzled (swz): the 16-byte column of an
-// element is XORed with a rotation of the XOR of all its higher 3-bit digits,
-// which makes every access pattern used here (8 lanes varying one digit, or
-// 4 consecutive elements x 2 values of a digit bit) bank-conflict free.
+// All pass functions work on A arrays at once (the ndof columns of one q-column,
+// or the rows of one row tile): the twiddles are fetched once per item and the
+// loads of all arrays are issued before the first butterfly.
+//
+// Shared-memory addressing is XOR-swizzled: the 16-byte column of an element is
+// XORed with a rotation of the XOR of all its higher 3-bit digits, which makes
+// every access pattern used here (8 lanes varying one digit, or 4 consecutive
+// elements x 2 values of a digit bit) bank-conflict free.  For an item with base
+// position `base` the key is computed once (swz_key); element r of the butterfly
+// then sits at (base ^ key ^ rot2(r)) + (r << stride).
 #pragma once
 
 #include "fft_engine.cuh"
@@ -39,6 +45,14 @@ template <int N> struct P2 {
   static_assert(NP >= 4 && NP <= 5, "fast path covers 1024 <= N <= 8192");
 };
 
+__host__ __device__ constexpr int rot2c(int x) { return ((x << 2) | (x >> 1)) & 7; }
+
+// 3-bit swizzle key of a position whose low 3 bits do not matter
+__device__ __forceinline__ int swz_key(int pos)
+{
+  const int x = ((pos >> 3) ^ (pos >> 6) ^ (pos >> 9) ^ (pos >> 12)) & 7;
+  return ((x << 2) | (x >> 1)) & 7;
+}
 __host__ __device__ __forceinline__ int swz(int pos)
 {
   int x = ((pos >> 3) ^ (pos >> 6) ^ (pos >> 9) ^ (pos >> 12)) & 7;
@@ -116,31 +130,36 @@ template <int N, int P, int NW> struct GA {
   }
 };
 
-// twiddles of a forward pass: v[q] *= w^(q * n_lo); backward: conj, applied to inputs
-template <int N, int P, int DIR>
-__device__ __forceinline__ void p2_twiddle(double2 *v, int n_lo, const double2 *__restrict__ tw, const double2 *tws)
+// twiddles w[q] = w_L^(q n_lo), q = 1..R-1, of pass P (forward sign)
+template <int N, int P>
+__device__ __forceinline__ void p2_get_tw(double2 *w, int n_lo, const double2 *__restrict__ tw, const double2 *tws)
 {
   constexpr int lr = P2<N>::lr(P), ls = P2<N>::ls(P), R = 1 << lr;
-  if (ls == 0) return;
   if (ls == 6) {
 #pragma unroll
-    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], twid<DIR>(tws[P2<N>::TW64 + (q - 1) * 64 + n_lo]));
+    for (int q = 1; q < R; ++q) w[q] = tws[P2<N>::TW64 + (q - 1) * 64 + n_lo];
   } else if (ls == 3) {
 #pragma unroll
-    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], twid<DIR>(tws[P2<N>::TW8 + (q - 1) * 8 + n_lo]));
+    for (int q = 1; q < R; ++q) w[q] = tws[P2<N>::TW8 + (q - 1) * 8 + n_lo];
   } else {
     // long strides: one table load, powers in registers
-    double2 w[8];
     tw_powers<R>(__ldg(tw + (n_lo << (P2<N>::LOG - ls - lr))), w);
-#pragma unroll
-    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], twid<DIR>(w[q]));
   }
 }
 
-// One in-place group-A pass over one array in shared memory (forward: butterfly
-// then twiddle; backward: conj twiddle then inverse butterfly).
-template <int N, int P, int NW, int DIR>
-__device__ __forceinline__ void p2_groupA_pass(double2 *a, const double2 *__restrict__ tw, const double2 *tws,
+template <int R, int DIR> __device__ __forceinline__ void p2_apply_tw(double2 *v, const double2 *w)
+{
+#pragma unroll
+  for (int q = 1; q < R; ++q) v[q] = DIR < 0 ? cmul(v[q], w[q]) : cmulc(v[q], w[q]);
+}
+
+// element r of an item: physical index inside one array
+template <int LS> __device__ __forceinline__ int p2_elem(int sb, int r) { return (sb ^ rot2c(r)) + (r << LS); }
+
+// One in-place group-A pass over A arrays (array a at sm + a*N).  Forward: butterfly
+// then twiddle; backward: conj twiddle then inverse butterfly.
+template <int N, int P, int NW, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupA_pass(double2 *sm, const double2 *__restrict__ tw, const double2 *tws,
                                                int lane, int warp)
 {
   using G = GA<N, P, NW>;
@@ -148,21 +167,28 @@ __device__ __forceinline__ void p2_groupA_pass(double2 *a, const double2 *__rest
 #pragma unroll 1
   for (int m = lane >> 2; m < G::M; m += 8) {
     const int base = G::base(m, lane, warp);
-    const int n_lo = base & ((1 << G::ls) - 1);
-    double2 v[R];
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, P>(w, base & ((1 << G::ls) - 1), tw, tws);
+    double2 v[A][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = a[swz(base + (r << G::ls))];
-    if (DIR > 0) p2_twiddle<N, P, DIR>(v, n_lo, tw, tws);
-    Butterfly<R, DIR>::run(v);
-    if (DIR < 0) p2_twiddle<N, P, DIR>(v, n_lo, tw, tws);
+    for (int a = 0; a < A; ++a)
 #pragma unroll
-    for (int r = 0; r < R; ++r) a[swz(base + (r << G::ls))] = v[r];
+      for (int r = 0; r < R; ++r) v[a][r] = sm[a * N + (p2_elem<G::ls>(sb, r) ^ ((a * AX) & 7))];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if (DIR > 0) p2_apply_tw<R, DIR>(v[a], w);
+      Butterfly<R, DIR>::run(v[a]);
+      if (DIR < 0) p2_apply_tw<R, DIR>(v[a], w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<G::ls>(sb, r) ^ ((a * AX) & 7))] = v[a][r];
+    }
   }
 }
 
-// Pass 0 forward with the inputs coming from global memory through `load(pos)`.
-template <int N, int NW, typename Load>
-__device__ __forceinline__ void p2_pass0_fwd(double2 *a, const double2 *__restrict__ tw, const double2 *tws,
+// Pass 0 forward, inputs from global memory through load(a, base, offset).
+template <int N, int NW, int A, int AX, typename Load>
+__device__ __forceinline__ void p2_pass0_fwd(double2 *sm, const double2 *__restrict__ tw, const double2 *tws,
                                              int lane, int warp, Load load)
 {
   using G = GA<N, 0, NW>;
@@ -170,19 +196,27 @@ __device__ __forceinline__ void p2_pass0_fwd(double2 *a, const double2 *__restri
 #pragma unroll 1
   for (int m = lane >> 2; m < G::M; m += 8) {
     const int base = G::base(m, lane, warp);
-    double2 v[R];
+    const int sb = base ^ swz_key(base);
+    double2 v[A][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = load(base + (r << G::ls));
-    Butterfly<R, -1>::run(v);
-    p2_twiddle<N, 0, -1>(v, base, tw, tws);          // n_lo = base (digit 0 is the top digit)
+    for (int a = 0; a < A; ++a)
 #pragma unroll
-    for (int r = 0; r < R; ++r) a[swz(base + (r << G::ls))] = v[r];
+      for (int r = 0; r < R; ++r) v[a][r] = load(a, base, r << G::ls);
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);                // n_lo = base (digit 0 is the top digit)
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      Butterfly<R, -1>::run(v[a]);
+      p2_apply_tw<R, -1>(v[a], w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<G::ls>(sb, r) ^ ((a * AX) & 7))] = v[a][r];
+    }
   }
 }
 
-// Pass 0 backward with the outputs going to global memory through `store(pos, value)`.
-template <int N, int NW, typename Store>
-__device__ __forceinline__ void p2_pass0_inv(const double2 *a, const double2 *__restrict__ tw, const double2 *tws,
+// Pass 0 backward, outputs to global memory through store(a, base, offset, value).
+template <int N, int NW, int A, int AX, typename Store>
+__device__ __forceinline__ void p2_pass0_inv(const double2 *sm, const double2 *__restrict__ tw, const double2 *tws,
                                              int lane, int warp, Store store)
 {
   using G = GA<N, 0, NW>;
@@ -190,85 +224,302 @@ __device__ __forceinline__ void p2_pass0_inv(const double2 *a, const double2 *__
 #pragma unroll 1
   for (int m = lane >> 2; m < G::M; m += 8) {
     const int base = G::base(m, lane, warp);
-    double2 v[R];
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);
+    double2 v[A][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = a[swz(base + (r << G::ls))];
-    p2_twiddle<N, 0, +1>(v, base, tw, tws);
-    Butterfly<R, +1>::run(v);
+    for (int a = 0; a < A; ++a)
 #pragma unroll
-    for (int r = 0; r < R; ++r) store(base + (r << G::ls), v[r]);
+      for (int r = 0; r < R; ++r) v[a][r] = sm[a * N + (p2_elem<G::ls>(sb, r) ^ ((a * AX) & 7))];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      p2_apply_tw<R, +1>(v[a], w);
+      Butterfly<R, +1>::run(v[a]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) store(a, base, r << G::ls, v[a][r]);
+    }
   }
 }
 
 // remaining group-A passes 1 .. NA-1 (forward) / NA-1 .. 1 (backward), warp-synchronous
-template <int N, int NW, int DIR>
-__device__ __forceinline__ void p2_groupA_rest(double2 *a, const double2 *__restrict__ tw, const double2 *tws,
+template <int N, int NW, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupA_rest(double2 *sm, const double2 *__restrict__ tw, const double2 *tws,
                                                int lane, int warp)
 {
+  constexpr int P2nd = P2<N>::NA > 2 ? 2 : 1;
   if (DIR < 0) {
     __syncwarp();
-    p2_groupA_pass<N, 1, NW, -1>(a, tw, tws, lane, warp);
+    p2_groupA_pass<N, 1, NW, -1, A, AX>(sm, tw, tws, lane, warp);
     if (P2<N>::NA > 2) {
       __syncwarp();
-      p2_groupA_pass<N, (P2<N>::NA > 2 ? 2 : 1), NW, -1>(a, tw, tws, lane, warp);
+      p2_groupA_pass<N, P2nd, NW, -1, A, AX>(sm, tw, tws, lane, warp);
     }
   } else {
     if (P2<N>::NA > 2) {
-      p2_groupA_pass<N, (P2<N>::NA > 2 ? 2 : 1), NW, +1>(a, tw, tws, lane, warp);
+      p2_groupA_pass<N, P2nd, NW, +1, A, AX>(sm, tw, tws, lane, warp);
       __syncwarp();
     }
-    p2_groupA_pass<N, 1, NW, +1>(a, tw, tws, lane, warp);
+    p2_groupA_pass<N, 1, NW, +1, A, AX>(sm, tw, tws, lane, warp);
     __syncwarp();
   }
 }
 
 // ------------------------------------------------------------ group B items ---
-// item idx in [0, N/8): block of 64 = idx >> 3, a = idx & 7 (the same 8 lanes own a
+// item idx in [0, N/8): block of 64 = idx >> 3, al = idx & 7 (the same 8 lanes own a
 // block in both passes).
 
-// forward pass NP-2 (stride 8) in place
-template <int N> __device__ __forceinline__ void p2_groupB_first_fwd(double2 *a, const double2 *tws, int idx)
+// pass NP-2 (stride 8) in place over A arrays
+template <int N, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupB_first(double2 *sm, const double2 *tws, int idx)
 {
   const int al = idx & 7, base = (idx >> 3) * 64 + al;
-  double2 v[8];
+  const int sb = base ^ swz_key(base);
+  double2 w[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) v[r] = a[swz(base + 8 * r)];
-  Butterfly<8, -1>::run(v);
+  for (int q = 1; q < 8; ++q) w[q] = tws[P2<N>::TW8 + (q - 1) * 8 + al];
+  double2 v[A][8];
 #pragma unroll
-  for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], tws[P2<N>::TW8 + (q - 1) * 8 + al]);
+  for (int a = 0; a < A; ++a)
 #pragma unroll
-  for (int r = 0; r < 8; ++r) a[swz(base + 8 * r)] = v[r];
+    for (int r = 0; r < 8; ++r) v[a][r] = sm[a * N + (p2_elem<3>(sb, r) ^ ((a * AX) & 7))];
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    if (DIR > 0) p2_apply_tw<8, DIR>(v[a], w);
+    Butterfly<8, DIR>::run(v[a]);
+    if (DIR < 0) p2_apply_tw<8, DIR>(v[a], w);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[a * N + (p2_elem<3>(sb, r) ^ ((a * AX) & 7))] = v[a][r];
+  }
 }
 
-// backward pass NP-2 in place
-template <int N> __device__ __forceinline__ void p2_groupB_first_inv(double2 *a, const double2 *tws, int idx)
-{
-  const int al = idx & 7, base = (idx >> 3) * 64 + al;
-  double2 v[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) v[r] = a[swz(base + 8 * r)];
-#pragma unroll
-  for (int q = 1; q < 8; ++q) v[q] = cmulc(v[q], tws[P2<N>::TW8 + (q - 1) * 8 + al]);
-  Butterfly<8, +1>::run(v);
-#pragma unroll
-  for (int r = 0; r < 8; ++r) a[swz(base + 8 * r)] = v[r];
-}
+// last pass (stride 1): element r of item idx sits at lastbase + (r ^ lastkey)
+__device__ __forceinline__ int p2_last_base(int idx) { return (idx >> 3) * 64 + 8 * (idx & 7); }
 
-// forward last pass (stride 1): result in registers, positions (idx>>3)*64 + 8*(idx&7) + r
-__device__ __forceinline__ void p2_last_fwd_load(const double2 *a, int idx, double2 *v)
+__device__ __forceinline__ void p2_last_fwd_load(const double2 *a, int base, int key, double2 *v)
 {
-  const int base = (idx >> 3) * 64 + 8 * (idx & 7);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) v[r] = a[swz(base + r)];
+  for (int r = 0; r < 8; ++r) v[r] = a[base + (r ^ key)];
   Butterfly<8, -1>::run(v);
 }
 
-__device__ __forceinline__ void p2_last_inv_store(double2 *a, int idx, double2 *v)
+__device__ __forceinline__ void p2_last_inv_store(double2 *a, int base, int key, double2 *v)
 {
-  const int base = (idx >> 3) * 64 + 8 * (idx & 7);
   Butterfly<8, +1>::run(v);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) a[swz(base + r)] = v[r];
+  for (int r = 0; r < 8; ++r) a[base + (r ^ key)] = v[r];
+}
+
+// ---------------------------------------------- low-register pass variants ---
+// Same passes, but the A arrays go through a two-deep register pipeline (array
+// a+1 is being loaded while array a is transformed) instead of being all live at
+// once: ~64 instead of 32*A data registers, for kernels that run 16 warps per SM.
+
+template <int N, int P, int NW, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupA_pass_seq(double2 *sm, const double2 *__restrict__ tw,
+                                                   const double2 *tws, int lane, int warp)
+{
+  using G = GA<N, P, NW>;
+  constexpr int R = 1 << G::lr;
+#pragma unroll 1
+  for (int m = lane >> 2; m < G::M; m += 8) {
+    const int base = G::base(m, lane, warp);
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, P>(w, base & ((1 << G::ls) - 1), tw, tws);
+    double2 v[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[0][r] = sm[p2_elem<G::ls>(sb, r)];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if (a + 1 < A) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          v[(a + 1) & 1][r] = sm[(a + 1) * N + (p2_elem<G::ls>(sb, r) ^ (((a + 1) * AX) & 7))];
+      }
+      if (DIR > 0) p2_apply_tw<R, DIR>(v[a & 1], w);
+      Butterfly<R, DIR>::run(v[a & 1]);
+      if (DIR < 0) p2_apply_tw<R, DIR>(v[a & 1], w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<G::ls>(sb, r) ^ ((a * AX) & 7))] = v[a & 1][r];
+    }
+  }
+}
+
+template <int N, int NW, int A, int AX, typename Load>
+__device__ __forceinline__ void p2_pass0_fwd_seq(double2 *sm, const double2 *__restrict__ tw, const double2 *tws,
+                                                 int lane, int warp, Load load)
+{
+  using G = GA<N, 0, NW>;
+  constexpr int R = 1 << G::lr;
+#pragma unroll 1
+  for (int m = lane >> 2; m < G::M; m += 8) {
+    const int base = G::base(m, lane, warp);
+    const int sb = base ^ swz_key(base);
+    double2 v[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[0][r] = load(0, base, r << G::ls);
+    if (A > 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[1][r] = load(1, base, r << G::ls);
+    }
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      Butterfly<R, -1>::run(v[a & 1]);
+      p2_apply_tw<R, -1>(v[a & 1], w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<G::ls>(sb, r) ^ ((a * AX) & 7))] = v[a & 1][r];
+      if (a + 2 < A) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[a & 1][r] = load(a + 2, base, r << G::ls);
+      }
+    }
+  }
+}
+
+template <int N, int NW, int A, int AX, typename Store>
+__device__ __forceinline__ void p2_pass0_inv_seq(const double2 *sm, const double2 *__restrict__ tw,
+                                                 const double2 *tws, int lane, int warp, Store store)
+{
+  using G = GA<N, 0, NW>;
+  constexpr int R = 1 << G::lr;
+#pragma unroll 1
+  for (int m = lane >> 2; m < G::M; m += 8) {
+    const int base = G::base(m, lane, warp);
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);
+    double2 v[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[0][r] = sm[p2_elem<G::ls>(sb, r)];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if (a + 1 < A) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          v[(a + 1) & 1][r] = sm[(a + 1) * N + (p2_elem<G::ls>(sb, r) ^ (((a + 1) * AX) & 7))];
+      }
+      p2_apply_tw<R, +1>(v[a & 1], w);
+      Butterfly<R, +1>::run(v[a & 1]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) store(a, base, r << G::ls, v[a & 1][r]);
+    }
+  }
+}
+
+// Pass 0 with a block-wide item mapping: item = thread (base position = item index), so
+// that 8 neighbouring lanes touch 8 consecutive elements = one full 128-byte line in
+// global memory.  NOT warp-local: needs a __syncthreads towards the other group-A passes.
+template <int N, int T, int A, int AX, typename Load>
+__device__ __forceinline__ void p2_pass0_fwd_blk(double2 *sm, const double2 *__restrict__ tw, const double2 *tws,
+                                                 Load load)
+{
+  constexpr int lr = P2<N>::lr(0), ls = P2<N>::ls(0), R = 1 << lr;
+#pragma unroll 1
+  for (int base = threadIdx.x; base < (N >> lr); base += T) {
+    const int sb = base ^ swz_key(base);
+    double2 v[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[0][r] = load(0, base, r << ls);
+    if (A > 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[1][r] = load(1, base, r << ls);
+    }
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      Butterfly<R, -1>::run(v[a & 1]);
+      p2_apply_tw<R, -1>(v[a & 1], w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<ls>(sb, r) ^ ((a * AX) & 7))] = v[a & 1][r];
+      if (a + 2 < A) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[a & 1][r] = load(a + 2, base, r << ls);
+      }
+    }
+  }
+}
+
+template <int N, int T, int A, int AX, typename Store>
+__device__ __forceinline__ void p2_pass0_inv_blk(const double2 *sm, const double2 *__restrict__ tw,
+                                                 const double2 *tws, Store store)
+{
+  constexpr int lr = P2<N>::lr(0), ls = P2<N>::ls(0), R = 1 << lr;
+#pragma unroll 1
+  for (int base = threadIdx.x; base < (N >> lr); base += T) {
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);
+    double2 v[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[0][r] = sm[p2_elem<ls>(sb, r)];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if (a + 1 < A) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[(a + 1) & 1][r] = sm[(a + 1) * N + (p2_elem<ls>(sb, r) ^ (((a + 1) * AX) & 7))];
+      }
+      p2_apply_tw<R, +1>(v[a & 1], w);
+      Butterfly<R, +1>::run(v[a & 1]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) store(a, base, r << ls, v[a & 1][r]);
+    }
+  }
+}
+
+template <int N, int NW, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupA_rest_seq(double2 *sm, const double2 *__restrict__ tw,
+                                                   const double2 *tws, int lane, int warp)
+{
+  constexpr int P2nd = P2<N>::NA > 2 ? 2 : 1;
+  if (DIR < 0) {
+    __syncwarp();
+    p2_groupA_pass_seq<N, 1, NW, -1, A, AX>(sm, tw, tws, lane, warp);
+    if (P2<N>::NA > 2) {
+      __syncwarp();
+      p2_groupA_pass_seq<N, P2nd, NW, -1, A, AX>(sm, tw, tws, lane, warp);
+    }
+  } else {
+    if (P2<N>::NA > 2) {
+      p2_groupA_pass_seq<N, P2nd, NW, +1, A, AX>(sm, tw, tws, lane, warp);
+      __syncwarp();
+    }
+    p2_groupA_pass_seq<N, 1, NW, +1, A, AX>(sm, tw, tws, lane, warp);
+    __syncwarp();
+  }
+}
+
+template <int N, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupB_first_seq(double2 *sm, const double2 *tws, int idx)
+{
+  const int al = idx & 7, base = (idx >> 3) * 64 + al;
+  const int sb = base ^ swz_key(base);
+  double2 w[8];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) w[q] = tws[P2<N>::TW8 + (q - 1) * 8 + al];
+  double2 v[2][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[0][r] = sm[p2_elem<3>(sb, r)];
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    if (a + 1 < A) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[(a + 1) & 1][r] = sm[(a + 1) * N + (p2_elem<3>(sb, r) ^ (((a + 1) * AX) & 7))];
+    }
+    if (DIR > 0) p2_apply_tw<8, DIR>(v[a & 1], w);
+    Butterfly<8, DIR>::run(v[a & 1]);
+    if (DIR < 0) p2_apply_tw<8, DIR>(v[a & 1], w);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[a * N + (p2_elem<3>(sb, r) ^ ((a * AX) & 7))] = v[a & 1][r];
+  }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 }  // namespace gfmd

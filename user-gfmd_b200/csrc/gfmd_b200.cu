@@ -490,6 +490,13 @@ inline void stage_mark(gfmd_b200 *h, int i)
   if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
 }
 
+int atom_blocks(const gfmd_b200 *h, int nall)
+{
+  const int tiles = (nall + kAtomTile - 1) / kAtomTile;
+  const int cap = h->num_sms * 8;           // 8 resident blocks of 256 threads per SM
+  return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
+}
+
 int exchange(gfmd_b200 *h, const double2 *src, double2 *dst)
 {
   const GridDesc &g = h->g;
@@ -554,7 +561,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
       h->launches++;
     }
   }
-  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc * (h->fast_cols ? kColsNW : 1), h->d_res);
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
   h->launches++;
   stage_mark(h, 4);
   if (g.P > 1) {
@@ -658,6 +665,24 @@ void try_pin(gfmd_b200 *h, const void *p, size_t bytes)
     cudaGetLastError();     // pageable copies still work
 }
 
+// Where plane c of wavevector kx lives inside one column's block of d*d*nx doubles:
+// off + c * cstride.  Generic kernels: plane-major [c][kx].  Specialised column kernels:
+// the spectrum is digit-reversed (pos) and the planes are interleaved item by item,
+// [pos / 64][(pos & 7) / 2][c][(pos >> 3) & 7][pos & 1], so that the 9 x 16-byte loads of
+// one contraction round of 8 neighbouring threads form one contiguous 1152-byte chunk.
+inline void phi_slot(bool fast, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
+{
+  if (!fast) {
+    off = (size_t) kx;
+    cstride = (size_t) nx;
+    return;
+  }
+  const int pos = p2_freq_to_pos(lognx, kx);
+  const int blk = pos >> 6, a = (pos >> 3) & 7, r = pos & 7;
+  off = (size_t) blk * 64 * dsq + (size_t) (r >> 1) * 16 * dsq + (size_t) a * 2 + (r & 1);
+  cstride = 16;
+}
+
 // Hermitian packing of one q: M = full d x d complex matrix (row-major), scale s.
 inline void pack_hermitian(const double *M, const double *Mneg, int d, double s, double *dst,
                            size_t plane_stride, double &amax, double &hdev, double &cdev)
@@ -704,6 +729,17 @@ inline void pack_hermitian(const double *M, const double *Mneg, int d, double s,
 // -------------------------------------------------------------------- ABI ---
 
 extern "C" {
+
+#ifdef GFMD_PHASE_TIMING
+int gfmd_b200_debug_phase_cycles(long long *out, int reset)
+{
+  long long z[16] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(z));
+  if (reset) cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  return 0;
+}
+#endif
 
 const char *gfmd_b200_version(void) { return "gfmd_b200 0.1 (sm_100a, fp64)"; }
 
@@ -826,9 +862,9 @@ int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised,
         const int kxn = (nx - kx) % nx;
         const double *M = phi + 2 * dsq * ((size_t) kx * ny + ky);
         const double *Mn = phi + 2 * dsq * ((size_t) kxn * ny + kyn);
-        const int pos = h->fast_cols ? p2_freq_to_pos(lognx, kx) : kx;
-        pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + pos, (size_t) nx, amax, hdev,
-                       cdev);
+        size_t off, cstride;
+        phi_slot(h->fast_cols != 0, lognx, nx, dsq, kx, off, cstride);
+        pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     }
     CU(h, cudaMemcpy(h->d_phi + (size_t) k0 * dsq * nx, buf.data(), sizeof(double) * (size_t) nk * dsq * nx,
@@ -867,9 +903,9 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
     for (int kl = 0; kl < nk; ++kl)
       for (int kx = 0; kx < nx; ++kx) {
         const double *M = phi + 2 * dsq * ((size_t) kx * nky + k0 + kl);
-        const int pos = h->fast_cols ? p2_freq_to_pos(lognx, kx) : kx;
-        pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + pos, (size_t) nx, amax, hdev,
-                       cdev);
+        size_t off, cstride;
+        phi_slot(h->fast_cols != 0, lognx, nx, dsq, kx, off, cstride);
+        pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     CU(h, cudaMemcpy(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),
                      sizeof(double) * (size_t) nk * dsq * nx, cudaMemcpyHostToDevice));
@@ -944,7 +980,7 @@ int gfmd_b200_gather(gfmd_b200_t *h, const double *d_x, const double *d_xeq, int
   CU(h, cudaMemsetAsync(&h->d_res->n_out_of_range, 0, sizeof(int), h->stream));
   stage_mark(h, 0);
   if (nall > 0) {
-    k_gather<<<(nall + 255) / 256, 256, 0, h->stream>>>(d_x, d_xeq, d_gid, d_mask, groupbit, nall, h->g, xprd,
+    k_gather<<<atom_blocks(h, nall), kAtomTile, 0, h->stream>>>(d_x, d_xeq, d_gid, d_mask, groupbit, nall, h->g, xprd,
                                                         yprd, dxshift, dyshift, d_u ? d_u : h->d_u, h->d_res);
     h->launches++;
   }
@@ -963,7 +999,7 @@ int gfmd_b200_scatter(gfmd_b200_t *h, const double *d_fgrid, const int *d_gid, c
   if (!h || !d_gid || !d_mask || !d_f) return fail(h, GFMD_B200_EINVAL, "scatter: null argument");
   int rc = set_device(h);
   if (rc) return rc;
-  const int nblk = (nall + 255) / 256;
+  const int nblk = atom_blocks(h, nall);
   if (nblk > h->fsum_part_cap) {
     CU(h, cudaStreamSynchronize(h->stream));
     cudaFree(h->d_fsum_part);
@@ -974,7 +1010,7 @@ int gfmd_b200_scatter(gfmd_b200_t *h, const double *d_fgrid, const int *d_gid, c
   CU(h, cudaMemsetAsync(&h->d_res->natoms_scattered, 0, sizeof(int), h->stream));
   if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
   if (nall > 0) {
-    k_scatter<<<nblk, 256, 0, h->stream>>>(d_fgrid ? d_fgrid : h->d_f, d_gid, d_mask, groupbit, nall, nlocal,
+    k_scatter<<<nblk, kAtomTile, 0, h->stream>>>(d_fgrid ? d_fgrid : h->d_f, d_gid, d_mask, groupbit, nall, nlocal,
                                            h->g, d_f, h->d_fsum_part, h->d_res);
     k_sum_partials<<<1, 256, 0, h->stream>>>(h->d_fsum_part, nblk, 3, h->d_res->fsum);
     h->launches += 2;

@@ -15,10 +15,13 @@
 #include "fft_engine.cuh"
 #include "fft_pow2.cuh"
 #include "kernels_generic.cuh"
+#include "kernel_cols_lr.cuh"
 
 namespace gfmd {
 
-constexpr int kColsNW = 8;      // warps of the fused column kernel (epart has kColsNW slots per column)
+constexpr int kColsNW = 16;     // epart slots allocated per column (max warps of a column kernel)
+inline int fast_cols_nw(int variant) { return variant == 4096 ? 16 : 8; }
+constexpr int kColsNW8 = 8;      // warps of the fused column kernel (epart has kColsNW slots per column)
 
 // ------------------------------------------------------------------ columns ---
 
@@ -29,75 +32,61 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
                 const double *__restrict__ linf, double *__restrict__ epart, StepResults *res)
 {
   constexpr int NW = T / 32;
-  static_assert(NW == kColsNW, "epart layout");
+  static_assert(NW <= kColsNW, "epart layout");
   extern __shared__ double2 sm[];
   double2 *tws = sm + D * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xmask = (1 << lnxl) - 1;
   p2_fill_tws<N>(tws, tw);
   __syncthreads();
 
   for (int kl = blockIdx.x; kl < g.nky_loc; kl += gridDim.x) {
     const int ky = g.ky0 + kl;
-    const int xmask = (1 << lnxl) - 1;
-    auto addr = [&](int dof, int x) -> size_t {
+    auto addr = [&](int kcol, int dof, int x) -> size_t {
       const int p = x >> lnxl;
-      return ((((size_t) (p * D + dof)) * g.kyb + kl) << lnxl) + (x & xmask);
+      return ((((size_t) (p * D + dof)) * g.kyb + kcol) << lnxl) + (x & xmask);
     };
+    const double *ph = phi + (size_t) kl * D * D * N;
 
     // ---- group A forward: pass 0 straight from global memory, all dofs in flight
-    {
-      using G = GA<N, 0, NW>;
-      constexpr int R = 1 << G::lr;
-#pragma unroll 1
-      for (int m = lane >> 2; m < G::M; m += 8) {
-        const int base = G::base(m, lane, warp);
-        double2 v[D][R];
-#pragma unroll
-        for (int dof = 0; dof < D; ++dof)
-#pragma unroll
-          for (int r = 0; r < R; ++r) v[dof][r] = sin[addr(dof, base + (r << G::ls))];
-#pragma unroll
-        for (int dof = 0; dof < D; ++dof) {
-          Butterfly<R, -1>::run(v[dof]);
-          p2_twiddle<N, 0, -1>(v[dof], base, tw, tws);
-#pragma unroll
-          for (int r = 0; r < R; ++r) sm[dof * N + swz(base + (r << G::ls))] = v[dof][r];
-        }
-      }
-    }
-#pragma unroll
-    for (int dof = 0; dof < D; ++dof) p2_groupA_rest<N, NW, -1>(sm + dof * N, tw, tws, lane, warp);
+    p2_pass0_fwd<N, NW, D, 0>(sm, tw, tws, lane, warp, [&](int a, int base, int off) { return sin[addr(kl, a, base + off)]; });
+
+    p2_groupA_rest<N, NW, -1, D, 0>(sm, tw, tws, lane, warp);
     __syncthreads();
 
     // ---- group B forward, contraction in registers, group B backward
-#pragma unroll
-    for (int dof = 0; dof < D; ++dof)
 #pragma unroll 1
-      for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first_fwd<N>(sm + dof * N, tws, idx);
+    for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first<N, -1, D, 0>(sm, tws, idx);
     __syncwarp();
 
     const double wgt = (ky == 0 || (2 * ky == g.ny)) ? 1.0 : 2.0;
-    const double *ph = phi + (size_t) kl * D * D * N;
     double e = 0.0;
 #pragma unroll 1
     for (int idx = threadIdx.x; idx < N / 8; idx += T) {
+      const int pos = p2_last_base(idx);
+      const int key = swz_key(pos);
+      // interleaved Phi planes of this item (see phi_slot in gfmd_b200.cu)
+      const double *phi_item = ph + (size_t) (idx >> 3) * (64 * D * D) + (idx & 7) * 2;
+      double2 pl[2][D * D];
+#pragma unroll
+      for (int c = 0; c < D * D; ++c) pl[0][c] = __ldg(reinterpret_cast<const double2 *>(phi_item + c * 16));
       double2 u[D][8];
 #pragma unroll
-      for (int dof = 0; dof < D; ++dof) p2_last_fwd_load(sm + dof * N, idx, u[dof]);
-      const int pos = (idx >> 3) * 64 + 8 * (idx & 7);
+      for (int dof = 0; dof < D; ++dof) p2_last_fwd_load(sm + dof * N, pos, key, u[dof]);
 #pragma unroll
       for (int rp = 0; rp < 4; ++rp) {
-        double2 pl[D * D];
+        if (rp < 3) {
 #pragma unroll
-        for (int c = 0; c < D * D; ++c)
-          pl[c] = __ldg(reinterpret_cast<const double2 *>(ph + (size_t) c * N + pos + 2 * rp));
+          for (int c = 0; c < D * D; ++c)
+            pl[(rp + 1) & 1][c] = __ldg(reinterpret_cast<const double2 *>(phi_item + (rp + 1) * (16 * D * D) + c * 16));
+        }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const int r = 2 * rp + s;
           double2 uv[D], F[D];
 #pragma unroll
           for (int i = 0; i < D; ++i) uv[i] = u[i][r];
-          phi_matvec<D>(uv, F, [&](int c) { return s == 0 ? pl[c].x : pl[c].y; });
+          phi_matvec<D>(uv, F, [&](int c) { return s == 0 ? pl[rp & 1][c].x : pl[rp & 1][c].y; });
           double eq = 0.0;
 #pragma unroll
           for (int i = 0; i < D; ++i) {
@@ -121,13 +110,11 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
         }
       }
 #pragma unroll
-      for (int dof = 0; dof < D; ++dof) p2_last_inv_store(sm + dof * N, idx, u[dof]);
+      for (int dof = 0; dof < D; ++dof) p2_last_inv_store(sm + dof * N, pos, key, u[dof]);
     }
     __syncwarp();
-#pragma unroll
-    for (int dof = 0; dof < D; ++dof)
 #pragma unroll 1
-      for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first_inv<N>(sm + dof * N, tws, idx);
+    for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first<N, +1, D, 0>(sm, tws, idx);
 
     // energy partial of this warp (fixed order -> deterministic)
 #pragma unroll
@@ -136,19 +123,16 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
     __syncthreads();
 
     // ---- group A backward, last pass straight to global memory
-#pragma unroll
-    for (int dof = 0; dof < D; ++dof) p2_groupA_rest<N, NW, +1>(sm + dof * N, tw, tws, lane, warp);
-#pragma unroll
-    for (int dof = 0; dof < D; ++dof)
-      p2_pass0_inv<N, NW>(sm + dof * N, tw, tws, lane, warp,
-                          [&](int pos, double2 v) { sout[addr(dof, pos)] = v; });
+    p2_groupA_rest<N, NW, +1, D, 0>(sm, tw, tws, lane, warp);
+    p2_pass0_inv<N, NW, D, 0>(sm, tw, tws, lane, warp,
+                              [&](int a, int base, int off, double2 v) { sout[addr(kl, a, base + off)] = v; });
     // no barrier: the next column's group A touches only what this warp owns
   }
 }
 
 // --------------------------------------------------------------------- rows ---
 
-// RB rows (same dof) of ny = 2 NR reals per CTA.
+// RB rows (same dof) of ny = 2 NR reals per CTA; array a = row a of the tile.
 template <int NR, int RB, int T>
 __global__ void __launch_bounds__(T)
 k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
@@ -156,6 +140,7 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
 {
   constexpr int NW = T / 32;
   constexpr int LOG = P2<NR>::LOG;
+  constexpr int AX = RB == 2 ? 2 : 1;       // per-row column XOR: rows of a tile never collide
   extern __shared__ double2 sm[];
   double2 *tws = sm + RB * NR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,40 +151,37 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   p2_fill_tws<NR>(tws, tw);
   __syncthreads();
 
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * ny);
-    p2_pass0_fwd<NR, NW>(sm + r * NR, tw, tws, lane, warp, [&](int pos) { return src[pos]; });
-  }
-#pragma unroll
-  for (int r = 0; r < RB; ++r) p2_groupA_rest<NR, NW, -1>(sm + r * NR, tw, tws, lane, warp);
+  const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0) * ny);
+  p2_pass0_fwd<NR, NW, RB, AX>(sm, tw, tws, lane, warp, [&](int a, int base, int off) { return src[(size_t) a * NR + base + off]; });
+  p2_groupA_rest<NR, NW, -1, RB, AX>(sm, tw, tws, lane, warp);
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_fwd<NR>(sm + r * NR, tws, idx);
+  for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first<NR, -1, RB, AX>(sm, tws, idx);
   __syncwarp();
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
-      double2 v[8];
-      p2_last_fwd_load(sm + r * NR, idx, v);
-      const int base = (idx >> 3) * 64 + 8 * (idx & 7);
+  for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
+    const int base = p2_last_base(idx);
+    const int key = swz_key(base);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) sm[r * NR + swz(base + q)] = v[q];
+    for (int a = 0; a < RB; ++a) {
+      double2 v[8];
+      p2_last_fwd_load(sm + a * NR, base, key ^ ((a * AX) & 7), v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sm[a * NR + base + (q ^ key ^ ((a * AX) & 7))] = v[q];
     }
+  }
   __syncthreads();
 
   // un-mix the packed transform and store transposed: X[ky] = A - i w B
   constexpr int h = NR;
-#pragma unroll 1
+#pragma unroll 4
   for (int i = threadIdx.x; i < RB * (h + 1); i += T) {
     const int r = i % RB, ky = i / RB;
     const int ka = ky == h ? 0 : ky;
     const int kb = ky == 0 ? 0 : h - ky;
-    const double2 zk = sm[r * NR + swz(p2_freq_to_pos(LOG, ka))];
-    const double2 zc = cconj(sm[r * NR + swz(p2_freq_to_pos(LOG, kb))]);
+    const int rx = (r * AX) & 7;
+    const double2 zk = sm[r * NR + (swz(p2_freq_to_pos(LOG, ka)) ^ rx)];
+    const double2 zc = cconj(sm[r * NR + (swz(p2_freq_to_pos(LOG, kb)) ^ rx)]);
     const double2 A = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
     const double2 B = make_double2(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
     const double2 t = cmul(__ldg(tw_ny + ky), B);
@@ -214,6 +196,7 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
 {
   constexpr int NW = T / 32;
   constexpr int LOG = P2<NR>::LOG;
+  constexpr int AX = RB == 2 ? 2 : 1;
   extern __shared__ double2 sm[];
   double2 *tws = sm + RB * NR;
   double2 *yh = tws + P2<NR>::TWS;          // Y[h] of each row
@@ -225,23 +208,37 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   constexpr int h = NR;
   p2_fill_tws<NR>(tws, tw);
 
+  // transposed load, 8 independent 16-byte loads in flight per thread
+  constexpr int UL = 8;
 #pragma unroll 1
-  for (int i = threadIdx.x; i < RB * (h + 1); i += T) {
-    const int r = i % RB, ky = i / RB;
-    const double2 y = stage[stage_index(g, ky, dof, ix0 + r)];
-    if (ky < h) sm[r * NR + swz(p2_freq_to_pos(LOG, ky))] = y;
-    else yh[r] = y;
+  for (int i0 = threadIdx.x; i0 < RB * (h + 1); i0 += T * UL) {
+    double2 y[UL];
+#pragma unroll
+    for (int j = 0; j < UL; ++j) {
+      const int i = i0 + j * T;
+      if (i < RB * (h + 1)) y[j] = stage[stage_index(g, i / RB, dof, ix0 + i % RB)];
+    }
+#pragma unroll
+    for (int j = 0; j < UL; ++j) {
+      const int i = i0 + j * T;
+      if (i < RB * (h + 1)) {
+        const int r = i % RB, ky = i / RB;
+        if (ky < h) sm[r * NR + (swz(p2_freq_to_pos(LOG, ky)) ^ ((r * AX) & 7))] = y[j];
+        else yh[r] = y[j];
+      }
+    }
   }
   __syncthreads();
 
   // Z'[k] = (Y[k] + conj Y[h-k]) + i e^{+2 pi i k/ny} (Y[k] - conj Y[h-k]), in place pairwise
   constexpr int np = h / 2 + 1;
-#pragma unroll 1
+#pragma unroll 2
   for (int i = threadIdx.x; i < RB * np; i += T) {
     const int r = i % RB, k = i / RB;
     const int k2 = h - k;
-    const int pk = r * NR + swz(p2_freq_to_pos(LOG, k));
-    const int p2i = r * NR + swz(p2_freq_to_pos(LOG, k2 & (h - 1)));
+    const int rx = (r * AX) & 7;
+    const int pk = r * NR + (swz(p2_freq_to_pos(LOG, k)) ^ rx);
+    const int p2i = r * NR + (swz(p2_freq_to_pos(LOG, k2 & (h - 1))) ^ rx);
     const double2 yk = sm[pk];
     const double2 y2 = k == 0 ? yh[r] : sm[p2i];
     {
@@ -259,29 +256,27 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   }
   __syncthreads();
 
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
-      const int base = (idx >> 3) * 64 + 8 * (idx & 7);
+  for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
+    const int base = p2_last_base(idx);
+    const int key = swz_key(base);
+#pragma unroll
+    for (int a = 0; a < RB; ++a) {
+      const int ka = key ^ ((a * AX) & 7);
       double2 v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = sm[r * NR + swz(base + q)];
-      p2_last_inv_store(sm + r * NR, idx, v);
+      for (int q = 0; q < 8; ++q) v[q] = sm[a * NR + base + (q ^ ka)];
+      p2_last_inv_store(sm + a * NR, base, ka, v);
     }
-  __syncwarp();
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
-#pragma unroll 1
-    for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_inv<NR>(sm + r * NR, tws, idx);
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RB; ++r) p2_groupA_rest<NR, NW, +1>(sm + r * NR, tw, tws, lane, warp);
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * ny);
-    p2_pass0_inv<NR, NW>(sm + r * NR, tw, tws, lane, warp, [&](int pos, double2 v) { dst[pos] = v; });
   }
+  __syncwarp();
+#pragma unroll 1
+  for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first<NR, +1, RB, AX>(sm, tws, idx);
+  __syncthreads();
+  p2_groupA_rest<NR, NW, +1, RB, AX>(sm, tw, tws, lane, warp);
+  double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0) * ny);
+  p2_pass0_inv<NR, NW, RB, AX>(sm, tw, tws, lane, warp,
+                               [&](int a, int base, int off, double2 v) { dst[(size_t) a * NR + base + off] = v; });
 }
 
 // ---------------------------------------------------------------- selection ---
@@ -347,7 +342,18 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols)
                            (int) fast_cols_smem(3, N));
     switch (g.nx) {
       case 2048: COLS_ATTR(2048) break;
-      case 4096: COLS_ATTR(4096) break;
+      case 4096:
+        switch (g.P) {
+#define LR_ATTR(LP, PP)                                                                                    \
+  case PP:                                                                                                 \
+    e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int) fast_cols_smem(3, 4096));                                               \
+    break;
+          LR_ATTR(0, 1) LR_ATTR(1, 2) LR_ATTR(2, 4) LR_ATTR(3, 8)
+#undef LR_ATTR
+          default: fast_cols = 0; break;
+        }
+        break;
     }
 #undef COLS_ATTR
     if (e != cudaSuccess) return 1;
@@ -403,7 +409,15 @@ inline int fast_cols_fused(int variant, const double2 *sin, double2 *sout, const
       k_cols_fused_p2<3, 2048, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, fd.core.tw, phi, linf, epart, res);
       break;
     case 4096:
-      k_cols_fused_p2<3, 4096, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, fd.core.tw, phi, linf, epart, res);
+      switch (12 - lnxl) {
+#define LR_LAUNCH(LP)                                                                                           \
+  case LP:                                                                                                      \
+    k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, fd.core.tw, phi, linf, epart, res); \
+    break;
+        LR_LAUNCH(0) LR_LAUNCH(1) LR_LAUNCH(2) LR_LAUNCH(3)
+#undef LR_LAUNCH
+        default: return 1;
+      }
       break;
     default: return 1;
   }

@@ -45,6 +45,7 @@ struct StepResults {     // device-resident, copied to the host on request
 
 __device__ __forceinline__ size_t stage_index(const GridDesc &g, int ky, int dof, int ix)
 {
+  if (g.P == 1) return ((size_t) dof * g.kyb + ky) * g.nx_loc + ix;
   const int r = ky / g.kyb;
   const int kl = ky - r * g.kyb;
   return ((size_t) (r * g.d + dof) * g.kyb + kl) * g.nx_loc + ix;
@@ -52,100 +53,137 @@ __device__ __forceinline__ size_t stage_index(const GridDesc &g, int ky, int dof
 
 // ------------------------------------------------------------------ gather ---
 
-// One thread per atom.  x, xeq: [nall][3]; gid: [nall][3] = (ix, iy, iu).
-__global__ void k_gather(const double *__restrict__ x, const double *__restrict__ xeq,
-                         int *__restrict__ gid, const int *__restrict__ mask, int groupbit, int nall,
-                         GridDesc g, double xprd, double yprd, int dxshift, int dyshift,
-                         double *__restrict__ u, StepResults *res)
+constexpr int kAtomTile = 256;   // atoms per tile = threads per block of gather / scatter
+
+// Grid-stride over tiles of 256 atoms.  The AoS atom arrays ([nall][3]) are staged
+// through shared memory with fully coalesced loads; thread t then owns atom t of the
+// tile.  x, xeq: [nall][3]; gid: [nall][3] = (ix, iy, iu).
+__global__ void __launch_bounds__(kAtomTile)
+k_gather(const double *__restrict__ x, const double *__restrict__ xeq, int *__restrict__ gid,
+         const int *__restrict__ mask, int groupbit, int nall, GridDesc g, double xprd, double yprd,
+         int dxshift, int dyshift, double *__restrict__ u, StepResults *res)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double sx[3 * kAtomTile], sq[3 * kAtomTile];
+  __shared__ int sg[3 * kAtomTile];
+  __shared__ int scount[2];
+  if (threadIdx.x < 2) scount[threadIdx.x] = 0;
   int stored = 0, bad = 0;
-  if (i < nall && (mask[i] & groupbit)) {
-    int ix = gid[3 * i] - dxshift;
-    int iy = gid[3 * i + 1] - dyshift;
-    const int iu = gid[3 * i + 2];
-    if (dxshift != 0 || dyshift != 0) {
-      ix %= g.nx; if (ix < 0) ix += g.nx;
-      iy %= g.ny; if (iy < 0) iy += g.ny;
-      gid[3 * i] = ix;
-      gid[3 * i + 1] = iy;
+  const double xh = 0.5 * xprd, yh = 0.5 * yprd;
+  const size_t nxy = (size_t) g.nx_loc * g.ny;
+  for (long long t0 = (long long) blockIdx.x * kAtomTile; t0 < nall; t0 += (long long) gridDim.x * kAtomTile) {
+    const int n = nall - t0 < kAtomTile ? (int) (nall - t0) : kAtomTile;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * n; k += kAtomTile) {
+      sx[k] = x[3 * t0 + k];
+      sq[k] = xeq[3 * t0 + k];
+      sg[k] = gid[3 * t0 + k];
     }
-    ix -= g.x0;
-    if (ix >= 0 && ix < g.nx_loc && iy >= 0 && iy < g.ny) {
-      if (iu < 0 || 3 * iu + 2 >= g.d) {
-        bad = 1;
-      } else {
-        const double xh = 0.5 * xprd, yh = 0.5 * yprd;
-        double ux = x[3 * i] - xeq[3 * i];
-        double uy = x[3 * i + 1] - xeq[3 * i + 1];
-        const double uz = x[3 * i + 2] - xeq[3 * i + 2];
-        while (ux > xh) ux -= xprd;
-        while (ux < -xh) ux += xprd;
-        while (uy > yh) uy -= yprd;
-        while (uy < -yh) uy += yprd;
-        const size_t nxy = (size_t) g.nx_loc * g.ny;
-        const size_t iloc = (size_t) ix * g.ny + iy;
-        u[(size_t) (3 * iu) * nxy + iloc] = ux;
-        u[(size_t) (3 * iu + 1) * nxy + iloc] = uy;
-        u[(size_t) (3 * iu + 2) * nxy + iloc] = uz;
-        stored = 1;
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < n && (mask[t0 + t] & groupbit)) {
+      int ix = sg[3 * t] - dxshift;
+      int iy = sg[3 * t + 1] - dyshift;
+      const int iu = sg[3 * t + 2];
+      if (dxshift != 0 || dyshift != 0) {
+        ix %= g.nx; if (ix < 0) ix += g.nx;
+        iy %= g.ny; if (iy < 0) iy += g.ny;
+        gid[3 * (t0 + t)] = ix;
+        gid[3 * (t0 + t) + 1] = iy;
+      }
+      ix -= g.x0;
+      if (ix >= 0 && ix < g.nx_loc && iy >= 0 && iy < g.ny) {
+        if (iu < 0 || 3 * iu + 2 >= g.d) {
+          bad++;
+        } else {
+          double ux = sx[3 * t] - sq[3 * t];
+          double uy = sx[3 * t + 1] - sq[3 * t + 1];
+          const double uz = sx[3 * t + 2] - sq[3 * t + 2];
+          while (ux > xh) ux -= xprd;
+          while (ux < -xh) ux += xprd;
+          while (uy > yh) uy -= yprd;
+          while (uy < -yh) uy += yprd;
+          const size_t iloc = (size_t) ix * g.ny + iy;
+          u[(size_t) (3 * iu) * nxy + iloc] = ux;
+          u[(size_t) (3 * iu + 1) * nxy + iloc] = uy;
+          u[(size_t) (3 * iu + 2) * nxy + iloc] = uz;
+          stored++;
+        }
       }
     }
   }
-  // warp-aggregated counters
-  unsigned ms = __ballot_sync(0xffffffffu, stored);
-  unsigned mb = __ballot_sync(0xffffffffu, bad);
-  if ((threadIdx.x & 31) == 0) {
-    if (ms) atomicAdd(&res->natoms_gathered, __popc(ms));
-    if (mb) atomicAdd(&res->n_out_of_range, __popc(mb));
+  // one atomic per block and counter
+  __syncthreads();
+  if (stored) atomicAdd(&scount[0], stored);
+  if (bad) atomicAdd(&scount[1], bad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (scount[0]) atomicAdd(&res->natoms_gathered, scount[0]);
+    if (scount[1]) atomicAdd(&res->n_out_of_range, scount[1]);
   }
 }
 
 // ----------------------------------------------------------------- scatter ---
 
-__global__ void k_scatter(const double *__restrict__ fgrid, const int *__restrict__ gid,
-                          const int *__restrict__ mask, int groupbit, int nall, int nlocal, GridDesc g,
-                          double *__restrict__ f, double *__restrict__ fsum_part, StepResults *res)
+// f[nall][3] += grid force of the atom's cell; per-block partial sums of the forces on
+// the first nlocal atoms go to fsum_part[3*blockIdx + c] (summed in fixed order later).
+__global__ void __launch_bounds__(kAtomTile)
+k_scatter(const double *__restrict__ fgrid, const int *__restrict__ gid, const int *__restrict__ mask,
+          int groupbit, int nall, int nlocal, GridDesc g, double *__restrict__ f,
+          double *__restrict__ fsum_part, StepResults *res)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double fx = 0.0, fy = 0.0, fz = 0.0;
+  __shared__ double sf[3 * kAtomTile];
+  __shared__ int sg[3 * kAtomTile];
+  __shared__ double sh[3][kAtomTile / 32];
+  __shared__ int scount;
+  if (threadIdx.x == 0) scount = 0;
+  double ax = 0.0, ay = 0.0, az = 0.0;
   int known = 0;
-  if (i < nall && (mask[i] & groupbit)) {
-    int ix = gid[3 * i] - g.x0;
-    const int iy = gid[3 * i + 1];
-    const int iu = gid[3 * i + 2];
-    if (ix >= 0 && ix < g.nx_loc && iy >= 0 && iy < g.ny && iu >= 0 && 3 * iu + 2 < g.d) {
-      const size_t nxy = (size_t) g.nx_loc * g.ny;
-      const size_t iloc = (size_t) ix * g.ny + iy;
-      fx = fgrid[(size_t) (3 * iu) * nxy + iloc];
-      fy = fgrid[(size_t) (3 * iu + 1) * nxy + iloc];
-      fz = fgrid[(size_t) (3 * iu + 2) * nxy + iloc];
-      f[3 * i] += fx;
-      f[3 * i + 1] += fy;
-      f[3 * i + 2] += fz;
-      known = 1;
-      if (i >= nlocal) fx = fy = fz = 0.0;   // fsum_loc counts local atoms only (:997-1001)
+  const size_t nxy = (size_t) g.nx_loc * g.ny;
+  for (long long t0 = (long long) blockIdx.x * kAtomTile; t0 < nall; t0 += (long long) gridDim.x * kAtomTile) {
+    const int n = nall - t0 < kAtomTile ? (int) (nall - t0) : kAtomTile;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * n; k += kAtomTile) {
+      sf[k] = f[3 * t0 + k];
+      sg[k] = gid[3 * t0 + k];
     }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < n && (mask[t0 + t] & groupbit)) {
+      const int ix = sg[3 * t] - g.x0;
+      const int iy = sg[3 * t + 1];
+      const int iu = sg[3 * t + 2];
+      if (ix >= 0 && ix < g.nx_loc && iy >= 0 && iy < g.ny && iu >= 0 && 3 * iu + 2 < g.d) {
+        const size_t iloc = (size_t) ix * g.ny + iy;
+        const double fx = fgrid[(size_t) (3 * iu) * nxy + iloc];
+        const double fy = fgrid[(size_t) (3 * iu + 1) * nxy + iloc];
+        const double fz = fgrid[(size_t) (3 * iu + 2) * nxy + iloc];
+        sf[3 * t] += fx;
+        sf[3 * t + 1] += fy;
+        sf[3 * t + 2] += fz;
+        known++;
+        if (t0 + t < nlocal) { ax += fx; ay += fy; az += fz; }   // fsum_loc: local atoms only (:997-1001)
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * n; k += kAtomTile) f[3 * t0 + k] = sf[k];
   }
-  // deterministic block partials: fsum_part[3*blockIdx + c]
-  __shared__ double sh[3][32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    fx += __shfl_down_sync(0xffffffffu, fx, o);
-    fy += __shfl_down_sync(0xffffffffu, fy, o);
-    fz += __shfl_down_sync(0xffffffffu, fz, o);
+    ax += __shfl_down_sync(0xffffffffu, ax, o);
+    ay += __shfl_down_sync(0xffffffffu, ay, o);
+    az += __shfl_down_sync(0xffffffffu, az, o);
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][w] = fx; sh[1][w] = fy; sh[2][w] = fz; }
-  unsigned mk = __ballot_sync(0xffffffffu, known);
-  if (lane == 0 && mk) atomicAdd(&res->natoms_scattered, __popc(mk));
+  if (lane == 0) { sh[0][w] = ax; sh[1][w] = ay; sh[2][w] = az; }
+  __syncthreads();
+  if (known) atomicAdd(&scount, known);
   __syncthreads();
   if (threadIdx.x < 3) {
     double a = 0.0;
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int k = 0; k < nw; ++k) a += sh[threadIdx.x][k];
+    for (int k = 0; k < kAtomTile / 32; ++k) a += sh[threadIdx.x][k];
     fsum_part[3 * blockIdx.x + threadIdx.x] = a;
   }
+  if (threadIdx.x == 0 && scount) atomicAdd(&res->natoms_scattered, scount);
 }
 
 // fixed-order sum of per-block partials: part[nblk][ncomp] -> out[ncomp]
