@@ -1,0 +1,23 @@
+import sys, numpy as np, torch
+sys.path.insert(0,'/root/repo/user-gfmd_b200'); sys.path.insert(0,'/root/repo')
+import gfmd_b200
+from gfmd_b200 import synthetic
+n=int(sys.argv[1]) if len(sys.argv)>1 else 4096
+nx=ny=n; d=3
+s=gfmd_b200.GFMDSolverB200(); s.set_grid_size(nx,ny,d)
+print(s.describe())
+for k0 in range(0,s.nky,256):
+    nk=min(256,s.nky-k0); s.set_kernel_columns(synthetic.phi_columns(nx,ny,k0,nk),k0,normalized=False)
+s.set_linf(np.zeros(1))
+u=torch.rand((d,nx*ny),device='cuda',dtype=torch.float64)-0.5; f=torch.empty_like(u); torch.cuda.synchronize()
+for i in range(5): s.post_force_device(u,f)
+s.synchronize()
+import time
+t0=time.perf_counter(); N=50
+for i in range(N): s.post_force_device(u,f)
+s.synchronize(); dt=(time.perf_counter()-t0)/N
+s.profile(True)
+for i in range(20): s.post_force_device(u,f)
+s.profile(False)
+st=s.stage_times()
+print('solver ms %.4f  steps/s %.1f'%(dt*1e3,1/dt), {k:round(v[0]/max(v[1],1),4) for k,v in st.items() if v[1]})

@@ -470,6 +470,62 @@ __device__ __forceinline__ void p2_pass0_inv_blk(const double2 *sm, const double
   }
 }
 
+// In-place group-A pass P with the block-wide item mapping (item j of N/R: the digit of
+// pass P is spliced out of j).  Needs __syncthreads before and after.
+template <int N, int P, int T, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupA_pass_blk(double2 *sm, const double2 *__restrict__ tw,
+                                                   const double2 *tws)
+{
+  constexpr int lr = P2<N>::lr(P), ls = P2<N>::ls(P), R = 1 << lr;
+#pragma unroll 1
+  for (int j = threadIdx.x; j < (N >> lr); j += T) {
+    const int base = ((j >> ls) << (ls + lr)) | (j & ((1 << ls) - 1));
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, P>(w, base & ((1 << ls) - 1), tw, tws);
+    double2 v[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[0][r] = sm[p2_elem<ls>(sb, r)];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if (a + 1 < A) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[(a + 1) & 1][r] = sm[(a + 1) * N + (p2_elem<ls>(sb, r) ^ (((a + 1) * AX) & 7))];
+      }
+      if (DIR > 0) p2_apply_tw<R, DIR>(v[a & 1], w);
+      Butterfly<R, DIR>::run(v[a & 1]);
+      if (DIR < 0) p2_apply_tw<R, DIR>(v[a & 1], w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<ls>(sb, r) ^ ((a * AX) & 7))] = v[a & 1][r];
+    }
+  }
+}
+
+// group-A passes 1 .. NA-1 (forward) / NA-1 .. 1 (backward) with block-wide mapping;
+// starts and ends with a __syncthreads
+template <int N, int T, int DIR, int A, int AX>
+__device__ __forceinline__ void p2_groupA_rest_blk(double2 *sm, const double2 *__restrict__ tw,
+                                                   const double2 *tws)
+{
+  constexpr int P2nd = P2<N>::NA > 2 ? 2 : 1;
+  __syncthreads();
+  if (DIR < 0) {
+    p2_groupA_pass_blk<N, 1, T, -1, A, AX>(sm, tw, tws);
+    __syncthreads();
+    if (P2<N>::NA > 2) {
+      p2_groupA_pass_blk<N, P2nd, T, -1, A, AX>(sm, tw, tws);
+      __syncthreads();
+    }
+  } else {
+    if (P2<N>::NA > 2) {
+      p2_groupA_pass_blk<N, P2nd, T, +1, A, AX>(sm, tw, tws);
+      __syncthreads();
+    }
+    p2_groupA_pass_blk<N, 1, T, +1, A, AX>(sm, tw, tws);
+    __syncthreads();
+  }
+}
+
 template <int N, int NW, int DIR, int A, int AX>
 __device__ __forceinline__ void p2_groupA_rest_seq(double2 *sm, const double2 *__restrict__ tw,
                                                    const double2 *tws, int lane, int warp)

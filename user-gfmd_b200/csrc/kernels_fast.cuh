@@ -138,12 +138,10 @@ __global__ void __launch_bounds__(T)
 k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny)
 {
-  constexpr int NW = T / 32;
   constexpr int LOG = P2<NR>::LOG;
   constexpr int AX = RB == 2 ? 2 : 1;       // per-row column XOR: rows of a tile never collide
   extern __shared__ double2 sm[];
   double2 *tws = sm + RB * NR;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblk = g.nx_loc / RB;
   const int dof = blockIdx.x / nblk;
   const int ix0 = (blockIdx.x - dof * nblk) * RB;
@@ -152,11 +150,11 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   __syncthreads();
 
   const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0) * ny);
-  p2_pass0_fwd<NR, NW, RB, AX>(sm, tw, tws, lane, warp, [&](int a, int base, int off) { return src[(size_t) a * NR + base + off]; });
-  p2_groupA_rest<NR, NW, -1, RB, AX>(sm, tw, tws, lane, warp);
-  __syncthreads();
+  p2_pass0_fwd_blk<NR, T, RB, AX>(sm, tw, tws,
+                                  [&](int a, int base, int off) { return src[(size_t) a * NR + base + off]; });
+  p2_groupA_rest_blk<NR, T, -1, RB, AX>(sm, tw, tws);
 #pragma unroll 1
-  for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first<NR, -1, RB, AX>(sm, tws, idx);
+  for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_seq<NR, -1, RB, AX>(sm, tws, idx);
   __syncwarp();
 #pragma unroll 1
   for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
@@ -194,13 +192,11 @@ __global__ void __launch_bounds__(T)
 k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny)
 {
-  constexpr int NW = T / 32;
   constexpr int LOG = P2<NR>::LOG;
   constexpr int AX = RB == 2 ? 2 : 1;
   extern __shared__ double2 sm[];
   double2 *tws = sm + RB * NR;
   double2 *yh = tws + P2<NR>::TWS;          // Y[h] of each row
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblk = g.nx_loc / RB;
   const int dof = blockIdx.x / nblk;
   const int ix0 = (blockIdx.x - dof * nblk) * RB;
@@ -271,24 +267,25 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   }
   __syncwarp();
 #pragma unroll 1
-  for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first<NR, +1, RB, AX>(sm, tws, idx);
-  __syncthreads();
-  p2_groupA_rest<NR, NW, +1, RB, AX>(sm, tw, tws, lane, warp);
+  for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_seq<NR, +1, RB, AX>(sm, tws, idx);
+  p2_groupA_rest_blk<NR, T, +1, RB, AX>(sm, tw, tws);
   double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0) * ny);
-  p2_pass0_inv<NR, NW, RB, AX>(sm, tw, tws, lane, warp,
-                               [&](int a, int base, int off, double2 v) { dst[(size_t) a * NR + base + off] = v; });
+  p2_pass0_inv_blk<NR, T, RB, AX>(sm, tw, tws,
+                                  [&](int a, int base, int off, double2 v) { dst[(size_t) a * NR + base + off] = v; });
 }
 
 // ---------------------------------------------------------------- selection ---
 
 struct FastRowsCfg { int nr, rb, t; };
 
-inline bool fast_rows_cfg(int ny, FastRowsCfg &c)
+// variant id = ny, or ny + 1 for the 4-rows-per-CTA variant of ny = 4096
+inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
-  switch (ny) {
+  switch (variant) {
     case 2048: c = {1024, 4, 128}; return true;
     case 4096: c = {2048, 2, 256}; return true;
-    case 8192: c = {4096, 2, 256}; return true;
+    case 4097: c = {2048, 4, 512}; return true;
+    case 8192: c = {4096, 2, 512}; return true;
     case 16384: c = {8192, 1, 512}; return true;
     default: return false;
   }
@@ -315,8 +312,10 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols)
   fast_cols = 0;
   if (getenv("GFMD_B200_NO_FAST")) return 0;
   FastRowsCfg rc;
-  if (fast_rows_cfg(g.ny, rc) && g.nx_loc % rc.rb == 0) {
-    fast_rows = g.ny;
+  int rv = g.ny;
+  if (g.ny == 4096 && getenv("GFMD_B200_ROWS_RB4") && g.nx_loc % 4 == 0) rv = 4097;
+  if (fast_rows_cfg(rv, rc) && g.nx_loc % rc.rb == 0) {
+    fast_rows = rv;
     cudaError_t e = cudaSuccess;
 #define ROWS_ATTR(NR, RB, T)                                                                              \
   e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
@@ -324,10 +323,11 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols)
   if (e == cudaSuccess)                                                                                   \
     e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                              (int) fast_rows_smem(rc));
-    switch (g.ny) {
+    switch (rv) {
       case 2048: ROWS_ATTR(1024, 4, 128) break;
       case 4096: ROWS_ATTR(2048, 2, 256) break;
-      case 8192: ROWS_ATTR(4096, 2, 256) break;
+      case 4097: ROWS_ATTR(2048, 4, 512) break;
+      case 8192: ROWS_ATTR(4096, 2, 512) break;
       case 16384: ROWS_ATTR(8192, 1, 512) break;
     }
 #undef ROWS_ATTR
@@ -371,7 +371,8 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   switch (variant) {
     case 2048: k_rows_fwd_p2<1024, 4, 128><<<grid, 128, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
     case 4096: k_rows_fwd_p2<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
-    case 8192: k_rows_fwd_p2<4096, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    case 4097: k_rows_fwd_p2<2048, 4, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    case 8192: k_rows_fwd_p2<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
     case 16384: k_rows_fwd_p2<8192, 1, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
     default: return 1;
   }
@@ -389,7 +390,8 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   switch (variant) {
     case 2048: k_rows_inv_p2<1024, 4, 128><<<grid, 128, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
     case 4096: k_rows_inv_p2<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
-    case 8192: k_rows_inv_p2<4096, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    case 4097: k_rows_inv_p2<2048, 4, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    case 8192: k_rows_inv_p2<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
     case 16384: k_rows_inv_p2<8192, 1, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
     default: return 1;
   }
