@@ -75,7 +75,7 @@ def main():
         s.close()
 
     # (b) large grid, specialised kernels: slab result == single-GPU result
-    for nx, ny in [(4096, 2048), (2048, 4096), (4096, 96)]:
+    for nx, ny in [(4096, 2048), (2048, 4096), (4096, 96), (8192, 4096), (16384, 256)]:
         d = 3
         s = new_slab(nx, ny, d)
         for k0 in range(s.kylo, s.kylo + s.nky, 128):

@@ -63,6 +63,8 @@ SIZES = [
     # specialised power-of-two kernels: fused columns (nx 2048/4096, ndof 3), rows (ny 2048..16384)
     (2048, 64, 3), (4096, 32, 3), (64, 2048, 3), (32, 4096, 3), (16, 8192, 3), (8, 16384, 3),
     (2048, 2048, 3),
+    # long columns: top-digit pass in HBM + 4096-point sub-columns
+    (8192, 64, 3), (16384, 32, 3), (8192, 2048, 3),
 ]
 
 

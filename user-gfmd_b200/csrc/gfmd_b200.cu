@@ -235,6 +235,8 @@ struct gfmd_b200 {
   int cols_ld = 0, cols_T = 64;
   size_t cols_smem = 0;
   int fast_rows = 0, fast_cols = 0;   // specialised kernels selected
+  int cols_top = 0;                   // log2(nx / 4096): top-digit pass of long columns
+  DevFft fft_sub;                     // twiddles of the 4096 sub-columns (long columns only)
   int num_sms = 148;
 
   bool phi_set = false;
@@ -350,18 +352,27 @@ int plan(gfmd_b200 *h)
   h->rows_T = t;
 
   // columns
+  {
+    int rc = fast_plan(h->g, h->fast_rows, h->fast_cols, h->cols_top);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast kernel setup failed");
+    if (h->cols_top > 0) {
+      CU(h, build_fft(4096, h->fft_sub));
+      h->bytes += (double) h->fft_sub.bytes;
+    }
+  }
   int cld = h->fft_cols.desc.ld_min;
   if (cld < g.nx) cld = g.nx;
   h->cols_ld = cld;
   h->cols_smem = (size_t) g.d * cld * sizeof(double2);
-  if (h->cols_smem > kMaxSmem)
+  if (h->cols_smem > kMaxSmem && !h->fast_cols)
     return fail(h, GFMD_B200_EUNSUPPORTED,
                 "nx = %d with ndof = %d: a column set (%zu B) exceeds the %zu B of shared memory per "
-                "CTA (long-column path not available in this build)",
+                "CTA (long columns are supported for ndof 3 and nx = 8192 or 16384 only)",
                 g.nx, g.d, h->cols_smem, kMaxSmem);
   tmin = min_threads_for(h->fft_cols.desc.core);
-  if (tmin > 512)
+  if (tmin > 512 && !h->fast_cols)
     return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d: column transform too long for one CTA", g.nx);
+  if (h->fast_cols) h->cols_smem = fast_cols_smem(3, h->fast_cols);
   t = round_up_pow2(g.d * h->fft_cols.desc.core.len / 8);
   if (t < tmin) t = round_up_pow2(tmin);
   if (t < 64) t = 64;
@@ -376,7 +387,7 @@ int plan(gfmd_b200 *h)
     SET_SMEM(k_rows_fwd<false>, h->rows_smem);
     SET_SMEM(k_rows_inv<false>, h->rows_smem);
   }
-  switch (g.d) {
+  if (!h->fast_cols) switch (g.d) {
     case 3: SET_SMEM(k_cols_fused<3>, h->cols_smem); break;
     case 6: SET_SMEM(k_cols_fused<6>, h->cols_smem); break;
     case 9: SET_SMEM(k_cols_fused<9>, h->cols_smem); break;
@@ -384,8 +395,6 @@ int plan(gfmd_b200 *h)
     default: SET_SMEM(k_cols_fused<0>, h->cols_smem); break;
   }
 #undef SET_SMEM
-  int rc = fast_plan(h->g, h->fast_rows, h->fast_cols);
-  if (rc) return fail(h, GFMD_B200_ECUDA, "fast kernel setup failed");
   return 0;
 }
 
@@ -446,7 +455,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess && g.P > 1) ce = dmalloc(h, &h->d_stage2, nstage);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_phi, nphi);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_linf, (size_t) GFMD_B200_MAX_NDOF);
-  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_epart, ((size_t) g.kyb + 1) * kColsNW);
+  if (ce == cudaSuccess) ce = dmalloc(h, &h->d_epart, ((size_t) g.kyb + 1) * kColsNW * 4);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_res, (size_t) 1);
   if (ce == cudaSuccess) ce = cudaMallocHost((void **) &h->h_res, sizeof(StepResults));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_u, 0, sizeof(double) * nxy * g.d);
@@ -454,7 +463,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess) ce = cudaMemset(h->d_stage, 0, sizeof(double2) * nstage);
   if (ce == cudaSuccess && g.P > 1) ce = cudaMemset(h->d_stage2, 0, sizeof(double2) * nstage);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_linf, 0, sizeof(double) * GFMD_B200_MAX_NDOF);
-  if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1) * kColsNW);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1) * kColsNW * 4);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_res, 0, sizeof(StepResults));
   if (ce != cudaSuccess) {
     h->err = std::string("device allocation failed: ") + cudaGetErrorString(ce);
@@ -543,8 +552,9 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   stage_mark(h, 3);
   if (g.nky_loc > 0) {
     if (h->fast_cols) {
-      int rc = fast_cols_fused(h->fast_cols, B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart,
-                               h->d_res, h->num_sms, h->stream, &h->launches);
+      const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
+      int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
+                               h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches);
       if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
     } else {
 #define LAUNCH_COLS(DT)                                                                          \
@@ -561,7 +571,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
       h->launches++;
     }
   }
-  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
   h->launches++;
   stage_mark(h, 4);
   if (g.P > 1) {
@@ -670,16 +680,19 @@ void try_pin(gfmd_b200 *h, const void *p, size_t bytes)
 // the spectrum is digit-reversed (pos) and the planes are interleaved item by item,
 // [pos / 64][(pos & 7) / 2][c][(pos >> 3) & 7][pos & 1], so that the 9 x 16-byte loads of
 // one contraction round of 8 neighbouring threads form one contiguous 1152-byte chunk.
-inline void phi_slot(bool fast, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
+inline void phi_slot(bool fast, int top, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
 {
   if (!fast) {
     off = (size_t) kx;
     cstride = (size_t) nx;
     return;
   }
-  const int pos = p2_freq_to_pos(lognx, kx);
+  // long columns: kx = R k' + q lives in sub-column q (a block of dsq * nx / R doubles)
+  const int q = kx & ((1 << top) - 1), ksub = kx >> top, logsub = lognx - top;
+  const int pos = p2_freq_to_pos(logsub, ksub);
   const int blk = pos >> 6, a = (pos >> 3) & 7, r = pos & 7;
-  off = (size_t) blk * 64 * dsq + (size_t) (r >> 1) * 16 * dsq + (size_t) a * 2 + (r & 1);
+  off = (size_t) q * dsq * ((size_t) nx >> top) + (size_t) blk * 64 * dsq + (size_t) (r >> 1) * 16 * dsq +
+        (size_t) a * 2 + (r & 1);
   cstride = 16;
 }
 
@@ -792,6 +805,7 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   if (h->h_res) cudaFreeHost(h->h_res);
   free_fft(h->fft_rows);
   free_fft(h->fft_cols);
+  free_fft(h->fft_sub);
   for (int i = 0; i <= GFMD_B200_NSTAGES; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -863,7 +877,7 @@ int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised,
         const double *M = phi + 2 * dsq * ((size_t) kx * ny + ky);
         const double *Mn = phi + 2 * dsq * ((size_t) kxn * ny + kyn);
         size_t off, cstride;
-        phi_slot(h->fast_cols != 0, lognx, nx, dsq, kx, off, cstride);
+        phi_slot(h->fast_cols != 0, h->cols_top, lognx, nx, dsq, kx, off, cstride);
         pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     }
@@ -904,7 +918,7 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
       for (int kx = 0; kx < nx; ++kx) {
         const double *M = phi + 2 * dsq * ((size_t) kx * nky + k0 + kl);
         size_t off, cstride;
-        phi_slot(h->fast_cols != 0, lognx, nx, dsq, kx, off, cstride);
+        phi_slot(h->fast_cols != 0, h->cols_top, lognx, nx, dsq, kx, off, cstride);
         pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     CU(h, cudaMemcpy(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),

@@ -1,4 +1,4 @@
-// Fused column kernel, 16-warp / low-register variant (ndof 3, nx = 4096):
+// Fused column kernel, 16-warp / low-register variant (ndof 3, sub-column length 4096):
 // x-FFT + Phi(q).u(q) + energy + gamma point + x-IFFT with one column set
 // (3 x 4096 complex = 192 KB) resident in shared memory.
 //
@@ -7,6 +7,13 @@
 // L2/DRAM latency.  The three dofs go through a two-deep register pipeline in
 // every pass, and in the contraction dofs 0 and 1 stay in registers while dof 2
 // is kept in place in shared memory (same thread, no barrier).
+//
+// Long columns (nx = 8192, 16384): the column transform is split once more,
+// decimation in frequency over the top digit (radix R = nx / 4096):
+//   k_cols_top_pass<-1>  y_q[n] = (sum_r x[r*4096 + n] w_R^{rq}) w_nx^{qn}, in place in HBM
+//   k_cols_fused_p2_lr   on the R * nky "virtual columns" (ky, q) of length 4096, which
+//                        hold the frequencies kx = R k' + q
+//   k_cols_top_pass<+1>  the transposed step on the way back.
 #pragma once
 
 #include "fft_pow2.cuh"
@@ -28,40 +35,48 @@ __device__ long long g_phase_cycles[16];
 #define PHASE_MARK(i)
 #endif
 
-// LP = log2(number of slab ranks): the column of dof a is made of 2^LP pieces of
-// nx_loc = N >> LP elements, piece p at sin + ((p*D + a)*kyb + kl) * nx_loc.  The piece of
-// a butterfly element is known at compile time (offset >> LNXL), so addresses are one
-// base pointer per dof plus constants.
+// LP = log2(pieces per 4096-element sub-column) = max(0, 12 - log2(nx_loc)): element
+// x = x0 + xi of dof a lives in source-rank piece p = x / nx_loc at
+// ((p*D + a)*kyb + kl) * nx_loc + x % nx_loc.  The piece of a butterfly element relative to
+// the first one is known at compile time (offset >> LNXLC).
 template <int N, int T, int LP>
 __global__ void __launch_bounds__(T, 1)
-k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g,
+k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, int lnxl, int ltop,
                    const double2 *__restrict__ tw, const double *__restrict__ phi,
                    const double *__restrict__ linf, double *__restrict__ epart, StepResults *res)
 {
   constexpr int D = 3;
   constexpr int NW = T / 32;
-  constexpr int LNXL = P2<N>::LOG - LP;
-  constexpr int XMASK = (1 << LNXL) - 1;
+  constexpr int LNXLC = P2<N>::LOG - LP;                      // min(log2 N, lnxl)
+  constexpr int XMASK = (1 << LNXLC) - 1;
   extern __shared__ double2 sm[];
   double2 *tws = sm + D * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t pstride = ((size_t) D * g.kyb) << LNXL;      // elements between pieces of one dof
+  const size_t pstride = ((size_t) D * g.kyb) << lnxl;        // elements between pieces of one dof
+  const size_t dstride = ((size_t) g.kyb) << lnxl;            // elements between dofs of one piece
+  const int nvc = g.nky_loc << ltop;                          // virtual columns (ky, q)
   p2_fill_tws<N>(tws, tw);
   __syncthreads();
+
+  auto column_base = [&](int vc) -> size_t {
+    const int kl = vc >> ltop;
+    const int x0 = (vc & ((1 << ltop) - 1)) << P2<N>::LOG;
+    const int p0 = x0 >> lnxl;
+    return ((((size_t) p0 * D) * g.kyb + kl) << lnxl) + (size_t) (x0 & ((1 << lnxl) - 1));
+  };
 
 #ifdef GFMD_PHASE_TIMING
   long long tprev__ = clock64();
 #endif
-  for (int kl = blockIdx.x; kl < g.nky_loc; kl += gridDim.x) {
-    const int ky = g.ky0 + kl;
-    const size_t col0 = ((size_t) kl) << LNXL;
-    const size_t dstride = ((size_t) g.kyb) << LNXL;          // elements between dofs of one piece
+  for (int vc = blockIdx.x; vc < nvc; vc += gridDim.x) {
+    const int ky = g.ky0 + (vc >> ltop);
+    const size_t col0 = column_base(vc);
     auto addr = [&](int a, int base, int off) -> size_t {
-      return col0 + a * dstride + (size_t) (off >> LNXL) * pstride + (size_t) ((off & XMASK) + base);
+      return col0 + a * dstride + (size_t) (off >> LNXLC) * pstride + (size_t) ((off & XMASK) + base);
     };
-    const double *ph = phi + (size_t) kl * D * D * N;
+    const double *ph = phi + (size_t) vc * D * D * N;
 
-    // ---- group A forward: pass 0 straight from global memory
+    // ---- pass 0 straight from global memory (block-wide mapping: full 128-byte lines)
     p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) { return sin[addr(a, base, off)]; });
     __syncthreads();
     PHASE_MARK(0);
@@ -70,8 +85,8 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     __syncthreads();
     PHASE_MARK(2);
     // just-in-time L2 prefetch of this column's Phi planes (contiguous D*D*N doubles): the DRAM
-    // fetch runs while the in-shared-memory passes compute; a much longer distance would be
-    // evicted by the streaming traffic of the other SMs before use
+    // fetch runs while the stride-8 pass computes; a much longer distance would be evicted by
+    // the streaming traffic of the other SMs before use
     for (int i = threadIdx.x; i < D * D * N / 16; i += T) prefetch_l2(ph + (size_t) i * 16);
 
     // ---- group B forward, contraction, group B backward
@@ -119,7 +134,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
             F[i] = make_double2(-F[i].x, -F[i].y);
           }
           e = fma(wgt, eq, e);
-          if (ky == 0 && pos + r == 0) {            // gamma point: kx = 0 sits at position 0
+          if (vc == 0 && g.ky0 == 0 && pos + r == 0) {   // gamma point: kx = 0 is position 0 of (ky 0, q 0)
 #pragma unroll
             for (int i = 0; i < D; ++i) res->u0[i] = uv[i].x;
             res->egamma = -2.0 * linf[0] * uv[2].x;
@@ -148,17 +163,18 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     // energy partial of this warp (fixed order -> deterministic)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-    if (lane == 0) epart[(size_t) kl * NW + warp] = e;
+    if (lane == 0) epart[(size_t) vc * NW + warp] = e;
     __syncthreads();
     PHASE_MARK(6);
     // next column's data -> L2 while the backward passes run
-    if (kl + (int) gridDim.x < g.nky_loc) {
-      const size_t ncol0 = ((size_t) (kl + gridDim.x)) << LNXL;
+    if (vc + (int) gridDim.x < nvc) {
+      const size_t ncol0 = column_base(vc + gridDim.x);
       for (int i = threadIdx.x; i < D * N / 8; i += T) {
         const int a = i / (N / 8), x = (i - a * (N / 8)) * 8;
-        prefetch_l2(sin + ncol0 + a * dstride + (size_t) (x >> LNXL) * pstride + (size_t) (x & XMASK));
+        prefetch_l2(sin + ncol0 + a * dstride + (size_t) (x >> LNXLC) * pstride + (size_t) (x & XMASK));
       }
     }
+
     // ---- group A backward, last pass straight to global memory
     p2_groupA_rest_seq<N, NW, +1, D, 0>(sm, tw, tws, lane, warp);
     __syncthreads();
@@ -167,6 +183,43 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
                                  [&](int a, int base, int off, double2 v) { sout[addr(a, base, off)] = v; });
     PHASE_MARK(8);
     // no barrier: the next column's pass 0 writes exactly what this thread just read
+  }
+}
+
+// Top-digit pass of a long column transform, in place in the staging buffer.
+// One thread per (dof, kl, n), n < S = nx >> LR; elements x = n + r*S, r < R = 2^LR.
+template <int LR, int DIR>
+__global__ void __launch_bounds__(256)
+k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx)
+{
+  constexpr int R = 1 << LR;
+  const int S = g.nx >> LR;
+  const int xmask = (1 << lnxl) - 1;
+  const long long total = (long long) g.d * g.nky_loc * S;
+  for (long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long) gridDim.x * blockDim.x) {
+    const int n = (int) (idx % S);
+    const int col = (int) (idx / S);
+    const int dof = col % g.d, kl = col / g.d;
+    double2 v[R];
+    size_t a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int x = n + r * S;
+      a[r] = ((((size_t) (x >> lnxl) * g.d + dof) * g.kyb + kl) << lnxl) + (size_t) (x & xmask);
+      v[r] = stage[a[r]];
+    }
+    if (DIR > 0) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw_nx + (size_t) q * n));
+    }
+    Butterfly<R, DIR>::run(v);
+    if (DIR < 0) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw_nx + (size_t) q * n));
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) stage[a[r]] = v[r];
   }
 }
 

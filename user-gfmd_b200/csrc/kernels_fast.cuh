@@ -306,7 +306,7 @@ inline int ilog2_rt(int n)
 }
 
 // returns 0 on success; fast_rows / fast_cols = 0 (generic kernels) or the variant id
-inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols)
+inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &cols_top)
 {
   fast_rows = 0;
   fast_cols = 0;
@@ -333,29 +333,30 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols)
 #undef ROWS_ATTR
     if (e != cudaSuccess) return 1;
   }
+  cols_top = 0;
   const bool p2ranks = (g.P & (g.P - 1)) == 0;
-  if (g.d == 3 && p2ranks && (g.nx == 2048 || g.nx == 4096) && g.nx_loc >= 64) {
-    fast_cols = g.nx;
+  if (g.d == 3 && p2ranks && g.nx == 2048 && g.nx_loc >= 64) {
+    fast_cols = 2048;
+    if (cudaFuncSetAttribute(k_cols_fused_p2<3, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) fast_cols_smem(3, 2048)) != cudaSuccess)
+      return 1;
+  } else if (g.d == 3 && p2ranks && (g.nx == 4096 || g.nx == 8192 || g.nx == 16384) && g.nx_loc >= 512) {
+    // sub-columns of 4096; nx = 8192 / 16384 add one top-digit pass in HBM (kernel_cols_lr.cuh)
+    fast_cols = 4096;
+    cols_top = ilog2_rt(g.nx) - 12;
+    const int lnxl = ilog2_rt(g.nx_loc);
+    const int lp = lnxl >= 12 ? 0 : 12 - lnxl;
     cudaError_t e = cudaSuccess;
-#define COLS_ATTR(N)                                                                                      \
-  e = cudaFuncSetAttribute(k_cols_fused_p2<3, N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                           (int) fast_cols_smem(3, N));
-    switch (g.nx) {
-      case 2048: COLS_ATTR(2048) break;
-      case 4096:
-        switch (g.P) {
-#define LR_ATTR(LP, PP)                                                                                    \
-  case PP:                                                                                                 \
+    switch (lp) {
+#define LR_ATTR(LP)                                                                                          \
+  case LP:                                                                                                   \
     e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int) fast_cols_smem(3, 4096));                                               \
+                             (int) fast_cols_smem(3, 4096));                                                 \
     break;
-          LR_ATTR(0, 1) LR_ATTR(1, 2) LR_ATTR(2, 4) LR_ATTR(3, 8)
+      LR_ATTR(0) LR_ATTR(1) LR_ATTR(2) LR_ATTR(3)
 #undef LR_ATTR
-          default: fast_cols = 0; break;
-        }
-        break;
+      default: fast_cols = 0; cols_top = 0; break;
     }
-#undef COLS_ATTR
     if (e != cudaSuccess) return 1;
   }
   return 0;
@@ -399,22 +400,37 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   return 0;
 }
 
-inline int fast_cols_fused(int variant, const double2 *sin, double2 *sout, const GridDesc &g, const FftDesc &fd,
-                           const double *phi, const double *linf, double *epart, StepResults *res,
-                           int num_sms, cudaStream_t s, long long *launches)
+// sin: staging buffer holding the received columns, sout: where the result columns go
+// (the same buffer on a single GPU).  tw_sub: twiddles of the in-shared-memory length
+// (2048 or 4096); tw_nx: twiddles of the full column length (top pass only).
+inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, const GridDesc &g,
+                           const double2 *tw_sub, const double2 *tw_nx, const double *phi, const double *linf,
+                           double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches)
 {
-  const int grid = g.nky_loc < num_sms ? g.nky_loc : num_sms;
+  const int nvc = g.nky_loc << top;
+  const int grid = nvc < num_sms ? nvc : num_sms;
   const int lnxl = ilog2_rt(g.nx_loc);
   const size_t smem = fast_cols_smem(3, variant);
+  const long long top_items = (long long) g.d * g.nky_loc * (g.nx >> top);
+  const int top_grid = (int) ((top_items + 255) / 256 < (long long) num_sms * 8 ? (top_items + 255) / 256
+                                                                                : (long long) num_sms * 8);
+  if (top == 1) {
+    k_cols_top_pass<1, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx);
+    ++*launches;
+  } else if (top == 2) {
+    k_cols_top_pass<2, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx);
+    ++*launches;
+  }
   switch (variant) {
     case 2048:
-      k_cols_fused_p2<3, 2048, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, fd.core.tw, phi, linf, epart, res);
+      k_cols_fused_p2<3, 2048, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, tw_sub, phi, linf, epart, res);
       break;
     case 4096:
-      switch (12 - lnxl) {
-#define LR_LAUNCH(LP)                                                                                           \
-  case LP:                                                                                                      \
-    k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, fd.core.tw, phi, linf, epart, res); \
+      switch (lnxl >= 12 ? 0 : 12 - lnxl) {
+#define LR_LAUNCH(LP)                                                                                       \
+  case LP:                                                                                                  \
+    k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, tw_sub, phi, linf,   \
+                                                              epart, res);                                  \
     break;
         LR_LAUNCH(0) LR_LAUNCH(1) LR_LAUNCH(2) LR_LAUNCH(3)
 #undef LR_LAUNCH
@@ -424,6 +440,13 @@ inline int fast_cols_fused(int variant, const double2 *sin, double2 *sout, const
     default: return 1;
   }
   ++*launches;
+  if (top == 1) {
+    k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx);
+    ++*launches;
+  } else if (top == 2) {
+    k_cols_top_pass<2, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx);
+    ++*launches;
+  }
   return 0;
 }
 
