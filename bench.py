@@ -47,9 +47,15 @@ def parse():
     return ap.parse_args()
 
 
+# weak scaling: 4096 x 4096 cells per GPU ("4096^2 -> 16384^2 surface, slab-sharded over 8 x B200")
+WEAK_GRIDS = {1: (4096, 4096), 2: (8192, 4096), 4: (8192, 8192), 8: (16384, 8192)}
+
+
 def workload(args):
-    n = args.grid if args.grid > 0 else 4096
-    return n, n, 3
+    if args.grid > 0:
+        return args.grid, args.grid, 3
+    nx, ny = WEAK_GRIDS.get(args.gpus, (4096, 4096))
+    return nx, ny, 3
 
 
 def measured_peaks():
@@ -175,7 +181,7 @@ def main_reference(args):
     r = reference_run(nx, ny, d, args.steps, args.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d" % (nx, ny, d),
                       "step": "GFMDSolver::post_force(u_xy, f_xy) on host arrays"},
@@ -306,6 +312,15 @@ def main_b200(args):
                 "solver_bytes_per_step": (80 * d + 4 * d * d) * cells_loc,
                 "solver_frac": ((80 * d + 4 * d * d) * cells_loc / (ms_solver * 1e-3) / 1e9) / peaks["hbm_gbs"]}
 
+    nvlink = None
+    if world > 1:
+        per_dir = 8.0 * d * cells_loc * (world - 1) / world          # bytes sent per GPU per transpose
+        t_x = (stage_ms["exchange_fwd"] + stage_ms["exchange_inv"]) * 1e-3
+        nvlink = {"bytes_out_per_gpu_per_step": 2 * per_dir, "exchange_ms": t_x * 1e3,
+                  "achieved_gbs_per_dir": (2 * per_dir / t_x / 1e9) if t_x > 0 else None,
+                  "peak_gbs_per_dir": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
+                  "note": "exchange_inv includes the u0 all-reduce"}
+
     # end to end through the plugin boundary with pinned host buffers
     n_e2e = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, 10))
     hu = torch.tensor(u.reshape(d, nx_loc * ny)).pin_memory()
@@ -338,7 +353,7 @@ def main_b200(args):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d, 1 atom/cell" % (nx, ny, d),
                           "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",
                           "decomposition": "x-slabs over %d GPU(s), NCCL all-to-all transposes" % world,
@@ -346,7 +361,7 @@ def main_b200(args):
                                 ((nat * (48 + 16 + 24) + 2 * grid_bytes) / 1e6),
                           "kernels": s.describe()},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-               "cpu_baseline": cpu,
+               "cpu_baseline": cpu, "nvlink": nvlink,
                "solver_only": {"value": 1e3 / ms_solver, "unit": UNIT, "ms_per_step": ms_solver},
                "stage_ms": stage_ms, "epot": res["epot"]}
         print(json.dumps(out))

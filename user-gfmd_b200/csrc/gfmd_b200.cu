@@ -473,14 +473,26 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   h->phi_cols_set.assign(g.nky_loc > 0 ? g.nky_loc : 0, 0);
   for (int i = 0; i <= GFMD_B200_NSTAGES; ++i) cudaEventCreate(&h->ev[i]);
 
-  char buf[512];
-  snprintf(buf, sizeof(buf),
-           "grid %dx%d ndof %d rank %d/%d | rows: %s len %d%s RB %d T %d smem %zu%s | cols: len %d%s T %d "
-           "smem %zu%s",
-           nx, ny, ndof, rank, nranks, h->even ? "half-length" : "full-length", h->fft_rows.desc.n,
-           h->fft_rows.desc.bluestein ? " (bluestein)" : "", h->rows_RB, h->rows_T, h->rows_smem,
-           h->fast_rows ? " [fast]" : "", h->fft_cols.desc.n, h->fft_cols.desc.bluestein ? " (bluestein)" : "",
-           h->cols_T, h->cols_smem, h->fast_cols ? " [fast]" : "");
+  char rows[160], cols[200], buf[512];
+  FastRowsCfg frc;
+  if (h->fast_rows && fast_rows_cfg(h->fast_rows, frc))
+    snprintf(rows, sizeof(rows), "k_rows_*_p2 half-length len %d, %d rows/CTA, %d threads, smem %zu [fast]",
+             frc.nr, frc.rb, frc.t, fast_rows_smem(frc));
+  else
+    snprintf(rows, sizeof(rows), "k_rows_* %s len %d%s, %d rows/CTA, %d threads, smem %zu",
+             h->even ? "half-length" : "full-length", h->fft_rows.desc.n,
+             h->fft_rows.desc.bluestein ? " (bluestein)" : "", h->rows_RB, h->rows_T, h->rows_smem);
+  if (h->fast_cols == 4096)
+    snprintf(cols, sizeof(cols), "k_cols_fused_p2_lr sub-column 4096 x %d (top radix %d in HBM), 512 threads, "
+             "smem %zu [fast]", 1 << h->cols_top, 1 << h->cols_top, h->cols_smem);
+  else if (h->fast_cols)
+    snprintf(cols, sizeof(cols), "k_cols_fused_p2 len %d, 256 threads, smem %zu [fast]", h->fast_cols,
+             h->cols_smem);
+  else
+    snprintf(cols, sizeof(cols), "k_cols_fused len %d%s, %d threads, smem %zu", h->fft_cols.desc.n,
+             h->fft_cols.desc.bluestein ? " (bluestein)" : "", h->cols_T, h->cols_smem);
+  snprintf(buf, sizeof(buf), "grid %dx%d ndof %d rank %d/%d | rows: %s | cols: %s", nx, ny, ndof, rank, nranks,
+           rows, cols);
   h->desc = buf;
   *out = h;
   return 0;
