@@ -524,8 +524,12 @@ int exchange(gfmd_b200 *h, const double2 *src, double2 *dst)
   if (!h->comm) return fail(h, GFMD_B200_ESTATE, "slab handle used before gfmd_b200_comm_init");
   const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;   // complex elements per peer block
   NcclApi &a = nccl();
+  // own block: plain device copy; peers: grouped NCCL send/recv over NVLink
+  CU(h, cudaMemcpyAsync(dst + g.rank * blk, src + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
+                        h->stream));
   NC(h, a.GroupStart());
   for (int r = 0; r < g.P; ++r) {
+    if (r == g.rank) continue;
     NC(h, a.Send(src + r * blk, blk * 2, ncclDouble, r, h->comm, h->stream));
     NC(h, a.Recv(dst + r * blk, blk * 2, ncclDouble, r, h->comm, h->stream));
   }

@@ -1,0 +1,195 @@
+/* Host glue of `solver static/b200`: see gfmd_solver_b200.h.  Mirrors, call by call,
+ * what GFMDSolverStatic does (reference src/solvers/gfmd_solver_static.cpp):
+ *
+ *   ctor            :47-62    name, optional solver arguments
+ *   set_grid_size   :79-87    -> gfmd_b200_create[_slab]; the brick comes from the library
+ *   set_kernel      :90-136   fill_phi_buffer for this rank's q columns -> gfmd_b200_set_phi_columns,
+ *                             kernel->get_force_at_gamma_point -> gfmd_b200_set_linf, same warning
+ *   post_force      :145-249  -> gfmd_b200_post_force_host (u_xy/f_xy are the fix's host arrays)
+ */
+#include <numeric>
+#include <string.h>
+#include <stdlib.h>
+
+#include "gfmd_solver_b200.h"
+
+#include "pointers.h"
+#include "comm.h"
+#include "domain.h"
+#include "memory.h"
+#include "mpi.h"
+
+#include "gfmd_misc.h"
+#include "gfmd_b200.h"
+
+using namespace LAMMPS_NS;
+
+GFMDSolverB200::GFMDSolverB200(LAMMPS *lmp, int narg, int *iarg, char **arg)
+  : GFMDSolver(lmp), handle_(NULL), device_(-1), async_(true)
+{
+  strcpy(name, "static/b200");
+
+  /* optional: `solver static/b200 device <id>` and `sync` (no launch from pre_force) */
+  while (narg > 0 && *iarg < narg) {
+    if (!strcmp(arg[*iarg], "device") && *iarg + 1 < narg) {
+      device_ = atoi(arg[*iarg + 1]);
+      (*iarg) += 2;
+    }
+    else if (!strcmp(arg[*iarg], "sync")) {
+      async_ = false;
+      (*iarg)++;
+    }
+    else break;
+  }
+}
+
+
+GFMDSolverB200::~GFMDSolverB200()
+{
+  if (handle_) gfmd_b200_destroy(handle_);
+}
+
+
+void GFMDSolverB200::check(int rc, const char *what)
+{
+  if (rc) {
+    char errstr[1280];
+    snprintf(errstr, sizeof(errstr), "fix gfmd solver static/b200: %s failed: %s", what,
+             gfmd_b200_last_error(handle_));
+    error->one(FLERR, errstr);
+  }
+}
+
+
+void GFMDSolverB200::set_grid_size(int in_nx, int in_ny, int in_ndof)
+{
+  nx = in_nx;
+  ny = in_ny;
+  nu_ = in_ndof/3;
+  ndof = in_ndof;
+  ndof_sq = ndof*ndof;
+
+  if (u0) delete [] u0;
+  u0 = new double[ndof];
+
+  /* The B200 path decomposes the grid into x-slabs, one per rank (procgrid = P x 1 x 1,
+     which is what fix gfmd requires anyway for z: src/main/fix_gfmd.cpp:167-170). */
+  if (comm->procgrid[1] != 1 || comm->procgrid[2] != 1)
+    error->all(FLERR,"fix gfmd solver static/b200 needs a processor grid of P x 1 x 1 "
+               "(use 'processors * 1 1').");
+
+  int dev = device_;
+  if (dev < 0) {
+    const char *lr = getenv("OMPI_COMM_WORLD_LOCAL_RANK");
+    if (!lr) lr = getenv("MV2_COMM_WORLD_LOCAL_RANK");
+    if (!lr) lr = getenv("SLURM_LOCALID");
+    dev = lr ? atoi(lr) : 0;
+  }
+
+  if (handle_) gfmd_b200_destroy(handle_);
+  handle_ = NULL;
+  if (nprocs == 1) {
+    check(gfmd_b200_create(&handle_, nx, ny, ndof, dev), "gfmd_b200_create");
+  }
+  else {
+    check(gfmd_b200_create_slab(&handle_, nx, ny, ndof, dev, me, nprocs), "gfmd_b200_create_slab");
+    char id[GFMD_B200_UNIQUE_ID_BYTES];
+    if (me == 0) check(gfmd_b200_get_unique_id(id), "gfmd_b200_get_unique_id");
+    MPI_Bcast(id, GFMD_B200_UNIQUE_ID_BYTES, MPI_CHAR, 0, world);
+    check(gfmd_b200_comm_init(handle_, id), "gfmd_b200_comm_init");
+  }
+
+  check(gfmd_b200_get_brick(handle_, &xlo_loc, &xhi_loc, &ylo_loc, &yhi_loc, &nxy_loc, &gammai_),
+        "gfmd_b200_get_brick");
+  nx_loc = xhi_loc-xlo_loc+1;
+  ny_loc = yhi_loc-ylo_loc+1;
+
+  /* the brick of the library must be the one LAMMPS' decomposition implies
+     (src/main/gfmd_solver.cpp:95-99) or atoms and grid would not line up */
+  int xlo_ref = (int) round(nx*(domain->sublo[0]-domain->boxlo[0])/domain->xprd);
+  int xhi_ref = (int) round(nx*(domain->subhi[0]-domain->boxlo[0])/domain->xprd)-1;
+  if (xlo_ref != xlo_loc || xhi_ref != xhi_loc) {
+    char errstr[256];
+    snprintf(errstr, sizeof(errstr), "fix gfmd solver static/b200: LAMMPS sub-domain maps to grid rows "
+             "%i..%i but the slab decomposition assigns %i..%i; use a uniform decomposition with nx "
+             "divisible by the number of ranks.", xlo_ref, xhi_ref, xlo_loc, xhi_loc);
+    error->one(FLERR, errstr);
+  }
+
+  gfmd_b200_pin_host_buffers(handle_, 1);   /* u_xy / f_xy live as long as the fix */
+}
+
+
+void GFMDSolverB200::init()
+{
+}
+
+
+void GFMDSolverB200::set_kernel(StiffnessKernel *kernel, bool normalize)
+{
+  if (screen && comm->me == 0)
+    fprintf(screen, "USER-GFMD: Computing stiffness matrices...\n");
+
+  /*
+   * Stiffness matrices for the q columns this rank owns after the transpose:
+   * all kx, kylo <= ky < kylo+nky of the half spectrum.  Streamed in chunks.
+   */
+  int kylo, nky;
+  check(gfmd_b200_get_q_columns(handle_, &kylo, &nky), "gfmd_b200_get_q_columns");
+  const int chunk = 32;
+  double_complex **phi = NULL;
+  for (int k0 = 0; k0 < nky; k0 += chunk) {
+    int nk = MIN(chunk, nky-k0);
+    memory->create(phi, nx*nk, ndof_sq, "GFMDSolverB200::phi");
+    fill_phi_buffer(ndof, nx, 0, nx-1, ny, kylo+k0, kylo+k0+nk-1, kernel, phi, normalize, error);
+    check(gfmd_b200_set_phi_columns(handle_, reinterpret_cast<double*>(phi[0]), kylo+k0, nk,
+                                    normalize ? 1 : 0), "gfmd_b200_set_phi_columns");
+    memory->destroy(phi);
+  }
+
+  /*
+   * Linear force contributions, with the reference's sanity check
+   * (src/solvers/gfmd_solver_static.cpp:107-122)
+   */
+  double *linf = new double[nu_];
+  kernel->get_force_at_gamma_point(linf);
+  if (std::abs(std::accumulate(linf, linf+nu_, 0.0)) > 1e-6 && screen) {
+    fprintf(screen, "USER-GFMD: Warning: Forces do not sum to zero at the "
+            "surface. Sum is = %e.\n", std::accumulate(linf, linf+nu_, 0.0));
+  }
+  check(gfmd_b200_set_linf(handle_, linf), "gfmd_b200_set_linf");
+  delete [] linf;
+
+  if (screen && comm->me == 0)
+    fprintf(screen, "USER-GFMD: ...done\n");
+}
+
+
+void GFMDSolverB200::pre_force(void *input_buffer_ptr, void *)
+{
+  if (!async_) return;
+  double **input_buffer = static_cast<double**>(input_buffer_ptr);
+  check(gfmd_b200_pre_force_async_host(handle_, input_buffer[0]), "gfmd_b200_pre_force_async_host");
+}
+
+
+double GFMDSolverB200::post_force(void *input_buffer_ptr, void *output_buffer_ptr, char *dump_prefix)
+{
+  double **input_buffer = static_cast<double**>(input_buffer_ptr);
+  double **output_buffer = static_cast<double**>(output_buffer_ptr);
+
+  if (dump_prefix)
+    error->all(FLERR,"fix gfmd solver static/b200: q-space dumps (dumpq_every) are not "
+               "available; use 'solver static' on dump steps.");
+
+  double epot;
+  check(gfmd_b200_post_force_host(handle_, input_buffer[0], output_buffer[0], &epot, u0),
+        "gfmd_b200_post_force_host");
+  return epot;
+}
+
+
+double GFMDSolverB200::memory_usage()
+{
+  return handle_ ? gfmd_b200_memory_usage(handle_) : 0.0;
+}
