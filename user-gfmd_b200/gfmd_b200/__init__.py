@@ -332,3 +332,23 @@ def gfmd_solver_factory(keyword=None, **kw):
     if name not in ("static/b200", "b200"):
         raise GFMDError(1, "Unknown solver name encountered.")
     return GFMDSolverB200(**kw)
+
+
+def slab_plan(nx, ny, ndof, rank, nranks):
+    """The x-slab / ky-slab decomposition the library uses (create_common in
+    csrc/gfmd_b200.cu), for hosts that place atoms and stiffness tables per rank.
+
+    Real space: rank r owns rows [x0, x0 + nx_loc) (the reference's brick for
+    procgrid = P x 1 x 1, src/main/gfmd_solver.cpp:95-101).  After the transpose it owns
+    the half-spectrum columns ky in [ky0, ky0 + nky_loc), all kx.  The exchange buffers are
+    [P][ndof][kyb][nx_loc] complex: block p is what goes to / comes from rank p."""
+    if nx % nranks:
+        raise GFMDError(4, "nx = %d not divisible by %d slab ranks" % (nx, nranks))
+    nyh = ny // 2 + 1
+    kyb = (nyh + nranks - 1) // nranks
+    ky0 = rank * kyb
+    nky_loc = max(0, min(kyb, nyh - ky0))
+    nx_loc = nx // nranks
+    return dict(nx_loc=nx_loc, x0=rank * nx_loc, nyh=nyh, kyb=kyb, ky0=ky0, nky_loc=nky_loc,
+                block_elems=ndof * kyb * nx_loc, gamma_rank=0,
+                ky_weights=[1.0 if (k == 0 or 2 * k == ny) else 2.0 for k in range(ky0, ky0 + nky_loc)])
