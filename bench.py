@@ -218,6 +218,13 @@ def main_b200(args):
     nx, ny, d = workload(args)
     s = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world, unique_id=uid)
     s.set_grid_size(nx, ny, d)
+    exchange = "none (single GPU)"
+    if world > 1:
+        try:
+            s.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(dev, world))
+            exchange = "CUDA IPC peer pushes over NVLink (copy engines) + NCCL barrier"
+        except gfmd_b200.GFMDError as ex:          # still a GPU path: grouped ncclSend/ncclRecv
+            exchange = "NCCL send/recv (peer copy unavailable: %s)" % ex
     # stiffness table for this rank's q columns (closed form, see synthetic.phi_columns)
     for k0 in range(s.kylo, s.kylo + s.nky, 128):
         nk = min(128, s.kylo + s.nky - k0)
@@ -356,7 +363,7 @@ def main_b200(args):
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d, 1 atom/cell" % (nx, ny, d),
                           "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",
-                          "decomposition": "x-slabs over %d GPU(s), NCCL all-to-all transposes" % world,
+                          "decomposition": "x-slabs over %d GPU(s); transposes: %s" % (world, exchange),
                           "l2": "inputs larger than L2 (%.0f MB of atoms+grids per step)" %
                                 ((nat * (48 + 16 + 24) + 2 * grid_bytes) / 1e6),
                           "kernels": s.describe()},

@@ -65,6 +65,15 @@ int gfmd_b200_create_slab(gfmd_b200_t **h, int nx, int ny, int ndof, int device,
 int gfmd_b200_get_unique_id(char id[GFMD_B200_UNIQUE_ID_BYTES]);
 int gfmd_b200_comm_init(gfmd_b200_t *h, const char id[GFMD_B200_UNIQUE_ID_BYTES]);
 
+/* Optional, after comm_init: replace the NCCL send/recv transposes by direct pushes into
+ * the peers' receive buffers over NVLink (CUDA IPC + copy engines; NCCL then only provides
+ * the barrier).  Every rank exports two 64-byte memory handles, the HOST gathers the
+ * 2*64*nranks bytes in rank order (MPI_Allgather / torch.distributed.all_gather) and every
+ * rank imports them.  All GPUs must be visible to every process (peer access). */
+#define GFMD_B200_IPC_HANDLE_BYTES 64
+int gfmd_b200_ipc_export(gfmd_b200_t *h, char *handles /* [2][64] */);
+int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles /* [nranks][2][64] */);
+
 void gfmd_b200_destroy(gfmd_b200_t *h);
 
 /* Last error message of this handle (or of the failed create when h == NULL). */

@@ -12,6 +12,7 @@ grids={1:(4096,4096),2:(8192,4096),4:(8192,8192),8:(16384,8192)}
 nx,ny=grids[world]; d=3
 s=gfmd_b200.GFMDSolverB200(device=local,rank=rank,nranks=world,unique_id=bytes(b.cpu().numpy().tobytes()))
 s.set_grid_size(nx,ny,d)
+if os.environ.get('EXCH','ipc')=='ipc': s.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(dev,world))
 for k0 in range(s.kylo,s.kylo+s.nky,128):
     nk=min(128,s.kylo+s.nky-k0); s.set_kernel_columns(synthetic.phi_columns(nx,ny,k0,nk),k0,normalized=False)
 s.set_linf(np.zeros(1))

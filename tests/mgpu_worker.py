@@ -35,6 +35,10 @@ def main():
     s = None
     ok = True
 
+    peer_copy = os.environ.get("GFMD_TEST_EXCHANGE", "ipc") == "ipc"
+    if rank == 0:
+        print("exchange:", "CUDA IPC peer copies + NCCL barrier" if peer_copy else "NCCL send/recv", flush=True)
+
     def new_slab(nx, ny, d):
         nonlocal uid
         # a fresh communicator per solver: rank 0 hands out a new id
@@ -45,6 +49,8 @@ def main():
         sl = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world,
                                       unique_id=bytes(b.cpu().numpy().tobytes()))
         sl.set_grid_size(nx, ny, d)
+        if peer_copy:
+            sl.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(dev, world))
         return sl
 
     # (a) golden vectors through the slab path (generic kernels)

@@ -221,7 +221,14 @@ struct gfmd_b200 {
   bool own_stream = false;
 
   double *d_u = nullptr, *d_f = nullptr;
-  double2 *d_stage = nullptr, *d_stage2 = nullptr;
+  double2 *d_stage = nullptr, *d_stage2 = nullptr, *d_stage3 = nullptr;
+  // peer-copy exchange over CUDA IPC (gfmd_b200_ipc_export / _import)
+  static constexpr int kMaxRanks = 16;
+  bool ipc_on = false;
+  double2 *peer_recv[2][kMaxRanks] = {};      // peers' receive buffers (forward, return), mapped here
+  cudaStream_t copy_stream[kMaxRanks] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxRanks] = {};
+  double *d_barrier = nullptr;
   double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
   int fsum_part_cap = 0;
   StepResults *d_res = nullptr, *h_res = nullptr;
@@ -408,6 +415,8 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
                 GFMD_B200_MAX_NDOF);
   if (nranks < 1 || rank < 0 || rank >= nranks)
     return fail(nullptr, GFMD_B200_EINVAL, "rank %d of %d invalid", rank, nranks);
+  if (nranks > gfmd_b200::kMaxRanks)
+    return fail(nullptr, GFMD_B200_EUNSUPPORTED, "at most %d slab ranks", gfmd_b200::kMaxRanks);
   if (nx % nranks != 0)
     return fail(nullptr, GFMD_B200_EUNSUPPORTED, "nx = %d not divisible by %d slab ranks", nx, nranks);
   int ndev = 0;
@@ -518,15 +527,38 @@ int atom_blocks(const gfmd_b200 *h, int nall)
   return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
 
-int exchange(gfmd_b200 *h, const double2 *src, double2 *dst)
+// All-to-all of the staging blocks: block r of src goes to rank r, block p of dst comes
+// from rank p.  which = 0 forward transpose, 1 return transpose.
+//
+// Peer-copy path (after gfmd_b200_ipc_import): every rank PUSHES its blocks straight into
+// the peers' receive buffers with copy-engine transfers over NVLink (one stream per peer),
+// then a tiny NCCL all-reduce on the compute stream serves as the cross-rank barrier:
+// it completes only when every rank's pushes, which precede its contribution in stream
+// order, have landed.  Forward and return use different receive buffers, so a buffer is
+// never overwritten before its reader of the previous step has passed a later barrier.
+// Without IPC handles the same exchange is a grouped ncclSend/ncclRecv.
+int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
 {
   const GridDesc &g = h->g;
   if (!h->comm) return fail(h, GFMD_B200_ESTATE, "slab handle used before gfmd_b200_comm_init");
   const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;   // complex elements per peer block
   NcclApi &a = nccl();
-  // own block: plain device copy; peers: grouped NCCL send/recv over NVLink
   CU(h, cudaMemcpyAsync(dst + g.rank * blk, src + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
                         h->stream));
+  if (h->ipc_on) {
+    CU(h, cudaEventRecord(h->ev_fork, h->stream));
+    for (int k = 1; k < g.P; ++k) {
+      const int r = (g.rank + k) % g.P;                 // staggered: no two ranks hit one peer first
+      CU(h, cudaStreamWaitEvent(h->copy_stream[r], h->ev_fork, 0));
+      CU(h, cudaMemcpyAsync(h->peer_recv[which][r] + g.rank * blk, src + r * blk, blk * sizeof(double2),
+                            cudaMemcpyDeviceToDevice, h->copy_stream[r]));
+      CU(h, cudaEventRecord(h->ev_join[r], h->copy_stream[r]));
+      CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[r], 0));
+    }
+    if (which == 0)   // the return transpose is followed by the u0 all-reduce, which is its barrier
+      NC(h, a.AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    return 0;
+  }
   NC(h, a.GroupStart());
   for (int r = 0; r < g.P; ++r) {
     if (r == g.rank) continue;
@@ -543,7 +575,8 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   const GridDesc &g = h->g;
   const int nrow_blocks = g.d * ((g.nx_loc + h->rows_RB - 1) / h->rows_RB);
   double2 *A = h->d_stage;
-  double2 *B = g.P > 1 ? h->d_stage2 : h->d_stage;
+  double2 *B = g.P > 1 ? h->d_stage2 : h->d_stage;                 // columns arrive here
+  double2 *B2 = (g.P > 1 && h->ipc_on) ? h->d_stage3 : B;          // rows arrive here on the way back
 
   CU(h, cudaMemsetAsync(&h->d_res->epot, 0, offsetof(StepResults, fsum), h->stream));
 
@@ -562,7 +595,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   }
   stage_mark(h, 2);
   if (g.P > 1) {
-    int rc = exchange(h, A, B);
+    int rc = exchange(h, A, B, 0);
     if (rc) return rc;
   }
   stage_mark(h, 3);
@@ -591,22 +624,22 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   h->launches++;
   stage_mark(h, 4);
   if (g.P > 1) {
-    int rc = exchange(h, A, B);
+    int rc = exchange(h, A, B2, 1);
     if (rc) return rc;
     NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
                            h->stream));
   }
   stage_mark(h, 5);
   if (h->fast_rows) {
-    int rc = fast_rows_inv(h->fast_rows, B, d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
+    int rc = fast_rows_inv(h->fast_rows, B2, d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
     if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_inv launch failed");
   } else {
     if (h->even)
       k_rows_inv<true><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(
-          B, d_f, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
+          B2, d_f, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
     else
       k_rows_inv<false><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(
-          B, d_f, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
+          B2, d_f, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
     h->launches++;
   }
   stage_mark(h, 6);
@@ -806,6 +839,63 @@ int gfmd_b200_comm_init(gfmd_b200_t *h, const char id[GFMD_B200_UNIQUE_ID_BYTES]
   return 0;
 }
 
+int gfmd_b200_ipc_export(gfmd_b200_t *h, char *handles)
+{
+  if (!h || !handles) return fail(h, GFMD_B200_EINVAL, "ipc_export: null argument");
+  if (h->g.P == 1) return fail(h, GFMD_B200_ESTATE, "ipc_export: single-GPU handle has no exchange");
+  int rc = set_device(h);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == GFMD_B200_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  const size_t nstage = (size_t) h->g.P * h->g.d * h->g.kyb * h->g.nx_loc;
+  if (!h->d_stage3) {
+    CU(h, dmalloc(h, &h->d_stage3, nstage));
+    CU(h, cudaMemset(h->d_stage3, 0, sizeof(double2) * nstage));
+  }
+  cudaIpcMemHandle_t m[2];
+  CU(h, cudaIpcGetMemHandle(&m[0], h->d_stage2));
+  CU(h, cudaIpcGetMemHandle(&m[1], h->d_stage3));
+  memcpy(handles, m, sizeof(m));
+  return 0;
+}
+
+int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
+{
+  if (!h || !all_handles) return fail(h, GFMD_B200_EINVAL, "ipc_import: null argument");
+  if (h->g.P == 1) return 0;
+  if (!h->d_stage3) return fail(h, GFMD_B200_ESTATE, "ipc_import before ipc_export");
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->g.P; ++r) {
+    if (r == h->g.rank) {
+      h->peer_recv[0][r] = h->d_stage2;
+      h->peer_recv[1][r] = h->d_stage3;
+      continue;
+    }
+    for (int w = 0; w < 2; ++w) {
+      cudaIpcMemHandle_t m;
+      memcpy(&m, all_handles + ((size_t) r * 2 + w) * GFMD_B200_IPC_HANDLE_BYTES, sizeof(m));
+      void *p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, m, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(h, GFMD_B200_ECUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s (the NCCL exchange stays "
+                    "in use)", r, cudaGetErrorString(e));
+      h->peer_recv[w][r] = (double2 *) p;
+    }
+    if (!h->copy_stream[r]) {
+      CU(h, cudaStreamCreateWithFlags(&h->copy_stream[r], cudaStreamNonBlocking));
+      CU(h, cudaEventCreateWithFlags(&h->ev_join[r], cudaEventDisableTiming));
+    }
+  }
+  if (!h->ev_fork) CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  if (!h->d_barrier) {
+    CU(h, dmalloc(h, &h->d_barrier, (size_t) 1));
+    CU(h, cudaMemset(h->d_barrier, 0, sizeof(double)));
+  }
+  h->ipc_on = true;
+  return 0;
+}
+
 void gfmd_b200_destroy(gfmd_b200_t *h)
 {
   if (!h) return;
@@ -815,6 +905,15 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
   for (auto &kv : h->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
   cudaGetLastError();
+  for (int w = 0; w < 2; ++w)
+    for (int r = 0; r < gfmd_b200::kMaxRanks; ++r)
+      if (h->peer_recv[w][r] && r != h->g.rank) cudaIpcCloseMemHandle(h->peer_recv[w][r]);
+  for (int r = 0; r < gfmd_b200::kMaxRanks; ++r) {
+    if (h->copy_stream[r]) cudaStreamDestroy(h->copy_stream[r]);
+    if (h->ev_join[r]) cudaEventDestroy(h->ev_join[r]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  cudaFree(h->d_barrier); cudaFree(h->d_stage3);
   cudaFree(h->d_u); cudaFree(h->d_f); cudaFree(h->d_stage); cudaFree(h->d_stage2);
   cudaFree(h->d_phi); cudaFree(h->d_linf); cudaFree(h->d_epart); cudaFree(h->d_fsum_part);
   cudaFree(h->d_res); cudaFree(h->d_tw_ny);

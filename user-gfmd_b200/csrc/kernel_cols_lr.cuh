@@ -50,6 +50,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
   constexpr int LNXLC = P2<N>::LOG - LP;                      // min(log2 N, lnxl)
   constexpr int XMASK = (1 << LNXLC) - 1;
   extern __shared__ double2 sm[];
+  __shared__ double warp_e[NW];
   double2 *tws = sm + D * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t pstride = ((size_t) D * g.kyb) << lnxl;        // elements between pieces of one dof
@@ -163,8 +164,14 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     // energy partial of this warp (fixed order -> deterministic)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-    if (lane == 0) epart[(size_t) vc * NW + warp] = e;
+    if (lane == 0) warp_e[warp] = e;
     __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) a += warp_e[k];
+      epart[vc] = a;
+    }
     PHASE_MARK(6);
     // next column's data -> L2 while the backward passes run
     if (vc + (int) gridDim.x < nvc) {

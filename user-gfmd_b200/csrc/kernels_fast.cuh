@@ -20,7 +20,7 @@
 namespace gfmd {
 
 constexpr int kColsNW = 16;     // epart slots allocated per column (max warps of a column kernel)
-inline int fast_cols_nw(int variant) { return variant == 4096 ? 16 : 8; }
+inline int fast_cols_nw(int) { return 1; }        // energy partials per (virtual) column
 constexpr int kColsNW8 = 8;      // warps of the fused column kernel (epart has kColsNW slots per column)
 
 // ------------------------------------------------------------------ columns ---
@@ -32,8 +32,8 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
                 const double *__restrict__ linf, double *__restrict__ epart, StepResults *res)
 {
   constexpr int NW = T / 32;
-  static_assert(NW <= kColsNW, "epart layout");
   extern __shared__ double2 sm[];
+  __shared__ double warp_e[NW];
   double2 *tws = sm + D * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int xmask = (1 << lnxl) - 1;
@@ -119,8 +119,14 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
     // energy partial of this warp (fixed order -> deterministic)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-    if (lane == 0) epart[(size_t) kl * NW + warp] = e;
+    if (lane == 0) warp_e[warp] = e;
     __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) a += warp_e[k];
+      epart[kl] = a;
+    }
 
     // ---- group A backward, last pass straight to global memory
     p2_groupA_rest<N, NW, +1, D, 0>(sm, tw, tws, lane, warp);

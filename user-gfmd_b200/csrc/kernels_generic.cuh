@@ -467,8 +467,16 @@ k_cols_fused(const double2 *__restrict__ stage_in, double2 *__restrict__ stage_o
 __global__ void k_finalize(const double *__restrict__ epart, int ncols, StepResults *res)
 {
   __shared__ double sh[256];
-  double a = 0.0;
-  for (int k = threadIdx.x; k < ncols; k += blockDim.x) a += epart[k];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // independent chains: loads overlap
+  int k = threadIdx.x;
+  for (; k + 3 * (int) blockDim.x < ncols; k += 4 * blockDim.x) {
+    a0 += epart[k];
+    a1 += epart[k + blockDim.x];
+    a2 += epart[k + 2 * blockDim.x];
+    a3 += epart[k + 3 * blockDim.x];
+  }
+  for (; k < ncols; k += blockDim.x) a0 += epart[k];
+  const double a = (a0 + a1) + (a2 + a3);
   sh[threadIdx.x] = a;
   __syncthreads();
   for (int o = blockDim.x >> 1; o > 0; o >>= 1) {

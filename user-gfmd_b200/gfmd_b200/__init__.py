@@ -25,6 +25,7 @@ NSTAGES = 7
 STAGE_NAMES = ("gather", "rows_fwd", "exchange_fwd", "cols_fused", "exchange_inv", "rows_inv",
                "scatter")
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 # every symbol include/gfmd_b200.h declares: (restype, argtypes)
 _vp = ctypes.c_void_p
@@ -35,6 +36,8 @@ ABI = {
     "gfmd_b200_create_slab": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
     "gfmd_b200_get_unique_id": (_i, [ctypes.c_char_p]),
     "gfmd_b200_comm_init": (_i, [_vp, ctypes.c_char_p]),
+    "gfmd_b200_ipc_export": (_i, [_vp, ctypes.c_char_p]),
+    "gfmd_b200_ipc_import": (_i, [_vp, ctypes.c_char_p]),
     "gfmd_b200_destroy": (None, [_vp]),
     "gfmd_b200_last_error": (ctypes.c_char_p, [_vp]),
     "gfmd_b200_get_brick": (_i, [_vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
@@ -173,6 +176,21 @@ class GFMDSolverB200:
 
     def init(self):
         pass
+
+    def ipc_export(self):
+        """This rank's two receive-buffer handles (128 bytes) for the peer-copy exchange."""
+        buf = ctypes.create_string_buffer(2 * IPC_HANDLE_BYTES)
+        self._check(self.lib.gfmd_b200_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_import(self, all_handles):
+        """all_handles: the exports of all ranks concatenated in rank order."""
+        assert len(all_handles) == 2 * IPC_HANDLE_BYTES * self.nranks
+        self._check(self.lib.gfmd_b200_ipc_import(self.h, all_handles))
+
+    def enable_peer_copy(self, all_gather_bytes):
+        """Convenience: all_gather_bytes(b) -> list of every rank's bytes, in rank order."""
+        self.ipc_import(b"".join(all_gather_bytes(self.ipc_export())))
 
     def set_kernel(self, phi, linf=None, normalized=True):
         """phi: the table fill_phi_buffer produced for the whole grid,
@@ -332,6 +350,18 @@ def gfmd_solver_factory(keyword=None, **kw):
     if name not in ("static/b200", "b200"):
         raise GFMDError(1, "Unknown solver name encountered.")
     return GFMDSolverB200(**kw)
+
+
+def all_gather_bytes_fn(dev, world):
+    import torch
+    import torch.distributed as dist
+
+    def f(b):
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+    return f
 
 
 def slab_plan(nx, ny, ndof, rank, nranks):
