@@ -2,8 +2,9 @@ import sys, numpy as np, torch
 sys.path.insert(0,'/root/repo/user-gfmd_b200'); sys.path.insert(0,'/root/repo')
 import gfmd_b200
 from gfmd_b200 import synthetic
-n=int(sys.argv[1]) if len(sys.argv)>1 else 4096
-nx=ny=n; d=3
+nx=int(sys.argv[1]) if len(sys.argv)>1 else 4096
+ny=int(sys.argv[2]) if len(sys.argv)>2 else nx
+d=3
 s=gfmd_b200.GFMDSolverB200(); s.set_grid_size(nx,ny,d)
 print(s.describe())
 for k0 in range(0,s.nky,256):

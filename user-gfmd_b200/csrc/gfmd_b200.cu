@@ -229,6 +229,10 @@ struct gfmd_b200 {
   cudaStream_t copy_stream[kMaxRanks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxRanks] = {};
   double *d_barrier = nullptr;
+  // chunked pipeline: column chunks overlap their own transposes
+  static constexpr int kMaxChunks = 8;
+  int nchunks = 1, chunk_kl = 0;
+  cudaEvent_t ev_chunk[kMaxChunks][kMaxRanks] = {}, ev_k2[kMaxChunks] = {};
   double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
   int fsum_part_cap = 0;
   StepResults *d_res = nullptr, *h_res = nullptr;
@@ -569,6 +573,64 @@ int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
   return 0;
 }
 
+// Multi-GPU column stage with the transposes overlapped: the local ky range is cut into
+// chunks; all forward pushes are queued on the per-peer copy streams right after the row
+// kernel, chunk c is transformed as soon as ITS pushes have landed everywhere (NCCL
+// all-reduce as barrier), and its result is pushed back while chunk c+1 is transformed.
+int pipelined_columns(gfmd_b200 *h, double2 *A, double2 *B, double2 *B2)
+{
+  const GridDesc &g = h->g;
+  NcclApi &a = nccl();
+  const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;
+  const size_t pitch = (size_t) g.kyb * g.nx_loc * sizeof(double2);     // between dofs of a block
+  const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
+  const int nc = h->nchunks, ck = h->chunk_kl;
+
+  stage_mark(h, 2);
+  stage_mark(h, 3);
+  // own blocks stay on the compute stream
+  CU(h, cudaMemcpyAsync(B + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
+                        h->stream));
+  CU(h, cudaEventRecord(h->ev_fork, h->stream));
+  for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->copy_stream[(g.rank + k) % g.P], h->ev_fork, 0));
+  for (int c = 0; c < nc; ++c) {
+    const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
+    const size_t off = (size_t) k0 * g.nx_loc, width = (size_t) (k1 - k0) * g.nx_loc * sizeof(double2);
+    for (int k = 1; k < g.P; ++k) {
+      const int r = (g.rank + k) % g.P;
+      CU(h, cudaMemcpy2DAsync(h->peer_recv[0][r] + g.rank * blk + off, pitch, A + r * blk + off, pitch, width,
+                              g.d, cudaMemcpyDeviceToDevice, h->copy_stream[r]));
+      CU(h, cudaEventRecord(h->ev_chunk[c][r], h->copy_stream[r]));
+    }
+  }
+  for (int c = 0; c < nc; ++c) {
+    const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
+    const size_t off = (size_t) k0 * g.nx_loc, width = (size_t) (k1 - k0) * g.nx_loc * sizeof(double2);
+    for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[c][(g.rank + k) % g.P], 0));
+    NC(h, a.AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
+                             h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, k0, k1);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+    CU(h, cudaEventRecord(h->ev_k2[c], h->stream));
+    for (int k = 1; k < g.P; ++k) {
+      const int r = (g.rank + k) % g.P;
+      CU(h, cudaStreamWaitEvent(h->copy_stream[r], h->ev_k2[c], 0));
+      CU(h, cudaMemcpy2DAsync(h->peer_recv[1][r] + g.rank * blk + off, pitch, A + r * blk + off, pitch, width,
+                              g.d, cudaMemcpyDeviceToDevice, h->copy_stream[r]));
+      if (c == nc - 1) CU(h, cudaEventRecord(h->ev_join[r], h->copy_stream[r]));
+    }
+  }
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc << h->cols_top, h->d_res);
+  h->launches++;
+  stage_mark(h, 4);
+  CU(h, cudaMemcpyAsync(B2 + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
+                        h->stream));
+  for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[(g.rank + k) % g.P], 0));
+  // u0 all-reduce (gfmd_solver_static.cpp:176) doubles as the barrier of the return pushes
+  NC(h, a.AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm, h->stream));
+  return 0;
+}
+
 // the kernels of one solver step, enqueued on h->stream
 int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
 {
@@ -593,41 +655,46 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
           d_u, A, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
     h->launches++;
   }
-  stage_mark(h, 2);
-  if (g.P > 1) {
-    int rc = exchange(h, A, B, 0);
+  if (g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->nchunks > 1) {
+    int rc = pipelined_columns(h, A, B, B2);
     if (rc) return rc;
-  }
-  stage_mark(h, 3);
-  if (g.nky_loc > 0) {
-    if (h->fast_cols) {
-      const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
-      int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
-                               h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches);
-      if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
-    } else {
-#define LAUNCH_COLS(DT)                                                                          \
-  k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
-      B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
-      switch (g.d) {
-        case 3: LAUNCH_COLS(3); break;
-        case 6: LAUNCH_COLS(6); break;
-        case 9: LAUNCH_COLS(9); break;
-        case 12: LAUNCH_COLS(12); break;
-        default: LAUNCH_COLS(0); break;
-      }
-#undef LAUNCH_COLS
-      h->launches++;
+  } else {
+    stage_mark(h, 2);
+    if (g.P > 1) {
+      int rc = exchange(h, A, B, 0);
+      if (rc) return rc;
     }
-  }
-  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
-  h->launches++;
-  stage_mark(h, 4);
-  if (g.P > 1) {
-    int rc = exchange(h, A, B2, 1);
-    if (rc) return rc;
-    NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
-                           h->stream));
+    stage_mark(h, 3);
+    if (g.nky_loc > 0) {
+      if (h->fast_cols) {
+        const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
+        int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
+                                 h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches);
+        if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+      } else {
+  #define LAUNCH_COLS(DT)                                                                          \
+    k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
+        B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
+        switch (g.d) {
+          case 3: LAUNCH_COLS(3); break;
+          case 6: LAUNCH_COLS(6); break;
+          case 9: LAUNCH_COLS(9); break;
+          case 12: LAUNCH_COLS(12); break;
+          default: LAUNCH_COLS(0); break;
+        }
+  #undef LAUNCH_COLS
+        h->launches++;
+      }
+    }
+    k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
+    h->launches++;
+    stage_mark(h, 4);
+    if (g.P > 1) {
+      int rc = exchange(h, A, B2, 1);
+      if (rc) return rc;
+      NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
+                             h->stream));
+    }
   }
   stage_mark(h, 5);
   if (h->fast_rows) {
@@ -892,6 +959,24 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     CU(h, dmalloc(h, &h->d_barrier, (size_t) 1));
     CU(h, cudaMemset(h->d_barrier, 0, sizeof(double)));
   }
+  // chunking of the column stage: whole waves of the persistent column kernel per chunk
+  {
+    int want = 4;
+    if (const char *e = getenv("GFMD_B200_CHUNKS")) want = atoi(e);
+    if (want < 1) want = 1;
+    if (want > gfmd_b200::kMaxChunks) want = gfmd_b200::kMaxChunks;
+    const int per_wave = h->num_sms >> h->cols_top > 0 ? h->num_sms >> h->cols_top : 1;   // ky per wave
+    int waves = (h->g.kyb + per_wave * want - 1) / (per_wave * want);
+    if (waves < 1) waves = 1;
+    h->chunk_kl = waves * per_wave;
+    h->nchunks = (h->g.kyb + h->chunk_kl - 1) / h->chunk_kl;
+    if (h->nchunks > gfmd_b200::kMaxChunks) { h->nchunks = 1; h->chunk_kl = h->g.kyb; }
+    for (int c = 0; c < h->nchunks; ++c) {
+      if (!h->ev_k2[c]) CU(h, cudaEventCreateWithFlags(&h->ev_k2[c], cudaEventDisableTiming));
+      for (int r = 0; r < h->g.P; ++r)
+        if (!h->ev_chunk[c][r]) CU(h, cudaEventCreateWithFlags(&h->ev_chunk[c][r], cudaEventDisableTiming));
+    }
+  }
   h->ipc_on = true;
   return 0;
 }
@@ -913,6 +998,11 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
     if (h->ev_join[r]) cudaEventDestroy(h->ev_join[r]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int c = 0; c < gfmd_b200::kMaxChunks; ++c) {
+    if (h->ev_k2[c]) cudaEventDestroy(h->ev_k2[c]);
+    for (int r = 0; r < gfmd_b200::kMaxRanks; ++r)
+      if (h->ev_chunk[c][r]) cudaEventDestroy(h->ev_chunk[c][r]);
+  }
   cudaFree(h->d_barrier); cudaFree(h->d_stage3);
   cudaFree(h->d_u); cudaFree(h->d_f); cudaFree(h->d_stage); cudaFree(h->d_stage2);
   cudaFree(h->d_phi); cudaFree(h->d_linf); cudaFree(h->d_epart); cudaFree(h->d_fsum_part);

@@ -42,6 +42,7 @@ __device__ long long g_phase_cycles[16];
 template <int N, int T, int LP>
 __global__ void __launch_bounds__(T, 1)
 k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, int lnxl, int ltop,
+                   int kl0, int kl1,   // local ky range of this launch (chunked multi-GPU pipeline)
                    const double2 *__restrict__ tw, const double *__restrict__ phi,
                    const double *__restrict__ linf, double *__restrict__ epart, StepResults *res)
 {
@@ -55,7 +56,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t pstride = ((size_t) D * g.kyb) << lnxl;        // elements between pieces of one dof
   const size_t dstride = ((size_t) g.kyb) << lnxl;            // elements between dofs of one piece
-  const int nvc = g.nky_loc << ltop;                          // virtual columns (ky, q)
+  const int nvc = kl1 << ltop;                                // virtual columns (ky, q) end
   p2_fill_tws<N>(tws, tw);
   __syncthreads();
 
@@ -69,7 +70,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 #ifdef GFMD_PHASE_TIMING
   long long tprev__ = clock64();
 #endif
-  for (int vc = blockIdx.x; vc < nvc; vc += gridDim.x) {
+  for (int vc = (kl0 << ltop) + blockIdx.x; vc < nvc; vc += gridDim.x) {
     const int ky = g.ky0 + (vc >> ltop);
     const size_t col0 = column_base(vc);
     auto addr = [&](int a, int base, int off) -> size_t {
@@ -197,17 +198,18 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 // One thread per (dof, kl, n), n < S = nx >> LR; elements x = n + r*S, r < R = 2^LR.
 template <int LR, int DIR>
 __global__ void __launch_bounds__(256)
-k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx)
+k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx, int kl0,
+                int kl1)
 {
   constexpr int R = 1 << LR;
   const int S = g.nx >> LR;
   const int xmask = (1 << lnxl) - 1;
-  const long long total = (long long) g.d * g.nky_loc * S;
+  const long long total = (long long) g.d * (kl1 - kl0) * S;
   for (long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long) gridDim.x * blockDim.x) {
     const int n = (int) (idx % S);
     const int col = (int) (idx / S);
-    const int dof = col % g.d, kl = col / g.d;
+    const int dof = col % g.d, kl = kl0 + col / g.d;
     double2 v[R];
     size_t a[R];
 #pragma unroll

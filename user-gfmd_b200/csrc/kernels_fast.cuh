@@ -411,20 +411,25 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
 // (2048 or 4096); tw_nx: twiddles of the full column length (top pass only).
 inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, const GridDesc &g,
                            const double2 *tw_sub, const double2 *tw_nx, const double *phi, const double *linf,
-                           double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches)
+                           double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches,
+                           int kl0 = 0, int kl1 = -1)
 {
-  const int nvc = g.nky_loc << top;
+  if (kl1 < 0) kl1 = g.nky_loc;
+  if (kl1 > g.nky_loc) kl1 = g.nky_loc;
+  if (kl0 >= kl1) return 0;
+  if (variant != 4096 && (kl0 != 0 || kl1 != g.nky_loc)) return 1;
+  const int nvc = (kl1 - kl0) << top;
   const int grid = nvc < num_sms ? nvc : num_sms;
   const int lnxl = ilog2_rt(g.nx_loc);
   const size_t smem = fast_cols_smem(3, variant);
-  const long long top_items = (long long) g.d * g.nky_loc * (g.nx >> top);
+  const long long top_items = (long long) g.d * (kl1 - kl0) * (g.nx >> top);
   const int top_grid = (int) ((top_items + 255) / 256 < (long long) num_sms * 8 ? (top_items + 255) / 256
                                                                                 : (long long) num_sms * 8);
   if (top == 1) {
-    k_cols_top_pass<1, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx);
+    k_cols_top_pass<1, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   } else if (top == 2) {
-    k_cols_top_pass<2, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx);
+    k_cols_top_pass<2, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   }
   switch (variant) {
@@ -435,8 +440,8 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
       switch (lnxl >= 12 ? 0 : 12 - lnxl) {
 #define LR_LAUNCH(LP)                                                                                       \
   case LP:                                                                                                  \
-    k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, tw_sub, phi, linf,   \
-                                                              epart, res);                                  \
+    k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, kl0, kl1, tw_sub,    \
+                                                              phi, linf, epart, res);                       \
     break;
         LR_LAUNCH(0) LR_LAUNCH(1) LR_LAUNCH(2) LR_LAUNCH(3)
 #undef LR_LAUNCH
@@ -447,10 +452,10 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   }
   ++*launches;
   if (top == 1) {
-    k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx);
+    k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   } else if (top == 2) {
-    k_cols_top_pass<2, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx);
+    k_cols_top_pass<2, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   }
   return 0;
