@@ -48,7 +48,7 @@ def parse():
 
 
 # weak scaling: 4096 x 4096 cells per GPU ("4096^2 -> 16384^2 surface, slab-sharded over 8 x B200")
-WEAK_GRIDS = {1: (4096, 4096), 2: (8192, 4096), 4: (8192, 8192), 8: (16384, 8192)}
+WEAK_GRIDS = {1: (4096, 4096), 2: (4096, 8192), 4: (8192, 8192), 8: (16384, 8192)}
 
 
 def workload(args):

@@ -8,7 +8,7 @@ dist.init_process_group('nccl', device_id=dev)
 b=torch.zeros(128,dtype=torch.uint8,device=dev)
 if rank==0: b.copy_(torch.frombuffer(bytearray(gfmd_b200.get_unique_id()),dtype=torch.uint8))
 dist.broadcast(b,0)
-grids={1:(4096,4096),2:(8192,4096),4:(8192,8192),8:(16384,8192)}
+grids={1:(4096,4096),2:(4096,8192),4:(8192,8192),8:(16384,8192)}
 nx,ny=grids[world]; d=3
 s=gfmd_b200.GFMDSolverB200(device=local,rank=rank,nranks=world,unique_id=bytes(b.cpu().numpy().tobytes()))
 s.set_grid_size(nx,ny,d)

@@ -1,0 +1,190 @@
+"""The reference's compound acceptance tests, restated without LAMMPS and run on the
+CUDA path.  Criteria are the reference's own:
+
+* tests/TEST_energy_conservation_two_layers (lammps.in, eval.py:34-40): 10 x 10 grid,
+  two-layer fcc100 kernel (ndof 6), random displacements 0.1 (seed 12472634),
+  v = (0.1, 0, 0), `fix nve`, dt = 0.01, 100 000 steps, thermo every 1000:
+  max|E - <E>| / <E> <= 1e-4.
+* tests/TEST_Hertz_sc100_128x128 (lammps.in, eval.py:33-39,73-86): rigid sphere R = 100
+  (fix contact/sphere: 12-6 wall in r - R, src/extras/fix_contact_sphere.cpp:130-141,
+  :207-264) pressed on the 128 x 128 sc100 layer by moving all atoms 2.0 down, minimised
+  to |f| <= 1e-6; final z-force map vs. the Hertz profile with E* = 8/3:
+  sum (f - f_Hertz)^2 < 1e-2.
+
+The stiffness tables are the reference plugin's own (tests/golden, produced by
+`ft fcc100 1.0 2 pair-potential 2 1.0 -0.1 height 10` and
+`ft sc100 1 1.0 pair-potential 2 1.0 1.0 height 128`).  The integrator / minimiser
+(LAMMPS' job in the reference) are a few torch element-wise lines here; every force and
+energy comes from gather -> solver -> scatter of libgfmd_b200."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def make_layer_atoms(nx, ny, nu):
+    gid = np.array([(ix, iy, iu) for ix in range(nx) for iy in range(ny) for iu in range(nu)], dtype=np.int32)
+    xeq = np.stack([gid[:, 0] + 0.5, gid[:, 1] + 0.5, 0.5 - gid[:, 2]], axis=1).astype(np.float64)
+    return gid, xeq
+
+
+def test_energy_conservation_two_layers():
+    import torch
+    import gfmd_b200
+    g = load_golden("C3_fcc100_two_layers_10x10")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    gid, xeq = make_layer_atoms(nx, ny, d // 3)
+    n = gid.shape[0]
+    rng = np.random.default_rng(12472634)
+    x0 = xeq + rng.uniform(-0.1, 0.1, size=(n, 3))           # displace_atoms all random 0.1 0.1 0.1
+    dev = torch.device("cuda")
+    s = gfmd_b200.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    s.set_stream(torch.cuda.current_stream().cuda_stream)     # library work is ordered with torch's
+    x = torch.tensor(x0, device=dev)
+    dxeq = torch.tensor(xeq, device=dev)
+    dgid = torch.tensor(gid, device=dev)
+    dmask = torch.ones(n, dtype=torch.int32, device=dev)
+    v = torch.zeros((n, 3), device=dev, dtype=torch.float64)
+    v[:, 0] = 0.1                                            # velocity all set 0.1 0.0 0.0
+    f = torch.zeros((n, 3), device=dev, dtype=torch.float64)
+    dt, mass = 0.01, 1.0
+
+    shift = [0, 0]                                           # FixGFMD xshift / yshift
+
+    def force(check_shift=False):
+        # fix_gfmd.cpp:695-715: when the layer's centre of mass has moved by a lattice constant
+        # the grid indices are shifted (gid rewritten by the gather); physics is unchanged
+        dxs = dys = 0
+        if check_shift:
+            dcm = (x - dxeq).mean(dim=0).cpu().numpy()
+            cur = [int(dcm[0] - 0.5) if dcm[0] < 0 else int(dcm[0] + 0.5),
+                   int(dcm[1] - 0.5) if dcm[1] < 0 else int(dcm[1] + 0.5)]      # the fix's nearbyint macro
+            dxs, dys = shift[0] - cur[0], shift[1] - cur[1]
+            shift[0], shift[1] = cur
+        f.zero_()
+        s.gather(x, dxeq, dgid, dmask, 1, n, float(nx), float(ny), dxs, dys)
+        s.post_force_device()
+        s.scatter(dgid, dmask, 1, n, n, f)
+        return dxs != 0 or dys != 0
+
+    force()
+    etot, com = [], []
+    nshifts = 0
+    nsteps, every = 100000, 1000
+    for step in range(nsteps + 1):
+        if step % every == 0:
+            r = s.results()                                   # synchronises
+            ke = 0.5 * mass * float((v * v).sum().item())
+            etot.append(ke + r["epot"])
+            com.append(float((x - dxeq)[:, 0].mean().item()))
+            assert r["natoms_gathered"] == n and r["natoms_scattered"] == n
+        if step == nsteps:
+            break
+        v.add_(f, alpha=0.5 * dt / mass)                      # fix nve: velocity Verlet
+        x.add_(v, alpha=dt)
+        nshifts += force(check_shift=(step % 25 == 0))
+        v.add_(f, alpha=0.5 * dt / mass)
+    e = np.array(etot)
+    de = np.max(np.abs(e - e.mean()))
+    # the layer oscillates by more than half a lattice constant: the re-indexing path ran
+    assert max(abs(c) for c in com) > 0.5 and nshifts > 0
+    assert e.mean() > 0
+    assert de / e.mean() <= 1e-4, (de, e.mean())
+    s.close()
+
+
+def test_hertz_sc100_128x128():
+    import torch
+    import gfmd_b200
+    g = load_golden("C1_sc100_128x128")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    gid, xeq = make_layer_atoms(nx, ny, 1)
+    n = gid.shape[0]
+    dev = torch.device("cuda")
+    s = gfmd_b200.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    dxeq = torch.tensor(xeq, device=dev)
+    dgid = torch.tensor(gid, device=dev)
+    dmask = torch.ones(n, dtype=torch.int32, device=dev)
+    x = dxeq.clone()
+    x[:, 2] -= 2.0                                           # displace_atoms all move 0 0 -2.0
+    f = torch.zeros((n, 3), device=dev, dtype=torch.float64)
+
+    # fix contact/sphere 0 0 99.5 100.0 1.38888888888889 0.890898718140339 1.0
+    cx, cy, cz, R = 0.0, 0.0, 99.5, 100.0
+    eps, sig, cut = 1.38888888888889, 0.890898718140339, 1.0
+    c1, c2 = 48.0 * eps * sig ** 12, 24.0 * eps * sig ** 6
+
+    def force():
+        f.zero_()
+        s.full_step(x, dxeq, dgid, dmask, 1, n, n, float(nx), float(ny), f)
+        rx = x[:, 0] - cx
+        ry = x[:, 1] - cy
+        rz = x[:, 2] - cz
+        rx = rx - nx * torch.round(rx / nx)                  # domain->minimum_image
+        ry = ry - ny * torch.round(ry / ny)
+        r = torch.sqrt(rx * rx + ry * ry + rz * rz)
+        assert bool((r > R).all()), "atom inside sphere"
+        inside = r < R + cut
+        rinv = 1.0 / torch.clamp(r - R, min=1e-300)
+        r6 = rinv ** 6
+        df = torch.where(inside, r6 * (c1 * r6 - c2) * rinv, torch.zeros_like(r))
+        f[:, 0] += df * rx / r
+        f[:, 1] += df * ry / r
+        f[:, 2] += df * rz / r
+
+    # FIRE minimiser (LAMMPS: min_style cg; any minimiser reaching |f| <= 1e-6 will do)
+    v = torch.zeros_like(x)
+    dt, dtmax, alpha, npos = 0.05, 0.25, 0.1, 0
+    fnorm = None
+    for it in range(200000):
+        force()
+        if it % 50 == 0:
+            fnorm = float(torch.linalg.vector_norm(f).item())
+            if fnorm <= 1e-6:
+                break
+        p = float((f * v).sum().item()) if it % 1 == 0 else 0.0
+        if p > 0:
+            vn = torch.linalg.vector_norm(v)
+            fn = torch.linalg.vector_norm(f)
+            v.mul_(1.0 - alpha).add_(f * (alpha * vn / fn))
+            npos += 1
+            if npos > 5:
+                dt = min(dt * 1.1, dtmax)
+                alpha *= 0.99
+        else:
+            v.zero_()
+            dt *= 0.5
+            alpha = 0.1
+            npos = 0
+        v.add_(f, alpha=dt)
+        x.add_(v, alpha=dt)
+    assert fnorm is not None and fnorm <= 1e-6, fnorm
+
+    # eval.py: z-force of the GFMD layer (gfmd.*.r.f2.out = f_xy[2]) vs Hertz
+    fg = torch.zeros((n, 3), device=dev, dtype=torch.float64)
+    s.full_step(x, dxeq, dgid, dmask, 1, n, n, float(nx), float(ny), fg)
+    s.results()
+    f_xy = fg[:, 2].reshape(nx, ny).cpu().numpy()
+    E = 8.0 / 3
+    xs = np.arange(nx) + 0.5
+    xs = np.where(xs > nx / 2, xs - nx, xs)
+    ys = np.arange(ny) + 0.5
+    ys = np.where(ys > ny / 2, ys - ny, ys)
+    r_xy = np.sqrt((xs ** 2).reshape(-1, 1) + (ys ** 2).reshape(1, -1))
+    N = np.sum(f_xy)
+    a = R * (3.0 / 4 * (N / (E * R ** 2))) ** (1.0 / 3)
+    p0 = 3 * N / (2 * math.pi * a * a)
+    fa_xy = np.where(r_xy < a, p0 * np.sqrt(np.maximum(0.0, 1 - (r_xy / a) ** 2)), np.zeros_like(r_xy))
+    res = np.sum((f_xy - fa_xy) ** 2)
+    assert N > 0 and a > 3
+    assert res < 1e-2, (res, N, a, p0)
+    s.close()
