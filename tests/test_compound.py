@@ -99,6 +99,73 @@ def test_energy_conservation_two_layers():
     s.close()
 
 
+def hertz_minimise(s, x, dxeq, dgid, dmask, n, xprd, yprd):
+    """Rigid sphere (fix contact/sphere 0 0 99.5 100.0 1.38888888888889 0.890898718140339 1.0) on
+    the GFMD layer, FIRE to |f| <= 1e-6 (LAMMPS: min_style cg; minimize 0.0 1e-6 ...).
+    Returns the GFMD force on the atoms at the minimum."""
+    import torch
+    cx, cy, cz, R = 0.0, 0.0, 99.5, 100.0
+    eps, sig, cut = 1.38888888888889, 0.890898718140339, 1.0
+    c1, c2 = 48.0 * eps * sig ** 12, 24.0 * eps * sig ** 6
+    f = torch.zeros_like(x)
+
+    def force():
+        f.zero_()
+        s.full_step(x, dxeq, dgid, dmask, 1, n, n, xprd, yprd, f)
+        rx = x[:, 0] - cx
+        ry = x[:, 1] - cy
+        rz = x[:, 2] - cz
+        rx = rx - xprd * torch.round(rx / xprd)              # domain->minimum_image
+        ry = ry - yprd * torch.round(ry / yprd)
+        r = torch.sqrt(rx * rx + ry * ry + rz * rz)
+        inside = r < R + cut
+        rinv = 1.0 / torch.clamp(r - R, min=1e-300)
+        r6 = rinv ** 6
+        df = torch.where(inside, r6 * (c1 * r6 - c2) * rinv, torch.zeros_like(r))
+        f[:, 0] += df * rx / r
+        f[:, 1] += df * ry / r
+        f[:, 2] += df * rz / r
+        return r
+
+    v = torch.zeros_like(x)
+    dt, dtmax, alpha, npos = 0.05, 0.25, 0.1, 0
+    fnorm = None
+    for it in range(200000):
+        r = force()
+        if it % 50 == 0:
+            assert bool((r > R).all()), "fix contact/sphere: atom inside sphere"
+            fnorm = float(torch.linalg.vector_norm(f).item())
+            if fnorm <= 1e-6:
+                break
+        p = float((f * v).sum().item())
+        if p > 0:
+            vn = torch.linalg.vector_norm(v)
+            fn = torch.linalg.vector_norm(f)
+            v.mul_(1.0 - alpha).add_(f * (alpha * vn / fn))
+            npos += 1
+            if npos > 5:
+                dt = min(dt * 1.1, dtmax)
+                alpha *= 0.99
+        else:
+            v.zero_()
+            dt *= 0.5
+            alpha = 0.1
+            npos = 0
+        v.add_(f, alpha=dt)
+        x.add_(v, alpha=dt)
+    assert fnorm is not None and fnorm <= 1e-6, fnorm
+    fg = torch.zeros_like(x)
+    s.full_step(x, dxeq, dgid, dmask, 1, n, n, xprd, yprd, fg)
+    s.results()
+    return fg
+
+
+def hertz_profile(r, N, E, R):
+    a = R * (3.0 / 4 * (N / (E * R ** 2))) ** (1.0 / 3)
+    p0 = 3 * N / (2 * math.pi * a * a)
+    return np.where(r < a, p0 * np.sqrt(np.maximum(0.0, 1 - (r / a) ** 2)), np.zeros_like(r)), a, p0
+
+
 def test_hertz_sc100_128x128():
     import torch
     import gfmd_b200
@@ -116,75 +183,58 @@ def test_hertz_sc100_128x128():
     dmask = torch.ones(n, dtype=torch.int32, device=dev)
     x = dxeq.clone()
     x[:, 2] -= 2.0                                           # displace_atoms all move 0 0 -2.0
-    f = torch.zeros((n, 3), device=dev, dtype=torch.float64)
-
-    # fix contact/sphere 0 0 99.5 100.0 1.38888888888889 0.890898718140339 1.0
-    cx, cy, cz, R = 0.0, 0.0, 99.5, 100.0
-    eps, sig, cut = 1.38888888888889, 0.890898718140339, 1.0
-    c1, c2 = 48.0 * eps * sig ** 12, 24.0 * eps * sig ** 6
-
-    def force():
-        f.zero_()
-        s.full_step(x, dxeq, dgid, dmask, 1, n, n, float(nx), float(ny), f)
-        rx = x[:, 0] - cx
-        ry = x[:, 1] - cy
-        rz = x[:, 2] - cz
-        rx = rx - nx * torch.round(rx / nx)                  # domain->minimum_image
-        ry = ry - ny * torch.round(ry / ny)
-        r = torch.sqrt(rx * rx + ry * ry + rz * rz)
-        assert bool((r > R).all()), "atom inside sphere"
-        inside = r < R + cut
-        rinv = 1.0 / torch.clamp(r - R, min=1e-300)
-        r6 = rinv ** 6
-        df = torch.where(inside, r6 * (c1 * r6 - c2) * rinv, torch.zeros_like(r))
-        f[:, 0] += df * rx / r
-        f[:, 1] += df * ry / r
-        f[:, 2] += df * rz / r
-
-    # FIRE minimiser (LAMMPS: min_style cg; any minimiser reaching |f| <= 1e-6 will do)
-    v = torch.zeros_like(x)
-    dt, dtmax, alpha, npos = 0.05, 0.25, 0.1, 0
-    fnorm = None
-    for it in range(200000):
-        force()
-        if it % 50 == 0:
-            fnorm = float(torch.linalg.vector_norm(f).item())
-            if fnorm <= 1e-6:
-                break
-        p = float((f * v).sum().item()) if it % 1 == 0 else 0.0
-        if p > 0:
-            vn = torch.linalg.vector_norm(v)
-            fn = torch.linalg.vector_norm(f)
-            v.mul_(1.0 - alpha).add_(f * (alpha * vn / fn))
-            npos += 1
-            if npos > 5:
-                dt = min(dt * 1.1, dtmax)
-                alpha *= 0.99
-        else:
-            v.zero_()
-            dt *= 0.5
-            alpha = 0.1
-            npos = 0
-        v.add_(f, alpha=dt)
-        x.add_(v, alpha=dt)
-    assert fnorm is not None and fnorm <= 1e-6, fnorm
-
-    # eval.py: z-force of the GFMD layer (gfmd.*.r.f2.out = f_xy[2]) vs Hertz
-    fg = torch.zeros((n, 3), device=dev, dtype=torch.float64)
-    s.full_step(x, dxeq, dgid, dmask, 1, n, n, float(nx), float(ny), fg)
-    s.results()
+    fg = hertz_minimise(s, x, dxeq, dgid, dmask, n, float(nx), float(ny))
+    # eval.py: z-force of the GFMD layer (gfmd.*.r.f2.out = f_xy[2]) vs Hertz, E* = 8/3
     f_xy = fg[:, 2].reshape(nx, ny).cpu().numpy()
-    E = 8.0 / 3
     xs = np.arange(nx) + 0.5
     xs = np.where(xs > nx / 2, xs - nx, xs)
     ys = np.arange(ny) + 0.5
     ys = np.where(ys > ny / 2, ys - ny, ys)
     r_xy = np.sqrt((xs ** 2).reshape(-1, 1) + (ys ** 2).reshape(1, -1))
     N = np.sum(f_xy)
-    a = R * (3.0 / 4 * (N / (E * R ** 2))) ** (1.0 / 3)
-    p0 = 3 * N / (2 * math.pi * a * a)
-    fa_xy = np.where(r_xy < a, p0 * np.sqrt(np.maximum(0.0, 1 - (r_xy / a) ** 2)), np.zeros_like(r_xy))
+    fa_xy, a, p0 = hertz_profile(r_xy, N, 8.0 / 3, 100.0)
     res = np.sum((f_xy - fa_xy) ** 2)
     assert N > 0 and a > 3
     assert res < 1e-2, (res, N, a, p0)
+    s.close()
+
+
+def test_hertz_fcc111_64x37():
+    """tests/TEST_Hertz_fcc111_64x37_2: non-power-of-two grid (Bluestein rows), two atoms
+    per rectangular surface cell (ndof 6), E = 1.54, residual of the PRESSURE < 2e-3
+    (eval.py:33-34, :94-106)."""
+    import torch
+    import gfmd_b200
+    g = load_golden("C2_fcc111_64x37")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    s3 = math.sqrt(3.0)
+    # lattice custom: a1 = (1,0,0), a2 = (0,sqrt 3,0), basis (0,0,0) and (1/2,1/2,0)
+    gid = np.array([(ix, iy, iu) for ix in range(nx) for iy in range(ny) for iu in range(2)], dtype=np.int32)
+    xeq = np.stack([gid[:, 0] + 0.5 * gid[:, 2], (gid[:, 1] + 0.5 * gid[:, 2]) * s3,
+                    np.zeros(len(gid))], axis=1)
+    n = gid.shape[0]
+    dev = torch.device("cuda")
+    s = gfmd_b200.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    dxeq = torch.tensor(xeq, device=dev)
+    dgid = torch.tensor(gid, device=dev)
+    dmask = torch.ones(n, dtype=torch.int32, device=dev)
+    x = dxeq.clone()
+    x[:, 2] -= 2.0
+    xprd, yprd = float(nx), ny * s3
+    fg = hertz_minimise(s, x, dxeq, dgid, dmask, n, xprd, yprd)
+    fz = fg[:, 2].cpu().numpy()
+    xe = xeq[:, 0].copy()
+    ye = xeq[:, 1].copy()
+    xe = np.where(xe > xprd / 2, xe - xprd, xe)
+    ye = np.where(ye > yprd / 2, ye - yprd, ye)
+    r = np.sqrt(xe ** 2 + ye ** 2)
+    A0 = s3 / 2                                              # area per atom
+    N = np.sum(fz)
+    pa, a, p0 = hertz_profile(r, N, 1.54, 100.0)
+    res = np.sum((fz / A0 - pa) ** 2)
+    assert N > 0 and a > 3
+    assert res < 0.002, (res, N, a, p0)
     s.close()
