@@ -202,6 +202,8 @@ def main_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL's own log lines (e.g. "NCCL version ...") must not land on stdout next to the JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
     torch.cuda.set_device(local)

@@ -484,6 +484,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   }
   memset(h->h_res, 0, sizeof(StepResults));
   h->phi_cols_set.assign(g.nky_loc > 0 ? g.nky_loc : 0, 0);
+  h->phi_set = g.nky_loc == 0;      // a rank without q columns has no table to wait for
   for (int i = 0; i <= GFMD_B200_NSTAGES; ++i) cudaEventCreate(&h->ev[i]);
 
   char rows[160], cols[200], buf[512];
