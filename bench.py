@@ -231,10 +231,14 @@ def main_b200(args):
             exchange = "CUDA IPC peer pushes over NVLink (copy engines) + NCCL barrier"
         except gfmd_b200.GFMDError as ex:          # still a GPU path: grouped ncclSend/ncclRecv
             exchange = "NCCL send/recv (peer copy unavailable: %s)" % ex
-    # stiffness table for this rank's q columns (closed form, see synthetic.phi_columns)
-    for k0 in range(s.kylo, s.kylo + s.nky, 128):
-        nk = min(128, s.kylo + s.nky - k0)
-        s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+    # stiffness table of the reference's `sc100 height 128` kernel (semi-infinite-like elastic
+    # substrate, 128 layers) for this rank's q columns: the host evaluates the per-q matrices
+    # U0, U, V (closed form, gfmd_b200.synthetic.sc100_dynamical_matrices == the plugin's
+    # get_dynamical_matrices), the transfer-matrix recursion runs on the GPU
+    # (gfmd_b200_build_phi_columns)
+    for k0 in range(s.kylo, s.kylo + s.nky, 64):
+        nk = min(64, s.kylo + s.nky - k0)
+        s.build_kernel_columns(synthetic.sc100_dynamical_matrices(nx, ny, k0, nk), k0, height=128)
     s.set_linf(np.zeros(d // 3))
 
     nx_loc, x0 = nx // world, rank * (nx // world)
@@ -373,7 +377,8 @@ def main_b200(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d, 1 atom/cell" % (nx, ny, d),
+               "config": {"workload": "synthetic surface %dx%d, stiffness kernel `sc100 height 128`, ndof %d, "
+                                      "1 atom/cell" % (nx, ny, d),
                           "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",
                           "decomposition": "x-slabs over %d GPU(s); transposes: %s" % (world, exchange),
                           "l2": "inputs larger than L2 (%.0f MB of atoms+grids per step)" %

@@ -112,6 +112,16 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi_ri, int ky_first
                               int already_normalised);
 int gfmd_b200_set_linf(gfmd_b200_t *h, const double *linf);
 
+/* Device-side table builder: runs the transfer-matrix recursion of
+ * greens_function_transfer_matrix_stiffness (src/main/surface_stiffness.cpp:811-873, iterate_Gnn
+ * :493-548) on the GPU.  uuv holds, for kx in [0,nx) and ky in [ky_first, ky_first+nky), the three
+ * matrices StiffnessKernel::get_dynamical_matrices returns (U0, U, V; each ndof*ndof complex128,
+ * row-major): index (((ix*nky + j)*3 + m)*ndof*ndof + i*ndof + jdof).  height as in the kernel
+ * arguments (`height N`): N-1 iterations, 0 means Phi = U0; negative (iterate to convergence)
+ * is not supported.  normalise != 0 applies the 1/(nx*ny) of fill_phi_buffer.  ndof 3, 6, 9, 12. */
+int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv_ri, int ky_first, int nky, int height,
+                                int normalise);
+
 /* Deviations found by the last gfmd_b200_set_phi: max |Phi - Phi^H| and
  * max |Phi(q) - conj Phi(-q)|, both relative to max |Phi|. */
 int gfmd_b200_phi_deviation(const gfmd_b200_t *h, double *herm_dev, double *conj_dev);

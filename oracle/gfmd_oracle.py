@@ -297,6 +297,9 @@ def rlib():
         lib.ref_phi_at.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                    ctypes.c_double, c_double_p]
         lib.ref_get_linf.argtypes = [ctypes.c_void_p, c_double_p]
+        lib.ref_dynamical_matrices_columns.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                       ctypes.c_int, ctypes.c_int, c_double_p]
+        lib.ref_kernel_height.argtypes = [ctypes.c_void_p]
         lib.ref_kernel_destroy.argtypes = [ctypes.c_void_p]
         lib.ref_solver_create.restype = ctypes.c_void_p
         lib.ref_solver_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -331,6 +334,15 @@ class RefKernel:
         out = np.empty((self.ndof, self.ndof), dtype=np.complex128)
         rlib().ref_phi_at(self.h, nx, ny, qx, qy, _dp(out.view(np.float64)))
         return out
+
+    def dynamical_matrices(self, nx, ny, ky_first, nky):
+        """(U0, U, V) of get_dynamical_matrices per q: [nx, nky, 3, ndof, ndof] complex128."""
+        out = np.empty((nx, nky, 3, self.ndof, self.ndof), dtype=np.complex128)
+        rlib().ref_dynamical_matrices_columns(self.h, nx, ny, ky_first, nky, _dp(out.view(np.float64)))
+        return out
+
+    def height(self):
+        return rlib().ref_kernel_height(self.h)
 
     def linf(self):
         out = np.zeros(max(self.nu, 1))

@@ -130,6 +130,30 @@ void ref_phi_at(void *h, int nx, int ny, double qx, double qy, double *phi_out)
   k->kernel->post_compute();
 }
 
+/* U0, U, V of StiffnessKernel::get_dynamical_matrices for kx in [0,nx), ky in
+ * [ky_first, ky_first+nky), q as in fill_phi_buffer (gfmd_misc.cpp:43-48);
+ * out: [nx][nky][3][ndof*ndof] complex128. */
+void ref_dynamical_matrices_columns(void *h, int nx, int ny, int ky_first, int nky, double *out)
+{
+  RefKernel *k = (RefKernel *) h;
+  int ndof = k->kernel->get_dimension();
+  size_t dsq = (size_t) ndof * ndof;
+  double_complex *o = reinterpret_cast<double_complex *>(out);
+  k->kernel->pre_compute();
+  for (int i = 0; i < nx; i++) {
+    double qx = (i <= int((nx)/2)) ? (2.0*M_PI*(i)/nx) : (2.0*M_PI*(i-nx)/nx);
+    for (int jj = 0; jj < nky; jj++) {
+      int j = ky_first + jj;
+      double qy = (j <= int((ny)/2)) ? (2.0*M_PI*(j)/ny) : (2.0*M_PI*(j-ny)/ny);
+      double_complex *base = o + ((size_t) i * nky + jj) * 3 * dsq;
+      k->kernel->get_dynamical_matrices(qx, qy, base, base + dsq, base + 2 * dsq);
+    }
+  }
+  k->kernel->post_compute();
+}
+
+int ref_kernel_height(void *h) { return ((RefKernel *) h)->kernel->get_height(); }
+
 void ref_get_linf(void *h, double *linf)
 {
   RefKernel *k = (RefKernel *) h;

@@ -123,3 +123,21 @@ def test_gather_scatter_oracles_agree(oracle_libs):
     f1, s1, k1 = O.scatter(fxy, gid, mask, 2, np.zeros((n, 3)), nx=nx, ny=ny)
     f2, s2, k2 = O.c_scatter(fxy, gid, mask, 2, np.zeros((n, 3)), nx, ny)
     assert k1 == k2 and np.array_equal(f1, f2) and np.allclose(s1, s2, rtol=0, atol=1e-12)
+
+
+def test_synthetic_sc100_matrices_equal_the_plugin(oracle_libs):
+    """gfmd_b200.synthetic.sc100_dynamical_matrices (used to build the bench's sc100 table on
+    the device) against the reference plugin's get_dynamical_matrices."""
+    O = oracle_libs
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    import sys, os
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "user-gfmd_b200"))
+    from gfmd_b200 import synthetic
+    k = O.RefKernel("sc100 height 128")
+    assert k.height() == 128
+    ref = k.dynamical_matrices(12, 10, 0, 6)
+    mine = synthetic.sc100_dynamical_matrices(12, 10, 0, 6)
+    assert np.abs(ref - mine).max() < 1e-15
+    k.close()

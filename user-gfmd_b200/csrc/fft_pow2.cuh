@@ -74,6 +74,27 @@ __host__ __device__ inline int p2_freq_to_pos(int log, int k)
   return pos;
 }
 
+// Where plane c of wavevector kx lives inside one column's block of d*d*nx doubles:
+// off + c * cstride.  Generic kernels: plane-major [c][kx].  Specialised column kernels:
+// the spectrum is digit-reversed (pos) and the planes are interleaved item by item,
+// [pos / 64][(pos & 7) / 2][c][(pos >> 3) & 7][pos & 1], so that the 9 x 16-byte loads of
+// one contraction round of 8 neighbouring threads form one contiguous 1152-byte chunk.
+__host__ __device__ inline void phi_slot(bool fast, int top, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
+{
+  if (!fast) {
+    off = (size_t) kx;
+    cstride = (size_t) nx;
+    return;
+  }
+  // long columns: kx = R k' + q lives in sub-column q (a block of dsq * nx / R doubles)
+  const int q = kx & ((1 << top) - 1), ksub = kx >> top, logsub = lognx - top;
+  const int pos = p2_freq_to_pos(logsub, ksub);
+  const int blk = pos >> 6, a = (pos >> 3) & 7, r = pos & 7;
+  off = (size_t) q * dsq * ((size_t) nx >> top) + (size_t) blk * 64 * dsq + (size_t) (r >> 1) * 16 * dsq +
+        (size_t) a * 2 + (r & 1);
+  cstride = 16;
+}
+
 __device__ __forceinline__ double2 csqr(double2 a)
 {
   return make_double2(fma(a.x, a.x, -(a.y * a.y)), 2.0 * a.x * a.y);

@@ -18,6 +18,7 @@
 #include "fft_engine.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_fast.cuh"
+#include "kernel_phi_build.cuh"
 
 using namespace gfmd;
 
@@ -792,27 +793,6 @@ void try_pin(gfmd_b200 *h, const void *p, size_t bytes)
     cudaGetLastError();     // pageable copies still work
 }
 
-// Where plane c of wavevector kx lives inside one column's block of d*d*nx doubles:
-// off + c * cstride.  Generic kernels: plane-major [c][kx].  Specialised column kernels:
-// the spectrum is digit-reversed (pos) and the planes are interleaved item by item,
-// [pos / 64][(pos & 7) / 2][c][(pos >> 3) & 7][pos & 1], so that the 9 x 16-byte loads of
-// one contraction round of 8 neighbouring threads form one contiguous 1152-byte chunk.
-inline void phi_slot(bool fast, int top, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
-{
-  if (!fast) {
-    off = (size_t) kx;
-    cstride = (size_t) nx;
-    return;
-  }
-  // long columns: kx = R k' + q lives in sub-column q (a block of dsq * nx / R doubles)
-  const int q = kx & ((1 << top) - 1), ksub = kx >> top, logsub = lognx - top;
-  const int pos = p2_freq_to_pos(logsub, ksub);
-  const int blk = pos >> 6, a = (pos >> 3) & 7, r = pos & 7;
-  off = (size_t) q * dsq * ((size_t) nx >> top) + (size_t) blk * 64 * dsq + (size_t) (r >> 1) * 16 * dsq +
-        (size_t) a * 2 + (r & 1);
-  cstride = 16;
-}
-
 // Hermitian packing of one q: M = full d x d complex matrix (row-major), scale s.
 inline void pack_hermitian(const double *M, const double *Mneg, int d, double s, double *dst,
                            size_t plane_stride, double &amax, double &hdev, double &cdev)
@@ -1132,6 +1112,54 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
   }
   if (amax > 0 && hdev / amax > 1e-6)
     return fail(h, GFMD_B200_EPHI, "Phi table is not Hermitian: relative deviation %g", hdev / amax);
+  for (int k = 0; k < nky; ++k) h->phi_cols_set[ky_first - g.ky0 + k] = 1;
+  bool all = true;
+  for (char c : h->phi_cols_set) all = all && c;
+  h->phi_set = all;
+  return 0;
+}
+
+int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first, int nky, int height,
+                                int normalise)
+{
+  if (!h || !uuv) return fail(h, GFMD_B200_EINVAL, "build_phi_columns: null argument");
+  const GridDesc &g = h->g;
+  if (nky < 0 || ky_first < g.ky0 || ky_first + nky > g.ky0 + g.nky_loc)
+    return fail(h, GFMD_B200_EINVAL, "build_phi_columns: ky range [%d,%d) outside this handle's [%d,%d)",
+                ky_first, ky_first + nky, g.ky0, g.ky0 + g.nky_loc);
+  if (height < 0)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "build_phi_columns: height < 0 (iterate to convergence) is not "
+                "available on the device; use the host plugin table (gfmd_b200_set_phi_columns)");
+  if (nky == 0) return 0;
+  int rc = set_device(h);
+  if (rc) return rc;
+  const int d = g.d, nx = g.nx;
+  const size_t dsq = (size_t) d * d;
+  const size_t n = (size_t) nx * nky * 3 * dsq;
+  double2 *d_uuv = nullptr;
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMalloc((void **) &d_uuv, n * sizeof(double2)));
+  cudaError_t e = cudaMemcpy(d_uuv, uuv, n * sizeof(double2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const double scale = normalise ? 1.0 / ((double) nx * (double) g.ny) : 1.0;
+    double *dst = h->d_phi + (size_t) (ky_first - g.ky0) * dsq * nx;
+    const long long nq = (long long) nx * nky;
+    const int grid = (int) ((nq + 63) / 64);
+    const int lognx = ilog2_rt(nx);
+    switch (d) {
+      case 3: k_build_phi<3><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
+      case 6: k_build_phi<6><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
+      case 9: k_build_phi<9><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
+      case 12: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
+      default:
+        cudaFree(d_uuv);
+        return fail(h, GFMD_B200_EUNSUPPORTED, "build_phi_columns: ndof %d (3, 6, 9, 12 supported)", d);
+    }
+    h->launches++;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_uuv);
+  CU(h, e);
   for (int k = 0; k < nky; ++k) h->phi_cols_set[ky_first - g.ky0 + k] = 1;
   bool all = true;
   for (char c : h->phi_cols_set) all = all && c;

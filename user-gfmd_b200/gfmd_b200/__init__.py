@@ -45,6 +45,7 @@ ABI = {
     "gfmd_b200_set_phi": (_i, [_vp, _vp, _i, _vp]),
     "gfmd_b200_set_phi_columns": (_i, [_vp, _vp, _i, _i, _i]),
     "gfmd_b200_set_linf": (_i, [_vp, _vp]),
+    "gfmd_b200_build_phi_columns": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "gfmd_b200_phi_deviation": (_i, [_vp, c_double_p, c_double_p]),
     "gfmd_b200_post_force_host": (_i, [_vp, _vp, _vp, c_double_p, _vp]),
     "gfmd_b200_pre_force_async_host": (_i, [_vp, _vp]),
@@ -212,6 +213,14 @@ class GFMDSolverB200:
         nky = phi_cols.size // (self.nx * self.ndof * self.ndof)
         self._check(self.lib.gfmd_b200_set_phi_columns(self.h, phi_cols.ctypes.data, ky_first, nky,
                                                        int(normalized)))
+
+    def build_kernel_columns(self, uuv, ky_first, height, normalize=True):
+        """Device-side transfer-matrix recursion.  uuv: [nx, nky, 3, ndof, ndof] complex128 =
+        (U0, U, V) of StiffnessKernel::get_dynamical_matrices for every q of the column block."""
+        uuv = np.ascontiguousarray(uuv, dtype=np.complex128)
+        nky = uuv.size // (self.nx * 3 * self.ndof * self.ndof)
+        self._check(self.lib.gfmd_b200_build_phi_columns(self.h, uuv.ctypes.data, ky_first, nky, height,
+                                                         int(normalize)))
 
     def set_linf(self, linf):
         linf = np.ascontiguousarray(linf, dtype=np.float64)

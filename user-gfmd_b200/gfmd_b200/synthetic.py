@@ -72,3 +72,33 @@ def atoms_for_slab(nx, ny, x0, nx_loc, u):
     x = xeq + np.moveaxis(u.reshape(3, n), 0, 1)
     mask = np.ones(n, dtype=np.int32)
     return x, xeq, gid, mask
+
+
+def sc100_dynamical_matrices(nx, ny, ky_first, nky):
+    """U0(q), U(q), V(q) of the simple-cubic (100) surface with unit nearest- and
+    next-nearest-neighbour springs -- what the reference's `sc100` stiffness kernel feeds
+    into the transfer-matrix recursion (SC100StiffnessKernel::get_per_layer_dynamical_matrices,
+    src/stiffness_kernels/sc100_stiffness.cpp:170-228).  Layout of
+    gfmd_b200_build_phi_columns: [nx, nky, 3, 3, 3] complex128, q as in fill_phi_buffer."""
+    i = np.arange(nx)
+    j = np.arange(ky_first, ky_first + nky)
+    qx = np.where(i <= nx // 2, 2.0 * np.pi * i / nx, 2.0 * np.pi * (i - nx) / nx)
+    qy = np.where(j <= ny // 2, 2.0 * np.pi * j / ny, 2.0 * np.pi * (j - ny) / ny)
+    QX, QY = np.meshgrid(qx, qy, indexing="ij")
+    cx, cy, sx, sy = np.cos(QX), np.cos(QY), np.sin(QX), np.sin(QY)
+    M = np.zeros((nx, nky, 3, 3, 3), dtype=np.complex128)
+    U0, U, V = M[:, :, 0], M[:, :, 1], M[:, :, 2]
+    U[..., 0, 0] = 6 - 2 * cx * (1 + cy)
+    U[..., 1, 1] = 6 - 2 * cy * (1 + cx)
+    U[..., 2, 2] = 6
+    U[..., 0, 1] = U[..., 1, 0] = 2 * sx * sy
+    U0[..., 0, 0] = 5 - 2 * cx * (1 + cy)
+    U0[..., 1, 1] = 5 - 2 * cy * (1 + cx)
+    U0[..., 2, 2] = 3
+    U0[..., 0, 1] = U0[..., 1, 0] = 2 * sx * sy
+    V[..., 0, 0] = -cx
+    V[..., 1, 1] = -cy
+    V[..., 2, 2] = -1 - cx - cy
+    V[..., 0, 2] = V[..., 2, 0] = 1j * sx
+    V[..., 1, 2] = V[..., 2, 1] = 1j * sy
+    return M
