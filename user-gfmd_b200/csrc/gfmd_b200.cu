@@ -233,7 +233,7 @@ struct gfmd_b200 {
   // chunked pipeline: column chunks overlap their own transposes
   static constexpr int kMaxChunks = 8;
   int nchunks = 1, chunk_kl = 0;
-  cudaEvent_t ev_chunk[kMaxChunks][kMaxRanks] = {}, ev_k2[kMaxChunks] = {};
+  cudaEvent_t ev_chunk[kMaxChunks][kMaxRanks] = {}, ev_k2[kMaxChunks] = {}, ev_row[GFMD_B200_MAX_NDOF] = {};
   double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
   int fsum_part_cap = 0;
   StepResults *d_res = nullptr, *h_res = nullptr;
@@ -575,36 +575,50 @@ int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
   return 0;
 }
 
-// Multi-GPU column stage with the transposes overlapped: the local ky range is cut into
-// chunks; all forward pushes are queued on the per-peer copy streams right after the row
-// kernel, chunk c is transformed as soon as ITS pushes have landed everywhere (NCCL
-// all-reduce as barrier), and its result is pushed back while chunk c+1 is transformed.
-int pipelined_columns(gfmd_b200 *h, double2 *A, double2 *B, double2 *B2)
+// Multi-GPU step with the transposes overlapped (peer pushes on copy-engine streams):
+//   * rows are transformed dof by dof; the blocks of a finished dof are pushed while the
+//     next dof is transformed (the last dof's push is cut into the ky chunks below);
+//   * the local ky range is cut into chunks of whole waves of the persistent column kernel;
+//     chunk c is transformed as soon as ITS data has landed everywhere (NCCL all-reduce as
+//     barrier), and its result is pushed back while chunk c+1 is transformed.
+int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, double2 *B2)
 {
   const GridDesc &g = h->g;
   NcclApi &a = nccl();
   const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;
-  const size_t pitch = (size_t) g.kyb * g.nx_loc * sizeof(double2);     // between dofs of a block
+  const size_t dblk = (size_t) g.kyb * g.nx_loc;                        // one dof of a block
+  const size_t pitch = dblk * sizeof(double2);
   const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
   const int nc = h->nchunks, ck = h->chunk_kl;
 
-  stage_mark(h, 2);
-  stage_mark(h, 3);
-  // own blocks stay on the compute stream
-  CU(h, cudaMemcpyAsync(B + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
-                        h->stream));
-  CU(h, cudaEventRecord(h->ev_fork, h->stream));
-  for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->copy_stream[(g.rank + k) % g.P], h->ev_fork, 0));
-  for (int c = 0; c < nc; ++c) {
-    const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
-    const size_t off = (size_t) k0 * g.nx_loc, width = (size_t) (k1 - k0) * g.nx_loc * sizeof(double2);
+  stage_mark(h, 1);
+  for (int dof = 0; dof < g.d; ++dof) {
+    int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, dof, 1);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
+    CU(h, cudaEventRecord(h->ev_row[dof], h->stream));
     for (int k = 1; k < g.P; ++k) {
       const int r = (g.rank + k) % g.P;
-      CU(h, cudaMemcpy2DAsync(h->peer_recv[0][r] + g.rank * blk + off, pitch, A + r * blk + off, pitch, width,
-                              g.d, cudaMemcpyDeviceToDevice, h->copy_stream[r]));
-      CU(h, cudaEventRecord(h->ev_chunk[c][r], h->copy_stream[r]));
+      CU(h, cudaStreamWaitEvent(h->copy_stream[r], h->ev_row[dof], 0));
+      if (dof < g.d - 1) {
+        CU(h, cudaMemcpyAsync(h->peer_recv[0][r] + g.rank * blk + dof * dblk, A + r * blk + dof * dblk,
+                              dblk * sizeof(double2), cudaMemcpyDeviceToDevice, h->copy_stream[r]));
+      } else {
+        for (int c = 0; c < nc; ++c) {
+          const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
+          const size_t off = dof * dblk + (size_t) k0 * g.nx_loc;
+          CU(h, cudaMemcpyAsync(h->peer_recv[0][r] + g.rank * blk + off, A + r * blk + off,
+                                (size_t) (k1 - k0) * g.nx_loc * sizeof(double2), cudaMemcpyDeviceToDevice,
+                                h->copy_stream[r]));
+          CU(h, cudaEventRecord(h->ev_chunk[c][r], h->copy_stream[r]));
+        }
+      }
     }
   }
+  stage_mark(h, 2);
+  stage_mark(h, 3);
+  // own block stays on the compute stream
+  CU(h, cudaMemcpyAsync(B + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
+                        h->stream));
   for (int c = 0; c < nc; ++c) {
     const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
     const size_t off = (size_t) k0 * g.nx_loc, width = (size_t) (k1 - k0) * g.nx_loc * sizeof(double2);
@@ -644,6 +658,11 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
 
   CU(h, cudaMemsetAsync(&h->d_res->epot, 0, offsetof(StepResults, fsum), h->stream));
 
+  const bool pipelined = g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->fast_rows && h->nchunks > 1;
+  if (pipelined) {
+    int rc = pipelined_step(h, d_u, A, B, B2);
+    if (rc) return rc;
+  } else {
   stage_mark(h, 1);
   if (h->fast_rows) {
     int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
@@ -657,10 +676,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
           d_u, A, g, h->fft_rows.desc, h->d_tw_ny, h->rows_RB, h->rows_ld);
     h->launches++;
   }
-  if (g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->nchunks > 1) {
-    int rc = pipelined_columns(h, A, B, B2);
-    if (rc) return rc;
-  } else {
+  {
     stage_mark(h, 2);
     if (g.P > 1) {
       int rc = exchange(h, A, B, 0);
@@ -698,6 +714,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
                              h->stream));
     }
   }
+  }   // !pipelined
   stage_mark(h, 5);
   if (h->fast_rows) {
     int rc = fast_rows_inv(h->fast_rows, B2, d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
@@ -952,6 +969,8 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     h->chunk_kl = waves * per_wave;
     h->nchunks = (h->g.kyb + h->chunk_kl - 1) / h->chunk_kl;
     if (h->nchunks > gfmd_b200::kMaxChunks) { h->nchunks = 1; h->chunk_kl = h->g.kyb; }
+    for (int i = 0; i < h->g.d; ++i)
+      if (!h->ev_row[i]) CU(h, cudaEventCreateWithFlags(&h->ev_row[i], cudaEventDisableTiming));
     for (int c = 0; c < h->nchunks; ++c) {
       if (!h->ev_k2[c]) CU(h, cudaEventCreateWithFlags(&h->ev_k2[c], cudaEventDisableTiming));
       for (int r = 0; r < h->g.P; ++r)
@@ -979,6 +998,8 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
     if (h->ev_join[r]) cudaEventDestroy(h->ev_join[r]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < GFMD_B200_MAX_NDOF; ++i)
+    if (h->ev_row[i]) cudaEventDestroy(h->ev_row[i]);
   for (int c = 0; c < gfmd_b200::kMaxChunks; ++c) {
     if (h->ev_k2[c]) cudaEventDestroy(h->ev_k2[c]);
     for (int r = 0; r < gfmd_b200::kMaxRanks; ++r)

@@ -142,15 +142,15 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
 template <int NR, int RB, int T>
 __global__ void __launch_bounds__(T)
 k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
-              const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny)
+              const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
 {
   constexpr int LOG = P2<NR>::LOG;
   constexpr int AX = RB == 2 ? 2 : 1;       // per-row column XOR: rows of a tile never collide
   extern __shared__ double2 sm[];
   double2 *tws = sm + RB * NR;
   const int nblk = g.nx_loc / RB;
-  const int dof = blockIdx.x / nblk;
-  const int ix0 = (blockIdx.x - dof * nblk) * RB;
+  const int dof = dof0 + blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x % nblk) * RB;
   const int ny = 2 * NR;
   p2_fill_tws<NR>(tws, tw);
   __syncthreads();
@@ -196,7 +196,7 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
 template <int NR, int RB, int T>
 __global__ void __launch_bounds__(T)
 k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
-              const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny)
+              const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
 {
   constexpr int LOG = P2<NR>::LOG;
   constexpr int AX = RB == 2 ? 2 : 1;
@@ -204,8 +204,8 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   double2 *tws = sm + RB * NR;
   double2 *yh = tws + P2<NR>::TWS;          // Y[h] of each row
   const int nblk = g.nx_loc / RB;
-  const int dof = blockIdx.x / nblk;
-  const int ix0 = (blockIdx.x - dof * nblk) * RB;
+  const int dof = dof0 + blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x % nblk) * RB;
   const int ny = 2 * NR;
   constexpr int h = NR;
   p2_fill_tws<NR>(tws, tw);
@@ -369,18 +369,19 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
 }
 
 inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const GridDesc &g, const double2 *tw_ny,
-                         const FftDesc &fd, cudaStream_t s, long long *launches)
+                         const FftDesc &fd, cudaStream_t s, long long *launches, int dof0 = 0, int ndofs = -1)
 {
   FastRowsCfg rc;
   if (!fast_rows_cfg(variant, rc)) return 1;
-  const int grid = g.d * (g.nx_loc / rc.rb);
+  if (ndofs < 0) ndofs = g.d - dof0;
+  const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-    case 2048: k_rows_fwd_p2<1024, 4, 128><<<grid, 128, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
-    case 4096: k_rows_fwd_p2<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
-    case 4097: k_rows_fwd_p2<2048, 4, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
-    case 8192: k_rows_fwd_p2<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
-    case 16384: k_rows_fwd_p2<8192, 1, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny); break;
+    case 2048: k_rows_fwd_p2<1024, 4, 128><<<grid, 128, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 4096: k_rows_fwd_p2<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 4097: k_rows_fwd_p2<2048, 4, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 8192: k_rows_fwd_p2<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 16384: k_rows_fwd_p2<8192, 1, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     default: return 1;
   }
   ++*launches;
@@ -388,18 +389,19 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
 }
 
 inline int fast_rows_inv(int variant, const double2 *stage, double *f, const GridDesc &g, const double2 *tw_ny,
-                         const FftDesc &fd, cudaStream_t s, long long *launches)
+                         const FftDesc &fd, cudaStream_t s, long long *launches, int dof0 = 0, int ndofs = -1)
 {
   FastRowsCfg rc;
   if (!fast_rows_cfg(variant, rc)) return 1;
-  const int grid = g.d * (g.nx_loc / rc.rb);
+  if (ndofs < 0) ndofs = g.d - dof0;
+  const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-    case 2048: k_rows_inv_p2<1024, 4, 128><<<grid, 128, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
-    case 4096: k_rows_inv_p2<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
-    case 4097: k_rows_inv_p2<2048, 4, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
-    case 8192: k_rows_inv_p2<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
-    case 16384: k_rows_inv_p2<8192, 1, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny); break;
+    case 2048: k_rows_inv_p2<1024, 4, 128><<<grid, 128, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 4096: k_rows_inv_p2<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 4097: k_rows_inv_p2<2048, 4, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 8192: k_rows_inv_p2<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 16384: k_rows_inv_p2<8192, 1, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     default: return 1;
   }
   ++*launches;
