@@ -321,9 +321,23 @@ def main_b200(args):
     alg_bytes = (16 * d + 4 * d * d) * cells_loc
     t_cols = stage_ms["cols_fused"] * 1e-3
     achieved = alg_bytes / t_cols / 1e9 if t_cols > 0 else 0.0
-    roofline = {"kernel": "k_cols_fused (x-FFT + Phi.u + energy + x-IFFT)", "bound": "hbm",
+    # DRAM bytes of that kernel from the committed ncu --set full capture (same grid, 1 GPU)
+    traffic = None
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")))
+        if world == 1 and (nx, ny) == (4096, 4096):
+            for kname, m in summ.items():
+                if "k_cols_fused" in kname:
+                    def gb(x):
+                        v, unit = x.split()[:2]
+                        return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+                    traffic = gb(m["dram__bytes_read.sum"]) + gb(m["dram__bytes_write.sum"])
+    except Exception:
+        traffic = None
+    roofline = {"kernel": "k_cols_fused_p2_lr (x-FFT + Phi.u + energy + gamma point + x-IFFT) + k_finalize",
+                "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": stage_ms["cols_fused"],
                 "solver_bytes_per_step": (80 * d + 4 * d * d) * cells_loc,

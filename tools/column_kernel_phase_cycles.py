@@ -1,5 +1,7 @@
+"""Cycle counts of the phases of k_cols_fused_p2_lr (clock64 marks of CTA 0); needs a library built with
+GFMD_NVCC_EXTRA=-DGFMD_PHASE_TIMING sh user-gfmd_b200/csrc/build.sh."""
 import sys, ctypes, numpy as np, torch
-sys.path.insert(0,'/root/repo/user-gfmd_b200'); sys.path.insert(0,'/root/repo')
+import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,os.path.join(ROOT,'user-gfmd_b200')); sys.path.insert(0,ROOT)
 import gfmd_b200
 from gfmd_b200 import synthetic
 nx=ny=4096; d=3

@@ -1,5 +1,6 @@
+"""Per-stage CUDA-event times of the solver step on one GPU: python tools/stage_times.py [nx [ny]]."""
 import sys, numpy as np, torch
-sys.path.insert(0,'/root/repo/user-gfmd_b200'); sys.path.insert(0,'/root/repo')
+import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,os.path.join(ROOT,'user-gfmd_b200')); sys.path.insert(0,ROOT)
 import gfmd_b200
 from gfmd_b200 import synthetic
 nx=int(sys.argv[1]) if len(sys.argv)>1 else 4096

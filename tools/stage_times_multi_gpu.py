@@ -1,5 +1,7 @@
+"""Per-stage times of the slab-decomposed step: torchrun --nproc-per-node N tools/stage_times_multi_gpu.py
+(EXCH=nccl selects the NCCL send/recv exchange, GFMD_B200_CHUNKS=n the pipeline depth)."""
 import os, sys, numpy as np, torch, torch.distributed as dist
-sys.path.insert(0,'/root/repo/user-gfmd_b200'); sys.path.insert(0,'/root/repo')
+import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,os.path.join(ROOT,'user-gfmd_b200')); sys.path.insert(0,ROOT)
 import gfmd_b200
 from gfmd_b200 import synthetic
 rank=int(os.environ['RANK']); world=int(os.environ['WORLD_SIZE']); local=int(os.environ['LOCAL_RANK'])
