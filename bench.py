@@ -122,7 +122,7 @@ class ClockSampler:
 
 # --------------------------------------------------------------- reference ---
 
-def reference_run(nx, ny, d, steps, warmup, budget_s=150.0):
+def reference_run(nx, ny, d, steps, warmup, budget_s=100.0):
     """Times the reference's GFMDSolverStatic::post_force (its own sources, FFT3d shim
     backed by oracle/fft_plain.c with OpenMP) on host arrays.  Returns a dict."""
     from oracle import gfmd_oracle as O
@@ -156,7 +156,8 @@ def reference_run(nx, ny, d, steps, warmup, budget_s=150.0):
     nxs, nys = nx, ny
     probe_n = min(nx, 1024)
     dt_probe, _ = one(probe_n, probe_n, 1, 1)
-    est_full = dt_probe * (nx * ny) / float(probe_n * probe_n) * 1.3
+    # large grids fall out of the caches and run ~2x slower per cell than the probe
+    est_full = dt_probe * (nx * ny) / float(probe_n * probe_n) * 2.5
     while est_full * (steps + warmup) * (nxs * nys) / float(nx * ny) > budget_s and nxs > 256:
         nxs //= 2
         nys //= 2
