@@ -110,13 +110,24 @@ bool factor_smooth(int n, FftCore &c)
   return rem == 1;
 }
 
+// Blocking host-to-device copy for set-up paths.  cudaMemcpy from pageable memory may return
+// once the data sits in the driver's staging buffer, before the DMA has landed (CUDA API
+// synchronisation notes), and the legacy stream it runs on is not ordered against this
+// library's non-blocking streams -- so wait for the device before any kernel may read it.
+cudaError_t h2d_blocking(void *dst, const void *src, size_t bytes)
+{
+  cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceSynchronize();
+}
+
 cudaError_t upload(const void *src, size_t bytes, void **dst, DevFft &f)
 {
   cudaError_t e = cudaMalloc(dst, bytes);
   if (e != cudaSuccess) return e;
   f.allocs.push_back(*dst);
   f.bytes += bytes;
-  return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  return h2d_blocking(*dst, src, bytes);
 }
 
 // host-side complex FFT by definition-free recursion is not needed: the chirp
@@ -336,7 +347,7 @@ int plan(gfmd_b200 *h)
     std::vector<double2> tw;
     fill_tw(tw, g.ny);
     CU(h, dmalloc(h, &h->d_tw_ny, (size_t) g.ny));
-    CU(h, cudaMemcpy(h->d_tw_ny, tw.data(), sizeof(double2) * g.ny, cudaMemcpyHostToDevice));
+    CU(h, h2d_blocking(h->d_tw_ny, tw.data(), sizeof(double2) * g.ny));
   }
   int ld = h->fft_rows.desc.ld_min;
   const int need = h->even ? g.ny / 2 + 1 : g.ny;
@@ -479,6 +490,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess) ce = cudaMemset(h->d_linf, 0, sizeof(double) * GFMD_B200_MAX_NDOF);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1) * kColsNW * 4);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_res, 0, sizeof(StepResults));
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();     // memsets ran on the legacy stream
   if (ce != cudaSuccess) {
     h->err = std::string("device allocation failed: ") + cudaGetErrorString(ce);
     return bail(GFMD_B200_ECUDA);
@@ -915,6 +927,7 @@ int gfmd_b200_ipc_export(gfmd_b200_t *h, char *handles)
   if (!h->d_stage3) {
     CU(h, dmalloc(h, &h->d_stage3, nstage));
     CU(h, cudaMemset(h->d_stage3, 0, sizeof(double2) * nstage));
+    CU(h, cudaDeviceSynchronize());      // before any peer may push into it
   }
   cudaIpcMemHandle_t m[2];
   CU(h, cudaIpcGetMemHandle(&m[0], h->d_stage2));
@@ -956,6 +969,7 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
   if (!h->d_barrier) {
     CU(h, dmalloc(h, &h->d_barrier, (size_t) 1));
     CU(h, cudaMemset(h->d_barrier, 0, sizeof(double)));
+    CU(h, cudaDeviceSynchronize());
   }
   // chunking of the column stage: whole waves of the persistent column kernel per chunk
   {
@@ -1055,7 +1069,7 @@ int gfmd_b200_set_linf(gfmd_b200_t *h, const double *linf)
   if (linf)
     for (int i = 0; i < h->g.d / 3; ++i) tmp[i] = linf[i];
   CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(h->d_linf, tmp, sizeof(tmp), cudaMemcpyHostToDevice));
+  CU(h, h2d_blocking(h->d_linf, tmp, sizeof(tmp)));
   return 0;
 }
 
@@ -1088,8 +1102,7 @@ int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised,
         pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     }
-    CU(h, cudaMemcpy(h->d_phi + (size_t) k0 * dsq * nx, buf.data(), sizeof(double) * (size_t) nk * dsq * nx,
-                     cudaMemcpyHostToDevice));
+    CU(h, h2d_blocking(h->d_phi + (size_t) k0 * dsq * nx, buf.data(), sizeof(double) * (size_t) nk * dsq * nx));
   }
   h->herm_dev = amax > 0 ? hdev / amax : 0.0;
   h->conj_dev = amax > 0 ? cdev / amax : 0.0;
@@ -1128,8 +1141,8 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
         phi_slot(h->fast_cols != 0, h->cols_top, lognx, nx, dsq, kx, off, cstride);
         pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
-    CU(h, cudaMemcpy(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),
-                     sizeof(double) * (size_t) nk * dsq * nx, cudaMemcpyHostToDevice));
+    CU(h, h2d_blocking(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),
+                       sizeof(double) * (size_t) nk * dsq * nx));
   }
   if (amax > 0 && hdev / amax > 1e-6)
     return fail(h, GFMD_B200_EPHI, "Phi table is not Hermitian: relative deviation %g", hdev / amax);
@@ -1160,7 +1173,7 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
   double2 *d_uuv = nullptr;
   CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMalloc((void **) &d_uuv, n * sizeof(double2)));
-  cudaError_t e = cudaMemcpy(d_uuv, uuv, n * sizeof(double2), cudaMemcpyHostToDevice);
+  cudaError_t e = h2d_blocking(d_uuv, uuv, n * sizeof(double2));
   if (e == cudaSuccess) {
     const double scale = normalise ? 1.0 / ((double) nx * (double) g.ny) : 1.0;
     double *dst = h->d_phi + (size_t) (ky_first - g.ky0) * dsq * nx;
