@@ -149,6 +149,27 @@ int gfmd_b200_pre_force_async_host(gfmd_b200_t *h, const double *u);
  * epot/u0 with gfmd_b200_get_results.  NULL selects the library-owned grids. */
 int gfmd_b200_post_force_device(gfmd_b200_t *h, const double *d_u, double *d_f);
 
+/* ---- off-path services of the reference solver (single-rank handles) ----- */
+
+/* What GFMDSolverFFT::dump writes on `dumpq_every` steps (gfmd_solver_fft.cpp:209-287,
+ * called from gfmd_solver_static.cpp:181-182): uq = u~(q), the unnormalised forward DFT of
+ * the HOST field u [ndof][nx*ny], and fq = Phi(q).u~(q) with the (normalised) table of this
+ * handle, no sign flip.  Both come back in the reference's q_buffer layout,
+ * [nx*ny][ndof] complex128 interleaved, idq = ix*ny + iy, full spectrum.  fq may be NULL.
+ * Limited to grids whose column set fits one CTA (nx * ndof * 16 B <= 227 KB). */
+int gfmd_b200_spectrum_host(gfmd_b200_t *h, const double *u, double *uq_ri, double *fq_ri);
+
+/* GFMDSolverStatic::prec_gradient (gfmd_solver_static.cpp:253-271) with
+ * precondition_gradient<DEF_G> (gfmd_misc.h:39-133):
+ *   gP = IDFT[ (Phi(q) + Cavg)^-1 DFT[g] ],  both transforms unnormalised, Phi the
+ * normalised table.  cavg: real [ndof][ndof] row-major; g, gP: HOST [ndof][nx*ny].
+ * ndof 3, 6, 9, 12.  first3_only != 0 reproduces the reference for ndof > 3, whose general
+ * branch copies only components 0..2 of the result back (`idim < 3`, gfmd_misc.h:113-115)
+ * and leaves the others un-preconditioned -- what the drop-in host glue passes;
+ * first3_only == 0 replaces all components. */
+int gfmd_b200_prec_gradient_host(gfmd_b200_t *h, const double *cavg, const double *g, double *gP,
+                                 int first3_only);
+
 /* ---- device-resident fix-side stages ------------------------------------ */
 
 /* FixGFMD::pre_force list->grid (fix_gfmd.cpp:734-803): u = x - xeq with x/y

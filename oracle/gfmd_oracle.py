@@ -19,6 +19,8 @@ Reference lines restated here:
   grid partition  src/main/gfmd_solver.cpp:95-135
   gather          src/main/fix_gfmd.cpp:734-803
   scatter         src/main/fix_gfmd.cpp:952-1010, :896-902
+  spectrum/dump   src/solvers/gfmd_solver_fft.cpp:209-287
+  prec_gradient   src/solvers/gfmd_solver_static.cpp:253-271, src/main/gfmd_misc.h:39-133
 
 PINNING: checked against libgfmd_ref.so and tests/golden in tests/test_oracle.py.
 """
@@ -100,6 +102,61 @@ def post_force(u, phi, linf, fft=None):
     fq = np.moveaxis(q, 0, 1).reshape(ndof, nx, ny)
     f = fft.ifft2(fq, axes=(1, 2)).real * (nx * ny)     # unnormalised backward
     return np.ascontiguousarray(f), epot, u0
+
+
+def spectrum(u, phi, fft=None):
+    """The q-space fields GFMDSolverFFT::dump writes (src/solvers/gfmd_solver_fft.cpp:209-287,
+    called from gfmd_solver_static.cpp:181-182): u(q) = unnormalised forward DFT in the
+    q_buffer layout [idq = ix*ny + iy][idim], and F(q) = Phi(q).u(q) (MatMulVec, no sign flip).
+    Returns uq, fq: [nx*ny, ndof] complex128."""
+    if fft is None:
+        fft = np.fft
+    ndof, nx, ny = u.shape
+    uq = fft.fft2(u, axes=(1, 2))
+    q = np.ascontiguousarray(np.moveaxis(uq.reshape(ndof, nx * ny), 0, 1))
+    F = np.einsum("qij,qj->qi", phi.reshape(nx * ny, ndof, ndof), q)
+    return q, F
+
+
+def dump_fields(uq, fq, nx, ny):
+    """What each <prefix>.q.*.out file of GFMDSolverFFT::dump holds, as [ny, nx] arrays (file
+    rows = iy, columns = ix; gfmd_solver_fft.cpp:247-275): u<i>.real/imag, f<i>.real/imag,
+    uP = sum |u|^2, fP = sum |F|^2, e = Re sum u conj(F)."""
+    ndof = uq.shape[1]
+    U = uq.reshape(nx, ny, ndof)
+    F = fq.reshape(nx, ny, ndof)
+    out = {}
+    for i in range(ndof):
+        out["u%d.real" % i] = U[:, :, i].real.T
+        out["u%d.imag" % i] = U[:, :, i].imag.T
+        out["f%d.real" % i] = F[:, :, i].real.T
+        out["f%d.imag" % i] = F[:, :, i].imag.T
+    out["uP"] = (np.abs(U) ** 2).sum(axis=2).T
+    out["fP"] = (np.abs(F) ** 2).sum(axis=2).T
+    out["e"] = (U * np.conj(F)).sum(axis=2).real.T
+    return out
+
+
+def prec_gradient(g, phi, cavg, fft=None, reference_quirk=False):
+    """GFMDSolverStatic::prec_gradient (src/solvers/gfmd_solver_static.cpp:253-271) with
+    precondition_gradient<DEF_G> (src/main/gfmd_misc.h:39-133):
+    gP = IDFT[(Phi(q) + Cavg)^-1 DFT[g]], transforms unnormalised, Phi as stored (divided by
+    nx*ny).  g: [ndof, nx, ny]; cavg: [ndof, ndof] real.
+
+    reference_quirk: for ndof > 3 the reference's general branch copies only the first
+    three components of the result back (``idim < 3``, gfmd_misc.h:113-115), leaving the
+    others un-preconditioned; True reproduces that."""
+    if fft is None:
+        fft = np.fft
+    ndof, nx, ny = g.shape
+    gq = fft.fft2(g, axes=(1, 2))
+    q = np.ascontiguousarray(np.moveaxis(gq.reshape(ndof, nx * ny), 0, 1))
+    M = phi.reshape(nx * ny, ndof, ndof) + np.asarray(cavg, dtype=np.float64).reshape(1, ndof, ndof)
+    y = np.linalg.solve(M, q[..., None])[..., 0]
+    if reference_quirk and ndof > 3:
+        y[:, 3:] = q[:, 3:]
+    yq = np.moveaxis(y, 0, 1).reshape(ndof, nx, ny)
+    return np.ascontiguousarray(fft.ifft2(yq, axes=(1, 2)).real * (nx * ny))
 
 
 def gather(x, xeq, gid, mask, groupbit, nx, ny, ndof, xprd, yprd,
@@ -308,6 +365,10 @@ def rlib():
         lib.ref_solver_post_force.restype = ctypes.c_double
         lib.ref_solver_post_force.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
         lib.ref_solver_destroy.argtypes = [ctypes.c_void_p]
+        lib.ref_solver_prec_gradient.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
+        lib.ref_solver_post_force_dump.restype = ctypes.c_double
+        lib.ref_solver_post_force_dump.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_char_p]
+        lib.ref_solver_dump_tables.argtypes = [ctypes.c_void_p]
         lib.ref_set_fft_backend.argtypes = [ctypes.c_int]
         _rlib = lib
     return _rlib
@@ -380,6 +441,32 @@ class RefSolver:
         u0 = np.empty(self.ndof)
         e = rlib().ref_solver_post_force(self.h, _dp(u), _dp(f), _dp(u0))
         return f.reshape(self.ndof, self.nx, self.ny), e, u0
+
+    def prec_gradient(self, cavg, g):
+        """GFMDSolverStatic::prec_gradient of the reference sources."""
+        rlib().ref_set_fft_backend(self.backend)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        cavg = np.ascontiguousarray(cavg, dtype=np.float64)
+        gP = np.empty_like(g)
+        rlib().ref_solver_prec_gradient(self.h, _dp(cavg), _dp(g), _dp(gP))
+        return gP.reshape(self.ndof, self.nx, self.ny)
+
+    def post_force_dump(self, u, prefix):
+        """post_force on a `dumpq_every` step: writes <prefix>.q.*.out (GFMDSolverFFT::dump)."""
+        rlib().ref_set_fft_backend(self.backend)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        f = np.empty_like(u)
+        e = rlib().ref_solver_post_force_dump(self.h, _dp(u), _dp(f), prefix.encode())
+        return f.reshape(self.ndof, self.nx, self.ny), e
+
+    def dump_tables(self, directory):
+        """dump_stiffness + dump_greens_function; they write into the current directory."""
+        cwd = os.getcwd()
+        os.chdir(directory)
+        try:
+            rlib().ref_solver_dump_tables(self.h)
+        finally:
+            os.chdir(cwd)
 
     def close(self):
         if self.h:

@@ -100,3 +100,81 @@ extern "C" int hostshim_compare(const char *kernel_string, int nx, int ny, unsig
   delete lmp;
   return 0;
 }
+
+
+/* The off-path services through the same plugin interface: dump_stiffness,
+ * dump_greens_function, post_force on a `dumpq_every` step (dump_prefix != NULL) and
+ * prec_gradient, run by the reference's GFMDSolverStatic in directory dir_ref and by
+ * GFMDSolverB200 in directory dir_b200 (the dumps go to the current directory); the test
+ * compares the two sets of files.  out[0] = max|gP_b200 - gP_ref| / max|gP_ref|,
+ * out[1] = max|f_b200 - f_ref| / max|f_ref| of the dump step.  Returns 0 on success. */
+#include <unistd.h>
+
+extern "C" int hostshim_compare_aux(const char *kernel_string, int nx, int ny, unsigned seed,
+                                    const char *dir_ref, const char *dir_b200, double cdiag, double *out)
+{
+  LAMMPS *lmp = new LAMMPS();
+  lmp->domain->set_cell(nx, ny, 1);
+  std::vector<char *> argv = split(kernel_string);
+  int carg = 1;
+  StiffnessKernel *kernel = stiffness_kernel_factory(argv[0], (int) argv.size(), &carg, argv.data(),
+                                                     lmp->domain, lmp->force, lmp->memory, lmp->error);
+  if (!kernel) return 1;
+  const int ndof = kernel->get_dimension();
+
+  oracle_fft_backend = (nx * ny <= 4096) ? 0 : 1;
+  char kw[] = "static";
+  int c0 = 0;
+  GFMDSolver *solvers[2] = {gfmd_solver_factory(kw, lmp, 0, &c0, NULL), new GFMDSolverB200(lmp, 0, &c0, NULL)};
+  const char *dirs[2] = {dir_ref, dir_b200};
+
+  double **u, **f[2], **gP[2];
+  lmp->memory->create(u, ndof, nx * ny, "u");
+  for (int s = 0; s < 2; s++) {
+    lmp->memory->create(f[s], ndof, nx * ny, "f");
+    lmp->memory->create(gP[s], ndof, nx * ny, "gP");
+  }
+  srand(seed);
+  for (int i = 0; i < ndof * nx * ny; i++) u[0][i] = 0.2 * (rand() / (double) RAND_MAX) - 0.1;
+  std::vector<double> cavg((size_t) ndof * ndof);
+  for (int i = 0; i < ndof; i++)
+    for (int j = 0; j < ndof; j++)
+      cavg[i * ndof + j] = ((i == j ? cdiag : 0.0) + 0.05 * cdiag * (rand() / (double) RAND_MAX - 0.5)) / (nx * ny);
+
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd))) return 4;
+  for (int s = 0; s < 2; s++) {
+    if (chdir(dirs[s])) return 5;
+    solvers[s]->set_grid_size(nx, ny, ndof);
+    solvers[s]->init();
+    solvers[s]->set_kernel(kernel);
+    solvers[s]->dump_stiffness();
+    solvers[s]->dump_greens_function();
+    char prefix[] = "dump";
+    solvers[s]->post_force(u, f[s], prefix);
+    solvers[s]->prec_gradient(cavg.data(), u, gP[s]);
+    if (chdir(cwd)) return 5;
+  }
+
+  double gmax = 0, gd = 0, fmax = 0, fd = 0;
+  for (int i = 0; i < ndof * nx * ny; i++) {
+    gmax = std::fmax(gmax, std::fabs(gP[0][0][i]));
+    gd = std::fmax(gd, std::fabs(gP[0][0][i] - gP[1][0][i]));
+    fmax = std::fmax(fmax, std::fabs(f[0][0][i]));
+    fd = std::fmax(fd, std::fabs(f[0][0][i] - f[1][0][i]));
+  }
+  out[0] = gd / gmax;
+  out[1] = fd / fmax;
+
+  delete solvers[0];
+  delete solvers[1];
+  lmp->memory->destroy(u);
+  for (int s = 0; s < 2; s++) {
+    lmp->memory->destroy(f[s]);
+    lmp->memory->destroy(gP[s]);
+  }
+  delete kernel;
+  for (char *a : argv) free(a);
+  delete lmp;
+  return 0;
+}

@@ -209,6 +209,40 @@ double ref_solver_post_force(void *hs, const double *u, double *f, double *u0)
   return epot;
 }
 
+/* GFMDSolverStatic::prec_gradient (src/solvers/gfmd_solver_static.cpp:253-271).
+ * cavg: [ndof*ndof]; g, gP: [ndof][nx*ny] contiguous. */
+void ref_solver_prec_gradient(void *hs, const double *cavg, const double *g, double *gP)
+{
+  RefSolver *s = (RefSolver *) hs;
+  size_t n = (size_t) s->ndof * s->nx * s->ny;
+  std::vector<double> c(cavg, cavg + (size_t) s->ndof * s->ndof);
+  memcpy(s->u[0], g, n * sizeof(double));
+  s->solver->prec_gradient(c.data(), s->u, s->f);
+  memcpy(gP, s->f[0], n * sizeof(double));
+}
+
+/* post_force with a dump prefix: GFMDSolverFFT::dump writes <prefix>.q.*.out
+ * (src/solvers/gfmd_solver_fft.cpp:209-287). */
+double ref_solver_post_force_dump(void *hs, const double *u, double *f, const char *prefix)
+{
+  RefSolver *s = (RefSolver *) hs;
+  size_t n = (size_t) s->ndof * s->nx * s->ny;
+  memcpy(s->u[0], u, n * sizeof(double));
+  std::string p(prefix);
+  double epot = s->solver->post_force(s->u, s->f, &p[0]);
+  memcpy(f, s->f[0], n * sizeof(double));
+  return epot;
+}
+
+/* dump_stiffness / dump_greens_function write phi??.*.out / g??.*.out into the
+ * current directory (src/solvers/gfmd_solver_fft.cpp:294-355, :362-430). */
+void ref_solver_dump_tables(void *hs)
+{
+  RefSolver *s = (RefSolver *) hs;
+  s->solver->dump_stiffness();
+  s->solver->dump_greens_function();
+}
+
 void ref_solver_destroy(void *hs)
 {
   RefSolver *s = (RefSolver *) hs;

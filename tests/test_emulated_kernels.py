@@ -1,0 +1,262 @@
+"""Kernel LOGIC on machines without a GPU: the unchanged sources of user-gfmd_b200/csrc compiled
+for the CPU against the CUDA emulation shim in tests/emu (threads of a block as cooperative
+fibers) and driven through the same C ABI and Python binding as on the B200.  This is test
+infrastructure -- it says nothing about performance or real data races, the product never loads
+it, and the parity claims rest on the `-m gpu` tests; what it buys is that indexing, barriers,
+table layouts and host orchestration of every kernel (generic, Bluestein, the specialised
+power-of-two kernels, long columns, device table builder, gather/scatter, the off-path services)
+are exercised by `pytest -m "not gpu"`."""
+import shutil
+
+import numpy as np
+import pytest
+
+import aux_checks
+from conftest import golden_cases, golden_names, load_golden, rel_err
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def B():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import build as emu_build
+    import gfmd_b200
+    lib = gfmd_b200.load_library(emu_build.build())
+    saved = gfmd_b200._lib
+    gfmd_b200._lib = lib
+    yield gfmd_b200
+    gfmd_b200._lib = saved
+
+
+def random_case(nx, ny, d):
+    """Same synthetic Hermitian, conj-symmetric table as tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(1000 * nx + ny + d)
+    Dr = rng.standard_normal((nx, ny, d, d)) * np.exp(-0.3 * rng.random((nx, ny, 1, 1)) * 10)
+    Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+    Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+    phi = np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+    return phi, rng.standard_normal(d // 3), rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "C1_sc100_128x128"])
+def test_golden_vectors(B, name):
+    g = load_golden(name)
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    for c in golden_cases(g):
+        u = np.ascontiguousarray(g["u_" + c].reshape(d, nx * ny))
+        f = np.full_like(u, np.nan)
+        e = s.post_force(u, f)
+        assert rel_err(f.reshape(d, nx, ny), g["f_" + c]) < TOL, (name, c)
+        assert abs(e - float(g["epot_" + c])) <= TOL * max(abs(float(g["epot_" + c])), 1e-300)
+        assert np.abs(s.get_u0() - g["u0_" + c]).max() <= TOL * max(1.0, np.abs(g["u0_" + c]).max())
+    s.close()
+
+
+SIZES = [
+    # generic kernels: every radix, odd/even/prime, Bluestein rows and columns, run-time ndof
+    (1, 1, 3), (2, 1, 3), (3, 5, 3), (7, 9, 6), (37, 64, 3), (64, 37, 6), (30, 42, 9), (35, 25, 12),
+    (11, 13, 15),
+    # specialised power-of-two kernels (the grids are thin in the other direction to stay cheap)
+    (2048, 4, 3), (4096, 2, 3), (4, 2048, 3), (2, 4096, 3), (2, 8192, 3), (1, 16384, 3),
+    # long columns: top-digit pass + 4096-point sub-columns
+    (8192, 2, 3), (16384, 1, 3),
+]
+
+
+@pytest.mark.parametrize("nx,ny,d", SIZES)
+def test_random_tables_against_oracle(B, nx, ny, d, oracle_libs):
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    if max(nx, ny) >= 2048:
+        assert "[fast]" in s.describe()
+    s.set_kernel(phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(s.get_u0() - u0_ref).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+    s.close()
+
+
+def test_device_table_builder(B):
+    """k_build_phi (transfer-matrix recursion) in small column chunks, against the golden
+    forces of the plugin's own table -- the chunked call pattern of bench.py."""
+    from gfmd_b200 import synthetic
+    g = load_golden("small_sc100_16x12")       # kernel: ft sc100 ... height 128 == sc100 height 128
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    for k0 in range(0, s.nky, 3):
+        nk = min(3, s.nky - k0)
+        s.build_kernel_columns(synthetic.sc100_dynamical_matrices(nx, ny, k0, nk), k0, height=128)
+    s.set_linf(g["linf"])
+    u = np.ascontiguousarray(g["u_uniform"].reshape(d, nx * ny))
+    f = np.full_like(u, np.nan)
+    e = s.post_force(u, f)
+    assert rel_err(f.reshape(d, nx, ny), g["f_uniform"]) < TOL
+    assert abs(e - float(g["epot_uniform"])) <= TOL * abs(float(g["epot_uniform"]))
+    s.close()
+
+
+@pytest.mark.parametrize("kernel,nx,ny", [
+    ("ft fcc111 1 1.0 pair-potential 1 1.0 height 16", 8, 7),
+    ("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height 7", 2048, 2),     # specialised table layout
+])
+def test_device_built_table_equals_plugin_table(B, kernel, nx, ny, oracle_libs):
+    O = oracle_libs
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    k = O.RefKernel(kernel)
+    d = k.ndof
+    u = np.random.default_rng(9).uniform(-0.1, 0.1, size=(d, nx * ny))
+    out = []
+    for mode in ("plugin", "device"):
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        if mode == "plugin":
+            s.set_kernel(k.phi(nx, ny), k.linf())
+        else:
+            s.build_kernel_columns(k.dynamical_matrices(nx, ny, 0, s.nky), 0, height=k.height())
+            s.set_linf(k.linf())
+        f = np.full_like(u, np.nan)
+        out.append((f, s.post_force(u, f)))
+        s.close()
+    assert rel_err(out[1][0], out[0][0]) < TOL
+    assert abs(out[1][1] - out[0][1]) <= TOL * abs(out[0][1])
+    k.close()
+
+
+def make_atoms(nx, ny, nu, rng):
+    n = nx * ny * nu
+    gid = np.array([(ix, iy, iu) for ix in range(nx) for iy in range(ny) for iu in range(nu)], dtype=np.int32)
+    gid = gid[rng.permutation(n)]
+    xeq = np.stack([gid[:, 0] + 0.5, gid[:, 1] + 0.5, -gid[:, 2].astype(float)], axis=1)
+    x = xeq + rng.uniform(-0.3, 0.3, size=(n, 3))
+    x[:, 0] = np.mod(x[:, 0], nx)
+    x[:, 1] = np.mod(x[:, 1], ny)
+    mask = np.where(rng.random(n) < 0.95, 3, 1).astype(np.int32)
+    return x, xeq, gid, mask
+
+
+@pytest.mark.parametrize("nx,ny,nu,shift", [(6, 5, 2, (0, 0)), (37, 16, 1, (3, -2))])
+def test_gather_scatter_against_oracle(B, nx, ny, nu, shift, oracle_libs):
+    """Under emulation "device" pointers are host pointers: numpy arrays stand in for them."""
+    O = oracle_libs
+    rng = np.random.default_rng(11)
+    d = 3 * nu
+    x, xeq, gid, mask = make_atoms(nx, ny, nu, rng)
+    n = x.shape[0]
+    g_ref = gid.copy()
+    u_ref, n_ref = O.gather(x, xeq, g_ref, mask, 2, nx, ny, d, float(nx), float(ny), *shift)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    dgid = gid.copy()
+    du = np.zeros((d, nx * ny))
+    s.gather(x, xeq, dgid, mask, 2, n, float(nx), float(ny), shift[0], shift[1], du)
+    r = s.results()
+    assert r["natoms_gathered"] == n_ref and r["n_out_of_range"] == 0
+    assert np.array_equal(du, u_ref)
+    assert np.array_equal(dgid, g_ref)
+    fxy = rng.standard_normal((d, nx * ny))
+    f0 = rng.standard_normal((n, 3))
+    nlocal = n - n // 7
+    f_ref, fsum_ref, k_ref = O.scatter(fxy, g_ref, mask, 2, f0.copy(), nlocal=nlocal, nx=nx, ny=ny)
+    df = f0.copy()
+    s.scatter(dgid, mask, 2, n, nlocal, df, fxy)
+    r = s.results()
+    assert r["natoms_scattered"] == k_ref
+    assert np.array_equal(df, f_ref)
+    assert np.abs(r["fsum"] - fsum_ref).max() <= 1e-12 * max(1.0, np.abs(fsum_ref).max())
+    s.close()
+
+
+def test_full_step(B, oracle_libs):
+    O = oracle_libs
+    g = load_golden("small_sc100_16x12")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    x, xeq, gid, mask = make_atoms(nx, ny, 1, np.random.default_rng(5))
+    mask[:] = 3
+    n = x.shape[0]
+    u_ref, _ = O.gather(x, xeq, gid.copy(), mask, 2, nx, ny, d, float(nx), float(ny))
+    f_ref, e_ref, _ = O.post_force(u_ref.reshape(d, nx, ny), g["phi"], g["linf"])
+    fa_ref, fsum_ref, _ = O.scatter(f_ref.reshape(d, nx * ny), gid, mask, 2, np.zeros((n, 3)), nx=nx, ny=ny)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(g["phi"], g["linf"])
+    df = np.zeros((n, 3))
+    s.full_step(x, xeq, gid.copy(), mask, 2, n, n, float(nx), float(ny), df)
+    r = s.results()
+    assert rel_err(df, fa_ref) < TOL
+    assert abs(r["epot"] - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(r["fsum"] - fsum_ref).max() <= 1e-9
+    s.close()
+
+
+def test_async_pre_force_and_errors(B):
+    g = load_golden("small_sc100_16x12")
+    nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    u = np.ascontiguousarray(g["u_uniform"].reshape(d, nx * ny))
+    f = np.zeros_like(u)
+    with pytest.raises(B.GFMDError) as ei:          # post_force before set_kernel
+        s.post_force(u, f)
+    assert ei.value.code == 6
+    with pytest.raises(B.GFMDError) as ei:          # so is the preconditioner
+        s.prec_gradient(np.eye(d), u, f)
+    assert ei.value.code == 6
+    bad = g["phi"].copy()
+    bad[5, 0, 1] += 0.1                              # break Hermiticity
+    with pytest.raises(B.GFMDError) as ei:
+        s.set_kernel(bad, g["linf"])
+    assert ei.value.code == 7
+    s.set_kernel(g["phi"], g["linf"])
+    s.pre_force(u, f)
+    with pytest.raises(B.GFMDError) as ei:          # off-path services may not cut into a pending step
+        s.spectrum(u)
+    assert ei.value.code == 6
+    e = s.post_force(u, f)
+    assert rel_err(f.reshape(d, nx, ny), g["f_uniform"]) < TOL
+    assert abs(e - float(g["epot_uniform"])) <= TOL * abs(e)
+    s.close()
+
+
+@pytest.mark.parametrize("name", [n for n in aux_checks.aux_names() if n != "C1_sc100_128x128"])
+def test_spectrum_and_dump_fields(B, name, oracle_libs):
+    aux_checks.check_spectrum(B, oracle_libs, name)
+
+
+@pytest.mark.parametrize("name", [n for n in aux_checks.aux_names() if n != "C1_sc100_128x128"])
+def test_prec_gradient(B, name, oracle_libs):
+    aux_checks.check_prec_gradient(B, oracle_libs, name)
+
+
+@pytest.mark.parametrize("nx,ny,d", [(2048, 2, 3), (4096, 2, 3), (11, 13, 15)])
+def test_aux_services_read_the_specialised_table_layout(B, nx, ny, d, oracle_libs):
+    """The off-path column kernel reads Phi in the digit-reversed, interleaved layout of the
+    specialised per-step kernels (phi_slot); run-time ndof (15) covers its generic branch."""
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(phi, linf)
+    uq, fq = s.spectrum(np.ascontiguousarray(u.reshape(d, nx * ny)))
+    uq_ref, fq_ref = O.spectrum(u, phi)
+    assert rel_err(uq, uq_ref) < TOL and rel_err(fq, fq_ref) < TOL
+    if d == 15:
+        with pytest.raises(B.GFMDError) as ei:
+            s.prec_gradient(np.eye(d), np.zeros((d, nx * ny)), np.zeros((d, nx * ny)))
+        assert ei.value.code == 4
+    s.close()

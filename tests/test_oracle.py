@@ -141,3 +141,47 @@ def test_synthetic_sc100_matrices_equal_the_plugin(oracle_libs):
     mine = synthetic.sc100_dynamical_matrices(12, 10, 0, 6)
     assert np.abs(ref - mine).max() < 1e-15
     k.close()
+
+
+# ---- off-path services: q-space dump fields and prec_gradient -------
+
+def _aux_names():
+    import aux_checks
+    return aux_checks.aux_names()
+
+
+@pytest.mark.parametrize("name", _aux_names())
+def test_numpy_oracle_matches_recorded_prec_gradient_and_dumps(name, oracle_libs):
+    """oracle.prec_gradient / oracle.spectrum against what the reference's own
+    GFMDSolverStatic::prec_gradient and GFMDSolverFFT::dump produced (tests/golden/aux)."""
+    import aux_checks
+    O = oracle_libs
+    g, a = load_golden(name), aux_checks.load_aux(name)
+    nx, ny = int(g["nx"]), int(g["ny"])
+    gP = O.prec_gradient(g["u_uniform"], g["phi"], a["cavg"], reference_quirk=True)
+    assert rel_err(gP, a["gP"]) < 1e-12
+    uq, fq = O.spectrum(g["u_uniform"], g["phi"])
+    fields = O.dump_fields(uq, fq, nx, ny)
+    for k in (k for k in a if k.startswith("dump_")):
+        assert rel_err(fields[k[5:]], a[k]) < aux_checks.TOL_TEXT, k
+
+
+def test_reference_sources_reproduce_recorded_prec_gradient(oracle_libs):
+    """The reference's solver sources, when built here, against the recorded fixture and
+    against the oracle's statement of the ndof > 3 behaviour (gfmd_misc.h:113-115)."""
+    import aux_checks
+    O = oracle_libs
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    for name in ("small_sc100_16x12", "small_fcc111_8x7"):
+        g, a = load_golden(name), aux_checks.load_aux(name)
+        s = O.RefSolver(int(g["nx"]), int(g["ny"]), int(g["ndof"]), fft_backend=0)
+        s.set_phi(g["phi"], g["linf"])
+        gP = s.prec_gradient(a["cavg"], g["u_uniform"])
+        assert np.array_equal(gP, a["gP"])
+        full = O.prec_gradient(g["u_uniform"], g["phi"], a["cavg"])
+        if int(g["ndof"]) == 3:
+            assert rel_err(full, gP) < 1e-12
+        else:
+            assert rel_err(full, gP) > 1e-3
+        s.close()

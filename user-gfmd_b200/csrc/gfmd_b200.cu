@@ -19,6 +19,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_fast.cuh"
 #include "kernel_phi_build.cuh"
+#include "kernel_cols_aux.cuh"
 
 using namespace gfmd;
 
@@ -261,6 +262,11 @@ struct gfmd_b200 {
   int cols_top = 0;                   // log2(nx / 4096): top-digit pass of long columns
   DevFft fft_sub;                     // twiddles of the 4096 sub-columns (long columns only)
   int num_sms = 148;
+  // auxiliary (off-path) column kernel: q-space dumps and the preconditioner
+  size_t aux_cols_smem = 0;           // 0: a column set does not fit one CTA
+  bool aux_attr_set = false;
+  double2 *d_spec = nullptr;          // Phi.u~ of the last spectrum request
+  double *d_cavg = nullptr;
 
   bool phi_set = false;
   std::vector<char> phi_cols_set;
@@ -393,6 +399,7 @@ int plan(gfmd_b200 *h)
                 "CTA (long columns are supported for ndof 3 and nx = 8192 or 16384 only)",
                 g.nx, g.d, h->cols_smem, kMaxSmem);
   tmin = min_threads_for(h->fft_cols.desc.core);
+  h->aux_cols_smem = (h->cols_smem <= kMaxSmem && tmin <= 512 && g.P == 1) ? h->cols_smem : 0;
   if (tmin > 512 && !h->fast_cols)
     return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d: column transform too long for one CTA", g.nx);
   if (h->fast_cols) h->cols_smem = fast_cols_smem(3, h->fast_cols);
@@ -402,7 +409,9 @@ int plan(gfmd_b200 *h)
   if (t > 512) t = 512;
   h->cols_T = t;
 
-#define SET_SMEM(k, bytes) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)))
+  // The attribute belongs to the kernel, not to this handle: always grant the full opt-in
+  // amount, or a second handle with a smaller grid would lower the limit under the first.
+#define SET_SMEM(k, bytes) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxSmem))
   if (h->even) {
     SET_SMEM(k_rows_fwd<true>, h->rows_smem);
     SET_SMEM(k_rows_inv<true>, h->rows_smem);
@@ -745,6 +754,80 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   return 0;
 }
 
+// Off-path transforms on the generic kernels (single rank): rows forward, the auxiliary column
+// kernel in `mode`, and for AUX_PREC rows backward.  d_in -> (stage, d_spec) or d_out.
+int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool want_f, int ncopy)
+{
+  const GridDesc &g = h->g;
+  if (g.P != 1)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "q-space dumps and prec_gradient run on a single rank only (the "
+                "reference's dumps do too, gfmd_solver_fft.cpp:211-212)");
+  if (!h->aux_cols_smem)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d with ndof = %d: a column set does not fit one CTA; q-space "
+                "dumps and prec_gradient are limited to nx * ndof * 16 B <= %zu B", g.nx, g.d, kMaxSmem);
+  if (mode == AUX_PREC && !(g.d == 3 || g.d == 6 || g.d == 9 || g.d == 12))
+    return fail(h, GFMD_B200_EUNSUPPORTED, "prec_gradient: ndof %d (3, 6, 9, 12 supported)", g.d);
+  if (!h->aux_attr_set) {
+#define SET_AUX(DT, MODE)                                                                        \
+  CU(h, cudaFuncSetAttribute(k_cols_aux<DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int) kMaxSmem))
+    switch (g.d) {
+      case 3: SET_AUX(3, AUX_SPECTRUM); SET_AUX(3, AUX_PREC); break;
+      case 6: SET_AUX(6, AUX_SPECTRUM); SET_AUX(6, AUX_PREC); break;
+      case 9: SET_AUX(9, AUX_SPECTRUM); SET_AUX(9, AUX_PREC); break;
+      case 12: SET_AUX(12, AUX_SPECTRUM); SET_AUX(12, AUX_PREC); break;
+      default: SET_AUX(0, AUX_SPECTRUM); break;
+    }
+#undef SET_AUX
+    h->aux_attr_set = true;
+  }
+  if (mode == AUX_SPECTRUM && want_f && !h->d_spec)
+    CU(h, dmalloc(h, &h->d_spec, (size_t) g.d * g.kyb * g.nx));
+  const int nrow_blocks = g.d * ((g.nx_loc + h->rows_RB - 1) / h->rows_RB);
+  double2 *A = h->d_stage;
+  if (h->even)
+    k_rows_fwd<true><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(d_in, A, g, h->fft_rows.desc, h->d_tw_ny,
+                                                                          h->rows_RB, h->rows_ld);
+  else
+    k_rows_fwd<false><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(d_in, A, g, h->fft_rows.desc, h->d_tw_ny,
+                                                                           h->rows_RB, h->rows_ld);
+  h->launches++;
+  const int lognx = ilog2_rt(g.nx);
+#define LAUNCH_AUX(DT, MODE)                                                                      \
+  k_cols_aux<DT, MODE><<<g.nky_loc, h->cols_T, h->aux_cols_smem, h->stream>>>(                     \
+      A, want_f ? h->d_spec : nullptr, g, h->fft_cols.desc, h->d_phi, h->d_cavg, h->fast_cols != 0, lognx, h->cols_ld, \
+      ncopy)
+  if (mode == AUX_SPECTRUM) {
+    switch (g.d) {
+      case 3: LAUNCH_AUX(3, AUX_SPECTRUM); break;
+      case 6: LAUNCH_AUX(6, AUX_SPECTRUM); break;
+      case 9: LAUNCH_AUX(9, AUX_SPECTRUM); break;
+      case 12: LAUNCH_AUX(12, AUX_SPECTRUM); break;
+      default: LAUNCH_AUX(0, AUX_SPECTRUM); break;
+    }
+  } else {
+    switch (g.d) {
+      case 3: LAUNCH_AUX(3, AUX_PREC); break;
+      case 6: LAUNCH_AUX(6, AUX_PREC); break;
+      case 9: LAUNCH_AUX(9, AUX_PREC); break;
+      default: LAUNCH_AUX(12, AUX_PREC); break;
+    }
+  }
+#undef LAUNCH_AUX
+  h->launches++;
+  if (mode == AUX_PREC) {
+    if (h->even)
+      k_rows_inv<true><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(A, d_out, g, h->fft_rows.desc,
+                                                                            h->d_tw_ny, h->rows_RB, h->rows_ld);
+    else
+      k_rows_inv<false><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(A, d_out, g, h->fft_rows.desc,
+                                                                             h->d_tw_ny, h->rows_RB, h->rows_ld);
+    h->launches++;
+  }
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
 void accumulate_stage_times(gfmd_b200 *h, int first, int last)
 {
   // events first..last+1 were recorded; requires a stream sync by the caller
@@ -1023,6 +1106,7 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   cudaFree(h->d_u); cudaFree(h->d_f); cudaFree(h->d_stage); cudaFree(h->d_stage2);
   cudaFree(h->d_phi); cudaFree(h->d_linf); cudaFree(h->d_epart); cudaFree(h->d_fsum_part);
   cudaFree(h->d_res); cudaFree(h->d_tw_ny);
+  cudaFree(h->d_spec); cudaFree(h->d_cavg);
   if (h->h_res) cudaFreeHost(h->h_res);
   free_fft(h->fft_rows);
   free_fft(h->fft_cols);
@@ -1249,6 +1333,64 @@ int gfmd_b200_post_force_host(gfmd_b200_t *h, const double *u, double *f, double
   if (epot) *epot = h->h_res->epot;
   if (u0)
     for (int i = 0; i < h->g.d; ++i) u0[i] = h->h_res->u0[i];
+  return 0;
+}
+
+int gfmd_b200_spectrum_host(gfmd_b200_t *h, const double *u, double *uq, double *fq)
+{
+  if (!h || !u || !uq) return fail(h, GFMD_B200_EINVAL, "spectrum_host: null argument");
+  if (!h->phi_set && fq) return fail(h, GFMD_B200_ESTATE, "spectrum_host before set_phi (set_kernel)");
+  if (h->pending_u) return fail(h, GFMD_B200_ESTATE, "spectrum_host between pre_force and post_force");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const GridDesc &g = h->g;
+  const int d = g.d, nx = g.nx, ny = g.ny, nyh = g.nyh;
+  const size_t bytes = sizeof(double) * (size_t) d * nx * ny;
+  CU(h, cudaMemcpyAsync(h->d_u, u, bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = enqueue_aux(h, AUX_SPECTRUM, h->d_u, nullptr, fq != nullptr, 0);
+  if (rc) return rc;
+  const size_t nhalf = (size_t) d * nyh * nx;
+  std::vector<double2> half(nhalf);
+  for (int which = 0; which < (fq ? 2 : 1); ++which) {
+    CU(h, cudaMemcpyAsync(half.data(), which ? h->d_spec : h->d_stage, nhalf * sizeof(double2),
+                          cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // half spectrum [dof][ky][kx] -> the reference's q_buffer [ix*ny + iy][dof]; the other half
+    // by X(-q) = conj X(q) (real field; Phi(-q) = conj Phi(q))
+    double2 *out = reinterpret_cast<double2 *>(which ? fq : uq);
+    for (int ix = 0; ix < nx; ++ix)
+      for (int iy = 0; iy < ny; ++iy) {
+        const bool lower = iy < nyh;
+        const int ky = lower ? iy : ny - iy, kx = lower ? ix : (nx - ix) % nx;
+        for (int dof = 0; dof < d; ++dof) {
+          double2 v = half[((size_t) dof * nyh + ky) * nx + kx];
+          if (!lower) v.y = -v.y;
+          out[((size_t) ix * ny + iy) * d + dof] = v;
+        }
+      }
+  }
+  return 0;
+}
+
+int gfmd_b200_prec_gradient_host(gfmd_b200_t *h, const double *cavg, const double *grad, double *gP,
+                                 int first3_only)
+{
+  if (!h || !cavg || !grad || !gP) return fail(h, GFMD_B200_EINVAL, "prec_gradient_host: null argument");
+  if (!h->phi_set) return fail(h, GFMD_B200_ESTATE, "prec_gradient before set_phi (set_kernel)");
+  if (h->pending_u) return fail(h, GFMD_B200_ESTATE, "prec_gradient between pre_force and post_force");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const GridDesc &g = h->g;
+  const size_t bytes = sizeof(double) * (size_t) g.d * g.nx_loc * g.ny;
+  if (!h->d_cavg) CU(h, dmalloc(h, &h->d_cavg, (size_t) GFMD_B200_MAX_NDOF * GFMD_B200_MAX_NDOF));
+  CU(h, cudaMemcpyAsync(h->d_cavg, cavg, sizeof(double) * g.d * g.d, cudaMemcpyHostToDevice, h->stream));
+  try_pin(h, grad, bytes);
+  try_pin(h, gP, bytes);
+  CU(h, cudaMemcpyAsync(h->d_u, grad, bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = enqueue_aux(h, AUX_PREC, h->d_u, h->d_f, false, first3_only ? 3 : g.d);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(gP, h->d_f, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
 

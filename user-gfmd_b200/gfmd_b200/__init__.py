@@ -50,6 +50,8 @@ ABI = {
     "gfmd_b200_post_force_host": (_i, [_vp, _vp, _vp, c_double_p, _vp]),
     "gfmd_b200_pre_force_async_host": (_i, [_vp, _vp]),
     "gfmd_b200_post_force_device": (_i, [_vp, _vp, _vp]),
+    "gfmd_b200_spectrum_host": (_i, [_vp, _vp, _vp, _vp]),
+    "gfmd_b200_prec_gradient_host": (_i, [_vp, _vp, _vp, _vp, _i]),
     "gfmd_b200_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i, _vp]),
     "gfmd_b200_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "gfmd_b200_full_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
@@ -242,6 +244,31 @@ class GFMDSolverB200:
         self._check(self.lib.gfmd_b200_post_force_host(self.h, _ptr(u), _ptr(f), ctypes.byref(e),
                                                        self.u0.ctypes.data))
         return e.value
+
+    def prec_gradient(self, cavg, g, gP, reference_quirk=True):
+        """GFMDSolverStatic::prec_gradient (gfmd_solver_static.cpp:253-271):
+        gP = IDFT[(Phi(q) + cavg)^-1 DFT[g]].  cavg: [ndof, ndof] real; g, gP: HOST [ndof, nxy_loc].
+        reference_quirk: for ndof > 3 only components 0..2 of gP(q) are replaced, like the
+        reference's general branch (gfmd_misc.h:113-115); False replaces all."""
+        cavg = np.ascontiguousarray(cavg, dtype=np.float64)
+        if cavg.size != self.ndof * self.ndof:
+            raise GFMDError(1, "cavg must hold ndof*ndof entries")
+        for a in (g, gP):
+            if isinstance(a, np.ndarray) and (a.dtype != np.float64 or not a.flags.c_contiguous):
+                raise GFMDError(1, "g and gP must be C-contiguous float64")
+        self._check(self.lib.gfmd_b200_prec_gradient_host(self.h, cavg.ctypes.data, _ptr(g), _ptr(gP),
+                                                          int(reference_quirk)))
+
+    def spectrum(self, u, with_force=True):
+        """The two q-space fields GFMDSolverFFT::dump writes (gfmd_solver_fft.cpp:209-287):
+        u~(q) and Phi(q).u~(q), each [nx*ny, ndof] complex128 (idq = ix*ny + iy)."""
+        if isinstance(u, np.ndarray) and (u.dtype != np.float64 or not u.flags.c_contiguous):
+            raise GFMDError(1, "u must be C-contiguous float64")
+        uq = np.empty((self.nx * self.ny, self.ndof), dtype=np.complex128)
+        fq = np.empty_like(uq) if with_force else None
+        self._check(self.lib.gfmd_b200_spectrum_host(self.h, _ptr(u), uq.ctypes.data,
+                                                     fq.ctypes.data if with_force else None))
+        return uq, fq
 
     def get_u0(self):
         return self.u0

@@ -5,7 +5,13 @@
  *   set_grid_size   :79-87    -> gfmd_b200_create[_slab]; the brick comes from the library
  *   set_kernel      :90-136   fill_phi_buffer for this rank's q columns -> gfmd_b200_set_phi_columns,
  *                             kernel->get_force_at_gamma_point -> gfmd_b200_set_linf, same warning
- *   post_force      :145-249  -> gfmd_b200_post_force_host (u_xy/f_xy are the fix's host arrays)
+ *   post_force      :145-249  -> gfmd_b200_post_force_host (u_xy/f_xy are the fix's host arrays);
+ *                             on `dumpq_every` steps the q-space fields come from
+ *                             gfmd_b200_spectrum_host and are written in the format of
+ *                             GFMDSolverFFT::dump (src/solvers/gfmd_solver_fft.cpp:209-287)
+ *   prec_gradient   :253-271  -> gfmd_b200_prec_gradient_host
+ *   dump_stiffness / dump_greens_function (gfmd_solver_fft.cpp:294-355, :362-430): init-time,
+ *                             host only, from the stiffness kernel of the last set_kernel
  */
 #include <numeric>
 #include <string.h>
@@ -20,12 +26,13 @@
 #include "mpi.h"
 
 #include "gfmd_misc.h"
+#include "linearalgebra.h"
 #include "gfmd_b200.h"
 
 using namespace LAMMPS_NS;
 
 GFMDSolverB200::GFMDSolverB200(LAMMPS *lmp, int narg, int *iarg, char **arg)
-  : GFMDSolver(lmp), handle_(NULL), device_(-1), async_(true)
+  : GFMDSolver(lmp), handle_(NULL), device_(-1), async_(true), kernel_(NULL), normalize_(true)
 {
   strcpy(name, "static/b200");
 
@@ -127,6 +134,9 @@ void GFMDSolverB200::init()
 
 void GFMDSolverB200::set_kernel(StiffnessKernel *kernel, bool normalize)
 {
+  kernel_ = kernel;
+  normalize_ = normalize;
+
   if (screen && comm->me == 0)
     fprintf(screen, "USER-GFMD: Computing stiffness matrices...\n");
 
@@ -178,14 +188,194 @@ double GFMDSolverB200::post_force(void *input_buffer_ptr, void *output_buffer_pt
   double **input_buffer = static_cast<double**>(input_buffer_ptr);
   double **output_buffer = static_cast<double**>(output_buffer_ptr);
 
-  if (dump_prefix)
-    error->all(FLERR,"fix gfmd solver static/b200: q-space dumps (dumpq_every) are not "
-               "available; use 'solver static' on dump steps.");
-
   double epot;
   check(gfmd_b200_post_force_host(handle_, input_buffer[0], output_buffer[0], &epot, u0),
         "gfmd_b200_post_force_host");
+
+  /* the reference dumps between the forward transform and the contraction
+     (src/solvers/gfmd_solver_static.cpp:181-182); the fields are the same afterwards */
+  if (dump_prefix)
+    dump(dump_prefix, input_buffer[0]);
+
   return epot;
+}
+
+
+/* ----------------------------------------------------------------------
+ * q-space dump of a `dumpq_every` step: same files, same layout (rows = iy,
+ * columns = ix) and same number format as GFMDSolverFFT::dump
+ * (src/solvers/gfmd_solver_fft.cpp:209-287)
+ * --------------------------------------------------------------------*/
+
+void GFMDSolverB200::dump(char *dump_prefix, double *u)
+{
+  if (nprocs > 1)
+    error->all(FLERR,"Can only dump from single processor run.");
+
+  size_t nq = (size_t) nx*ny;
+  double_complex *uq = new double_complex[nq*ndof];
+  double_complex *fq = new double_complex[nq*ndof];
+  check(gfmd_b200_spectrum_host(handle_, u, reinterpret_cast<double*>(uq), reinterpret_cast<double*>(fq)),
+        "gfmd_b200_spectrum_host");
+
+  char fn[1024];
+  FILE *fur[MAX_NDOF], *ffr[MAX_NDOF], *fui[MAX_NDOF], *ffi[MAX_NDOF];
+  for (int idof = 0; idof < ndof; idof++) {
+    sprintf(fn, "%s.q.u%i.real.out", dump_prefix, idof);
+    fur[idof] = fopen(fn, "w");
+    sprintf(fn, "%s.q.u%i.imag.out", dump_prefix, idof);
+    fui[idof] = fopen(fn, "w");
+    sprintf(fn, "%s.q.f%i.real.out", dump_prefix, idof);
+    ffr[idof] = fopen(fn, "w");
+    sprintf(fn, "%s.q.f%i.imag.out", dump_prefix, idof);
+    ffi[idof] = fopen(fn, "w");
+  }
+  sprintf(fn, "%s.q.uP.out", dump_prefix);
+  FILE *fuP = fopen(fn, "w");
+  sprintf(fn, "%s.q.fP.out", dump_prefix);
+  FILE *ffP = fopen(fn, "w");
+  sprintf(fn, "%s.q.e.out", dump_prefix);
+  FILE *fe = fopen(fn, "w");
+
+  for (int iy = 0; iy < ny; iy++) {
+    for (int ix = 0; ix < nx; ix++) {
+      const double_complex *uv = uq + ((size_t) ix*ny + iy)*ndof;
+      const double_complex *fv = fq + ((size_t) ix*ny + iy)*ndof;
+      double_complex uP = 0.0, fP = 0.0, e = 0.0;
+      for (int idof = 0; idof < ndof; idof++) {
+        fprintf(fur[idof], " %20.10e ", creal(uv[idof]));
+        fprintf(fui[idof], " %20.10e ", cimag(uv[idof]));
+        fprintf(ffr[idof], " %20.10e ", creal(fv[idof]));
+        fprintf(ffi[idof], " %20.10e ", cimag(fv[idof]));
+        uP += uv[idof]*conj(uv[idof]);
+        fP += fv[idof]*conj(fv[idof]);
+        e  += uv[idof]*conj(fv[idof]);
+      }
+      fprintf(fuP, " %20.10e ", creal(uP));
+      fprintf(ffP, " %20.10e ", creal(fP));
+      fprintf(fe, " %20.10e ", creal(e));
+    }
+    for (int idof = 0; idof < ndof; idof++) {
+      fputc('\n', fur[idof]);
+      fputc('\n', fui[idof]);
+      fputc('\n', ffr[idof]);
+      fputc('\n', ffi[idof]);
+    }
+    fputc('\n', fuP);
+    fputc('\n', ffP);
+    fputc('\n', fe);
+  }
+
+  for (int idof = 0; idof < ndof; idof++) {
+    fclose(fur[idof]);
+    fclose(fui[idof]);
+    fclose(ffr[idof]);
+    fclose(ffi[idof]);
+  }
+  fclose(fuP);
+  fclose(ffP);
+  fclose(fe);
+
+  delete [] uq;
+  delete [] fq;
+}
+
+
+void GFMDSolverB200::prec_gradient(double *cavg, double **g, double **gP)
+{
+  /* first3_only = 1: for ndof > 3 the reference replaces only the first three components
+     (src/main/gfmd_misc.h:113-115); a drop-in does the same */
+  check(gfmd_b200_prec_gradient_host(handle_, cavg, g[0], gP[0], 1), "gfmd_b200_prec_gradient_host");
+}
+
+
+/* ----------------------------------------------------------------------
+ * dump stiffness coefficients / Green's function for plotting in gnuplot.
+ * The reference prints its stored table entry by entry in storage order
+ * (n = ix*ny + iy) with a line break after every nx entries, and opens but
+ * never fills the two trace files (src/solvers/gfmd_solver_fft.cpp:294-355,
+ * :362-430); the table is recomputed here row block by row block because
+ * this solver keeps no host copy of it.
+ * --------------------------------------------------------------------*/
+
+void GFMDSolverB200::dump_table(const char *stem, bool invert)
+{
+  if (nprocs > 1) {
+    char errstr[256];
+    snprintf(errstr, sizeof(errstr), "fix gfmd/static: Dump %s only works from a single processor run.",
+             invert ? "Green's function" : "stiffness");
+    error->all(FLERR, errstr);
+  }
+  if (!kernel_)
+    error->all(FLERR,"fix gfmd solver static/b200: dump requested before set_kernel.");
+
+  if (me == 0) {
+    FILE *freal[MAX_NDOF][MAX_NDOF], *fimag[MAX_NDOF][MAX_NDOF];
+    for (int idim = 0; idim < ndof; idim++) {
+      for (int jdim = 0; jdim < ndof; jdim++) {
+        char fn[1024];
+        sprintf(fn, "%s%i%i.real.out", stem, idim, jdim);
+        freal[idim][jdim] = fopen(fn, "w");
+        sprintf(fn, "%s%i%i.imag.out", stem, idim, jdim);
+        fimag[idim][jdim] = fopen(fn, "w");
+      }
+    }
+    char fn[1024];
+    sprintf(fn, "%str.real.out", stem);
+    FILE *ftrreal = fopen(fn, "w");
+    sprintf(fn, "%str.imag.out", stem);
+    FILE *ftrimag = fopen(fn, "w");
+
+    double_complex **phi = NULL;
+    double_complex *G = new double_complex[ndof_sq];
+    size_t n = 0, nlines = 0;
+    for (int ix = 0; ix < nx; ix++) {
+      memory->create(phi, ny, ndof_sq, "GFMDSolverB200::phi");
+      fill_phi_buffer(ndof, nx, ix, ix, ny, 0, ny-1, kernel_, phi, normalize_, error);
+      for (int iy = 0; iy < ny; iy++) {
+        memcpy(G, phi[iy], ndof_sq*sizeof(double_complex));
+        if (invert) GaussJordan(ndof, G, error);
+        for (int k = 0; k < ndof_sq; k++) {
+          fprintf(freal[k/ndof][k%ndof], " %e ", creal(G[k]));
+          fprintf(fimag[k/ndof][k%ndof], " %e ", cimag(G[k]));
+        }
+        if (++n % nx == 0) {
+          for (int idim = 0; idim < ndof; idim++) {
+            for (int jdim = 0; jdim < ndof; jdim++) {
+              fputc('\n', freal[idim][jdim]);
+              fputc('\n', fimag[idim][jdim]);
+            }
+          }
+          fputc('\n', ftrreal);
+          fputc('\n', ftrimag);
+          nlines++;
+        }
+      }
+      memory->destroy(phi);
+    }
+    delete [] G;
+
+    for (int idim = 0; idim < ndof; idim++) {
+      for (int jdim = 0; jdim < ndof; jdim++) {
+        fclose(freal[idim][jdim]);
+        fclose(fimag[idim][jdim]);
+      }
+    }
+    fclose(ftrreal);
+    fclose(ftrimag);
+  }
+}
+
+
+void GFMDSolverB200::dump_stiffness()
+{
+  dump_table("phi", false);
+}
+
+
+void GFMDSolverB200::dump_greens_function()
+{
+  dump_table("g", true);
 }
 
 

@@ -32,13 +32,25 @@ class GFMDSolverB200 : public GFMDSolver {
   virtual void pre_force(void *, void *);
   virtual double post_force(void *, void *, char *);
 
+  /* gP = IDFT[(Phi(q) + Cavg)^-1 DFT[g]] (GFMDSolverStatic::prec_gradient) */
+  virtual void prec_gradient(double *, double **, double **);
+
   virtual double memory_usage();
+
+  /* init-time diagnostics of `fix gfmd ... dump_stiffness / dump_greens_function`
+     (GFMDSolverFFT::dump_stiffness, ::dump_greens_function) */
+  virtual void dump_stiffness();
+  virtual void dump_greens_function();
 
  protected:
   struct gfmd_b200 *handle_;
   int device_;
   bool async_;
+  StiffnessKernel *kernel_;     /* of the last set_kernel; owned by the fix */
+  bool normalize_;
   void check(int rc, const char *what);
+  void dump(char *dump_prefix, double *u);
+  void dump_table(const char *stem, bool invert);
 };
 
 }
