@@ -260,3 +260,25 @@ def test_aux_services_read_the_specialised_table_layout(B, nx, ny, d, oracle_lib
             s.prec_gradient(np.eye(d), np.zeros((d, nx * ny)), np.zeros((d, nx * ny)))
         assert ei.value.code == 4
     s.close()
+
+
+@pytest.mark.parametrize("nx,ny,variant", [(2, 4096, 4098), (2, 4096, 4099), (4, 4096, 4100), (2, 8192, 8195),
+                                            (4, 4096, 4097)])
+def test_row_kernel_variants(B, nx, ny, variant, oracle_libs, monkeypatch):
+    """Experimental row-kernel variants (GFMD_B200_ROWS_VARIANT, kernels_fast.cuh): 256-bit
+    transposed accesses with their own lane -> wavevector map, other CTA shapes."""
+    O = oracle_libs
+    d = 3
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, _ = O.post_force(u, phi, linf)
+    monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(variant))
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    assert "variant %d" % variant in s.describe(), s.describe()
+    s.set_kernel(phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    s.close()

@@ -294,3 +294,31 @@ def test_async_pre_force_and_errors(B):
     prof = s.stage_times()
     assert prof["cols_fused"][1] == 1 and prof["cols_fused"][0] > 0
     s.close()
+
+
+@pytest.mark.parametrize("nx,ny,variant", [(64, 4096, 4097), (64, 4096, 4098), (64, 4096, 4099),
+                                            (128, 4096, 4100), (32, 8192, 8195)])
+def test_row_kernel_variants_against_oracle(B, nx, ny, variant, oracle_libs, monkeypatch):
+    """Experimental row-kernel variants (GFMD_B200_ROWS_VARIANT, csrc/kernels_fast.cuh: 256-bit
+    transposed accesses, three CTAs per SM, four rows per CTA) keep the same parity bar."""
+    O = oracle_libs
+    d = 3
+    rng = np.random.default_rng(variant)
+    Dr = rng.standard_normal((nx, ny, d, d)) * np.exp(-3 * rng.random((nx, ny, 1, 1)))
+    Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+    Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+    phi = np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+    linf = rng.standard_normal(1)
+    u = rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(variant))
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    assert "variant %d" % variant in s.describe(), s.describe()
+    s.set_kernel(phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    s.close()
+    assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)

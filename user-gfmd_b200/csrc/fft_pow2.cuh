@@ -599,4 +599,27 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): two adjacent complex numbers, i.e. the
+// same wavevector of two neighbouring rows in the transposed staging layout.  p must be
+// 32-byte aligned.
+__device__ __forceinline__ void st_global_256(double2 *p, double2 a, double2 b)
+{
+#ifdef GFMD_CUDA_EMU
+  p[0] = a;
+  p[1] = b;
+#else
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void ld_global_256(const double2 *p, double2 &a, double2 &b)
+{
+#ifdef GFMD_CUDA_EMU
+  a = p[0];
+  b = p[1];
+#else
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#endif
+}
+
 }  // namespace gfmd

@@ -138,9 +138,21 @@ k_cols_fused_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, Gri
 
 // --------------------------------------------------------------------- rows ---
 
+// Lane -> wavevector map of the 256-bit transposed accesses: the eight lanes of a quarter
+// warp take eight values of the SECOND spectrum digit (the first one has only LR0 bits), so
+// that their shared-memory columns differ (swz_key) -- in global memory every lane touches
+// its own line anyway.  Bijection on [0, NR).
+template <int NR> __device__ __forceinline__ int rows256_ky(int i)
+{
+  constexpr int L0 = P2<NR>::LR0;
+  return (i & ~((8 << L0) - 1)) | ((i & 7) << L0) | ((i >> 3) & ((1 << L0) - 1));
+}
+
 // RB rows (same dof) of ny = 2 NR reals per CTA; array a = row a of the tile.
-template <int NR, int RB, int T>
-__global__ void __launch_bounds__(T)
+// MB = CTAs per SM the register allocation aims at; W256 = the transposed stores move the
+// two rows of a pair with one 256-bit instruction per wavevector (RB even).
+template <int NR, int RB, int T, int MB = 0, bool W256 = false>
+__global__ void __launch_bounds__(T, MB)
 k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
 {
@@ -178,6 +190,33 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
 
   // un-mix the packed transform and store transposed: X[ky] = A - i w B
   constexpr int h = NR;
+  if constexpr (W256) {
+    static_assert(RB % 2 == 0, "256-bit stores pair two rows");
+    constexpr int RP = RB / 2;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < RP * (h + 1); i += T) {
+      const int rp = i % RP, kk = i / RP;
+      const int ky = kk == h ? h : rows256_ky<NR>(kk);
+      const int ka = ky == h ? 0 : ky;
+      const int kb = ky == 0 ? 0 : h - ky;
+      const int pa = swz(p2_freq_to_pos(LOG, ka)), pb = swz(p2_freq_to_pos(LOG, kb));
+      const double2 w = __ldg(tw_ny + ky);
+      double2 X[2];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int r = 2 * rp + s2;
+        const int rx = (r * AX) & 7;
+        const double2 zk = sm[r * NR + (pa ^ rx)];
+        const double2 zc = cconj(sm[r * NR + (pb ^ rx)]);
+        const double2 A = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
+        const double2 B = make_double2(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
+        const double2 t = cmul(w, B);
+        X[s2] = make_double2(A.x + t.y, A.y - t.x);
+      }
+      st_global_256(stage + stage_index(g, ky, dof, ix0 + 2 * rp), X[0], X[1]);
+    }
+    return;
+  }
 #pragma unroll 4
   for (int i = threadIdx.x; i < RB * (h + 1); i += T) {
     const int r = i % RB, ky = i / RB;
@@ -193,8 +232,8 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   }
 }
 
-template <int NR, int RB, int T>
-__global__ void __launch_bounds__(T)
+template <int NR, int RB, int T, int MB = 0, bool W256 = false>
+__global__ void __launch_bounds__(T, MB)
 k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
 {
@@ -210,6 +249,39 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   constexpr int h = NR;
   p2_fill_tws<NR>(tws, tw);
 
+  if constexpr (W256) {
+    // transposed load, 4 independent 32-byte loads (both rows of a pair) in flight per thread
+    static_assert(RB % 2 == 0, "256-bit loads pair two rows");
+    constexpr int RP = RB / 2;
+    constexpr int UL2 = 4;
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < RP * (h + 1); i0 += T * UL2) {
+      double2 y[UL2][2];
+#pragma unroll
+      for (int j = 0; j < UL2; ++j) {
+        const int i = i0 + j * T;
+        if (i < RP * (h + 1)) {
+          const int kk = i / RP;
+          const int ky = kk == h ? h : rows256_ky<NR>(kk);
+          ld_global_256(stage + stage_index(g, ky, dof, ix0 + 2 * (i % RP)), y[j][0], y[j][1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UL2; ++j) {
+        const int i = i0 + j * T;
+        if (i < RP * (h + 1)) {
+          const int rp = i % RP, kk = i / RP;
+          const int ky = kk == h ? h : rows256_ky<NR>(kk);
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int r = 2 * rp + s2;
+            if (ky < h) sm[r * NR + (swz(p2_freq_to_pos(LOG, ky)) ^ ((r * AX) & 7))] = y[j][s2];
+            else yh[r] = y[j][s2];
+          }
+        }
+      }
+    }
+  } else {
   // transposed load, 8 independent 16-byte loads in flight per thread
   constexpr int UL = 8;
 #pragma unroll 1
@@ -229,6 +301,7 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
         else yh[r] = y[j];
       }
     }
+  }
   }
   __syncthreads();
 
@@ -284,18 +357,33 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
 
 struct FastRowsCfg { int nr, rb, t; };
 
-// variant id = ny, or ny + 1 for the 4-rows-per-CTA variant of ny = 4096
+// variant id = ny + k: k = 0 the default; experimental variants, selected with the environment
+// variable GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
+//   ny = 4096: +1 four rows per CTA, +2 three CTAs per SM, +3 256-bit transposed accesses,
+//              +4 both;   ny = 8192: +3 256-bit transposed accesses
 inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
   switch (variant) {
     case 2048: c = {1024, 4, 128}; return true;
-    case 4096: c = {2048, 2, 256}; return true;
+    case 4096: case 4098: case 4099: case 4100: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
-    case 8192: c = {4096, 2, 512}; return true;
+    case 8192: case 8195: c = {4096, 2, 512}; return true;
     case 16384: c = {8192, 1, 512}; return true;
     default: return false;
   }
 }
+
+// X(id, NR, RB, T, MB, W256) for every instantiated row-kernel variant
+#define ROWS_VARIANTS(X)            \
+  X(2048, 1024, 4, 128, 0, false)   \
+  X(4096, 2048, 2, 256, 0, false)   \
+  X(4097, 2048, 4, 512, 0, false)   \
+  X(4098, 2048, 2, 256, 3, false)   \
+  X(4099, 2048, 2, 256, 0, true)    \
+  X(4100, 2048, 2, 256, 3, true)    \
+  X(8192, 4096, 2, 512, 0, false)   \
+  X(8195, 4096, 2, 512, 0, true)    \
+  X(16384, 8192, 1, 512, 0, false)
 
 inline size_t fast_rows_smem(const FastRowsCfg &c)
 {
@@ -320,23 +408,25 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
   FastRowsCfg rc;
   int rv = g.ny;
   if (g.ny == 4096 && getenv("GFMD_B200_ROWS_RB4") && g.nx_loc % 4 == 0) rv = 4097;
+  if (const char *e = getenv("GFMD_B200_ROWS_VARIANT")) {
+    const int want = atoi(e);
+    if (want >= g.ny && want < g.ny + 8 && fast_rows_cfg(want, rc) && 2 * rc.nr == g.ny) rv = want;
+  }
   if (fast_rows_cfg(rv, rc) && g.nx_loc % rc.rb == 0) {
     fast_rows = rv;
     cudaError_t e = cudaSuccess;
-#define ROWS_ATTR(NR, RB, T)                                                                              \
-  e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                           (int) fast_rows_smem(rc));                                                     \
-  if (e == cudaSuccess)                                                                                   \
-    e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                             (int) fast_rows_smem(rc));
     switch (rv) {
-      case 2048: ROWS_ATTR(1024, 4, 128) break;
-      case 4096: ROWS_ATTR(2048, 2, 256) break;
-      case 4097: ROWS_ATTR(2048, 4, 512) break;
-      case 8192: ROWS_ATTR(4096, 2, 512) break;
-      case 16384: ROWS_ATTR(8192, 1, 512) break;
-    }
+#define ROWS_ATTR(ID, NR, RB, T, MB, W)                                                                       \
+  case ID:                                                                                                    \
+    e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T, MB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                             (int) fast_rows_smem(rc));                                                       \
+    if (e == cudaSuccess)                                                                                     \
+      e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T, MB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                               (int) fast_rows_smem(rc));                                                     \
+    break;
+      ROWS_VARIANTS(ROWS_ATTR)
 #undef ROWS_ATTR
+    }
     if (e != cudaSuccess) return 1;
   }
   cols_top = 0;
@@ -377,11 +467,10 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-    case 2048: k_rows_fwd_p2<1024, 4, 128><<<grid, 128, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
-    case 4096: k_rows_fwd_p2<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
-    case 4097: k_rows_fwd_p2<2048, 4, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
-    case 8192: k_rows_fwd_p2<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
-    case 16384: k_rows_fwd_p2<8192, 1, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+#define ROWS_LAUNCH(ID, NR, RB, T, MB, W) \
+  case ID: k_rows_fwd_p2<NR, RB, T, MB, W><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    ROWS_VARIANTS(ROWS_LAUNCH)
+#undef ROWS_LAUNCH
     default: return 1;
   }
   ++*launches;
@@ -397,11 +486,10 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-    case 2048: k_rows_inv_p2<1024, 4, 128><<<grid, 128, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
-    case 4096: k_rows_inv_p2<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
-    case 4097: k_rows_inv_p2<2048, 4, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
-    case 8192: k_rows_inv_p2<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
-    case 16384: k_rows_inv_p2<8192, 1, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+#define ROWS_LAUNCH(ID, NR, RB, T, MB, W) \
+  case ID: k_rows_inv_p2<NR, RB, T, MB, W><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    ROWS_VARIANTS(ROWS_LAUNCH)
+#undef ROWS_LAUNCH
     default: return 1;
   }
   ++*launches;
