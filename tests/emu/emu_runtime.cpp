@@ -138,8 +138,8 @@ void *dyn_smem() { return g_dyn; }
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
   const int n = (int) (block.x * block.y * block.z);
-  if (n < 1 || n > 1024) {
-    fprintf(stderr, "cuda emu: block of %d threads\n", n);
+  if (n < 1 || n > 1024 || smem_bytes > 232448) {
+    fprintf(stderr, "cuda emu: block of %d threads, %zu B of dynamic shared memory\n", n, smem_bytes);
     abort();
   }
   if ((int) g_fib.size() < n) g_fib.resize(n);
@@ -212,6 +212,7 @@ const char *cudaGetErrorString(cudaError_t e)
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 3; return cudaSuccess; }   /* "SMs" */
 cudaError_t cudaMalloc(void **p, size_t bytes)

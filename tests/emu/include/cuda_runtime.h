@@ -88,6 +88,7 @@ const char *cudaGetErrorString(cudaError_t);
 cudaError_t cudaGetLastError();
 cudaError_t cudaGetDeviceCount(int *);
 cudaError_t cudaSetDevice(int);
+cudaError_t cudaGetDevice(int *);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaDeviceGetAttribute(int *, cudaDeviceAttr, int);
 cudaError_t cudaMalloc(void **, size_t);

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -326,6 +327,23 @@ int fail(gfmd_b200 *h, int code, const char *fmt, ...)
       return fail(h, GFMD_B200_ENCCL, "%s failed: %s", #call, nccl().GetErrorString(r__)); \
   } while (0)
 
+// The dynamic shared-memory limit is an attribute of the kernel (per device), not of a handle:
+// only ever raise it, or a second handle with a smaller grid would lower it under the first.
+cudaError_t grow_dyn_smem(const void *func, size_t bytes)
+{
+  static std::mutex m;
+  static std::map<std::pair<int, const void *>, size_t> granted;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(m);
+  size_t &have = granted[std::make_pair(dev, func)];
+  if (bytes <= have) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
 template <typename T> cudaError_t dmalloc(gfmd_b200 *h, T **p, size_t count)
 {
   size_t bytes = sizeof(T) * (count ? count : 1);
@@ -409,9 +427,7 @@ int plan(gfmd_b200 *h)
   if (t > 512) t = 512;
   h->cols_T = t;
 
-  // The attribute belongs to the kernel, not to this handle: always grant the full opt-in
-  // amount, or a second handle with a smaller grid would lower the limit under the first.
-#define SET_SMEM(k, bytes) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxSmem))
+#define SET_SMEM(k, bytes) CU(h, grow_dyn_smem((const void *) k, bytes))
   if (h->even) {
     SET_SMEM(k_rows_fwd<true>, h->rows_smem);
     SET_SMEM(k_rows_inv<true>, h->rows_smem);
@@ -769,9 +785,7 @@ int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool 
   if (mode == AUX_PREC && !(g.d == 3 || g.d == 6 || g.d == 9 || g.d == 12))
     return fail(h, GFMD_B200_EUNSUPPORTED, "prec_gradient: ndof %d (3, 6, 9, 12 supported)", g.d);
   if (!h->aux_attr_set) {
-#define SET_AUX(DT, MODE)                                                                        \
-  CU(h, cudaFuncSetAttribute(k_cols_aux<DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int) kMaxSmem))
+#define SET_AUX(DT, MODE) CU(h, grow_dyn_smem((const void *) k_cols_aux<DT, MODE>, h->aux_cols_smem))
     switch (g.d) {
       case 3: SET_AUX(3, AUX_SPECTRUM); SET_AUX(3, AUX_PREC); break;
       case 6: SET_AUX(6, AUX_SPECTRUM); SET_AUX(6, AUX_PREC); break;

@@ -359,13 +359,16 @@ struct FastRowsCfg { int nr, rb, t; };
 
 // variant id = ny + k: k = 0 the default; experimental variants, selected with the environment
 // variable GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
-//   ny = 4096: +1 four rows per CTA, +2 three CTAs per SM, +3 256-bit transposed accesses,
-//              +4 both;   ny = 8192: +3 256-bit transposed accesses
+//   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise.
+// Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
+// rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
+// three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
+// is not kept.  The template parameter MB stays for such experiments.
 inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
   switch (variant) {
     case 2048: c = {1024, 4, 128}; return true;
-    case 4096: case 4098: case 4099: case 4100: c = {2048, 2, 256}; return true;
+    case 4096: case 4099: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
     case 8192: case 8195: c = {4096, 2, 512}; return true;
     case 16384: c = {8192, 1, 512}; return true;
@@ -378,9 +381,7 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
   X(2048, 1024, 4, 128, 0, false)   \
   X(4096, 2048, 2, 256, 0, false)   \
   X(4097, 2048, 4, 512, 0, false)   \
-  X(4098, 2048, 2, 256, 3, false)   \
   X(4099, 2048, 2, 256, 0, true)    \
-  X(4100, 2048, 2, 256, 3, true)    \
   X(8192, 4096, 2, 512, 0, false)   \
   X(8195, 4096, 2, 512, 0, true)    \
   X(16384, 8192, 1, 512, 0, false)
