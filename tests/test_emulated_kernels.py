@@ -281,3 +281,33 @@ def test_row_kernel_variants(B, nx, ny, variant, oracle_libs, monkeypatch):
     assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
     assert abs(e - e_ref) <= TOL * abs(e_ref)
     s.close()
+
+
+def test_sweep_of_small_grids(B, oracle_libs):
+    """Every grid up to 24 x 24 (all radix mixes, Bluestein for 11, 13, 17, 19, 23, odd and even
+    rows) plus a few long smooth / prime extents, ndof 3 or 6, against the oracle."""
+    O = oracle_libs
+    rng = np.random.default_rng(0)
+    grids = [(nx, ny) for nx in range(1, 25) for ny in range(1, 25)]
+    grids += [(n, m) for n in (49, 81, 97, 125, 243, 251, 343, 1021) for m in (1, 6)]
+    grids += [(m, n) for n, m in grids[-16:]]
+    bad = []
+    for nx, ny in grids:
+        d = 3 if (nx + ny) % 3 else 6
+        Dr = rng.standard_normal((nx, ny, d, d))
+        Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+        Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+        phi = np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+        linf = rng.standard_normal(d // 3)
+        u = rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+        f_ref, e_ref, _ = O.post_force(u, phi, linf)
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        s.set_kernel(phi, linf)
+        uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+        f = np.full_like(uu, np.nan)
+        e = s.post_force(uu, f)
+        s.close()
+        if not (rel_err(f.reshape(d, nx, ny), f_ref) < TOL and abs(e - e_ref) <= TOL * abs(e_ref)):
+            bad.append((nx, ny, d))
+    assert not bad, bad
