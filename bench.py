@@ -363,22 +363,34 @@ def main_b200(args):
     n_e2e = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, 10))
     hu = torch.tensor(u.reshape(d, nx_loc * ny)).pin_memory()
     hf = torch.empty_like(hu).pin_memory()
-    for _ in range(2):
-        s.post_force(hu, hf)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        s.post_force(hu, hf)
-    barrier()
-    dt_e2e = (time.perf_counter() - t0) / n_e2e
-    if world > 1:
-        t = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_e2e = float(t.item())
+
+    def time_e2e():
+        for _ in range(2):
+            s.post_force(hu, hf)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            s.post_force(hu, hf)
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    # the library default first (that is `e2e`), then the other setting of the host pipeline
+    hp_default = s.host_pipeline()
+    dt_e2e = time_e2e()
+    s.host_pipeline(not hp_default)
+    dt_e2e_other = time_e2e()
+    s.host_pipeline(hp_default)
     grid_bytes = d * nx_loc * ny * 8
     e2e = {"value": 1.0 / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": grid_bytes,
            "d2h_bytes_per_step": grid_bytes + 8 * (d + 1), "steps": n_e2e,
-           "call": "gfmd_b200_post_force_host (GFMDSolver::post_force boundary), pinned host u_xy/f_xy"}
+           "call": "gfmd_b200_post_force_host (GFMDSolver::post_force boundary), pinned host u_xy/f_xy",
+           "host_pipeline": hp_default,
+           "value_with_host_pipeline_%s" % ("off" if hp_default else "on"): 1.0 / dt_e2e_other}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -205,6 +205,15 @@ int gfmd_b200_synchronize(gfmd_b200_t *h);
  * post_force_host sees them; they are released by on=0 or destroy.  Only for
  * long-lived buffers such as the fix's u_xy/f_xy.  Default off. */
 int gfmd_b200_pin_host_buffers(gfmd_b200_t *h, int on);
+/* Host pipeline of gfmd_b200_pre_force_async_host / _post_force_host (default on; single rank
+ * with the specialised row kernels, i.e. ny a power of two >= 2048; otherwise ignored): u is
+ * uploaded and f downloaded dof by dof on two copy streams, so that the row transforms of one
+ * dof overlap the PCIe transfer of the next.  Same kernels, bit-identical results.
+ * on = 1 / 0 sets it, on < 0 only queries; returns the setting (0 / 1) -- NOT an error code --
+ * or GFMD_B200_EINVAL (>1) for a null handle.  Environment GFMD_B200_HOST_PIPE=0 disables it
+ * at creation. */
+int gfmd_b200_host_pipeline(gfmd_b200_t *h, int on);
+
 /* replay the solver step through a captured CUDA graph (single GPU) */
 int gfmd_b200_use_graph(gfmd_b200_t *h, int on);
 

@@ -311,3 +311,32 @@ def test_sweep_of_small_grids(B, oracle_libs):
         if not (rel_err(f.reshape(d, nx, ny), f_ref) < TOL and abs(e - e_ref) <= TOL * abs(e_ref)):
             bad.append((nx, ny, d))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("nx,ny,d", [(4, 2048, 3), (2, 4096, 6)])
+def test_host_pipeline_is_bit_identical(B, nx, ny, d, oracle_libs, monkeypatch):
+    """GFMD_B200_HOST_PIPE=1: u uploaded and f downloaded dof by dof around per-dof row kernels
+    (enqueue_solver_hostpipe) -- same kernels, so the same bits as the plain host path; also via
+    pre_force.  (Streams are synchronous here; the event ordering is checked on the GPU.)"""
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    out = {}
+    for pipe in ("0", "1"):
+        monkeypatch.setenv("GFMD_B200_HOST_PIPE", pipe)
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        s.set_kernel(phi, linf)
+        f = np.full_like(uu, np.nan)
+        e = s.post_force(uu, f)
+        f2 = np.full_like(uu, np.nan)
+        s.pre_force(uu, f2)
+        e2 = s.post_force(uu, f2)
+        assert np.array_equal(f, f2) and e == e2
+        out[pipe] = (f, e, s.get_u0().copy())
+        s.close()
+    assert np.array_equal(out["0"][0], out["1"][0]) and out["0"][1] == out["1"][1]
+    assert np.array_equal(out["0"][2], out["1"][2])
+    assert rel_err(out["1"][0].reshape(d, nx, ny), f_ref) < TOL
+    assert abs(out["1"][1] - e_ref) <= TOL * abs(e_ref)

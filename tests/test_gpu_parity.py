@@ -321,3 +321,42 @@ def test_row_kernel_variants_against_oracle(B, nx, ny, variant, oracle_libs, mon
     s.close()
     assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
     assert abs(e - e_ref) <= TOL * abs(e_ref)
+
+
+@pytest.mark.parametrize("nx,ny,d", [(2048, 2048, 3), (64, 2048, 6), (128, 4096, 3)])
+def test_host_pipeline_is_bit_identical(B, nx, ny, d, monkeypatch):
+    """GFMD_B200_HOST_PIPE: u uploaded and f downloaded dof by dof on copy streams around per-dof
+    row kernels.  Same kernels, so the forces must equal the plain host path bit for bit, on
+    repeated steps (event / stream ordering) and through pre_force."""
+    from gfmd_b200 import synthetic
+    rng = np.random.default_rng(nx + ny + d)
+    us = [rng.uniform(-0.1, 0.1, size=(d, nx * ny)) for _ in range(3)]
+    out = {}
+    for pipe in ("0", "1"):
+        monkeypatch.setenv("GFMD_B200_HOST_PIPE", pipe)
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        for k0 in range(0, s.nky, 256):
+            nk = min(256, s.nky - k0)
+            P = np.zeros((nx, nk, d, d), dtype=np.complex128)
+            P[..., :3, :3] = synthetic.phi_columns(nx, ny, k0, nk)
+            if d == 6:
+                P[..., 3:, 3:] = 0.5 * synthetic.phi_columns(nx, ny, k0, nk)
+                P[..., 0, 3] = P[..., 3, 0] = 0.25
+            s.set_kernel_columns(P, k0, normalized=False)
+        s.set_linf(np.full(d // 3, 0.125))
+        s.pin_host_buffers(True)
+        res = []
+        for it in range(6):
+            u = us[it % 3]
+            f = np.full_like(u, np.nan)
+            if it % 2:
+                s.pre_force(u, f)
+            e = s.post_force(u, f)
+            res.append((f, e, s.get_u0().copy()))
+        out[pipe] = res
+        s.close()
+    for (f0, e0, a0), (f1, e1, a1) in zip(out["0"], out["1"]):
+        assert np.array_equal(f0, f1) and e0 == e1 and np.array_equal(a0, a1)
+    assert np.isfinite(out["1"][0][0]).all() and abs(out["1"][0][1]) > 0
+    assert not np.array_equal(out["1"][0][0], out["1"][1][0])

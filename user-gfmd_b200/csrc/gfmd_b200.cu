@@ -284,6 +284,11 @@ struct gfmd_b200 {
 
   // async host path
   const double *pending_u = nullptr;
+  // host pipeline: u arrives and f leaves dof by dof on two copy streams, so that the row
+  // transforms of a dof overlap the PCIe transfer of the next one (single rank, specialised rows)
+  bool hp_enabled = true, hp_pending = false;
+  cudaStream_t hp_stream[2] = {};
+  cudaEvent_t hp_in[GFMD_B200_MAX_NDOF] = {}, hp_out[GFMD_B200_MAX_NDOF] = {}, hp_fork = nullptr, hp_done = nullptr;
   std::map<const void *, size_t> pinned;   // host ranges this handle page-locked
   bool pin_host = false;
 
@@ -492,6 +497,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
     return bail(GFMD_B200_ECUDA);
   }
   h->own_stream = true;
+  if (const char *e = getenv("GFMD_B200_HOST_PIPE")) h->hp_enabled = atoi(e) != 0;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   if ((rc = plan(h))) return bail(rc);
 
@@ -682,6 +688,67 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
   for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[(g.rank + k) % g.P], 0));
   // u0 all-reduce (gfmd_solver_static.cpp:176) doubles as the barrier of the return pushes
   NC(h, a.AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm, h->stream));
+  return 0;
+}
+
+// Host-pipelined solver step (single rank, specialised row kernels): the upload of dof k + 1
+// runs on a copy stream while the rows of dof k are transformed; the row results of the way
+// back are handed to the download stream dof by dof (events hp_out, consumed by
+// gfmd_b200_post_force_host).  Same kernels, same arithmetic as enqueue_solver.
+int enqueue_solver_hostpipe(gfmd_b200 *h, const double *u_host)
+{
+  const GridDesc &g = h->g;
+  const size_t nxy = (size_t) g.nx_loc * g.ny;
+  double2 *A = h->d_stage;
+  if (!h->hp_stream[0]) {
+    for (int i = 0; i < 2; ++i) CU(h, cudaStreamCreateWithFlags(&h->hp_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < g.d; ++i) {
+      CU(h, cudaEventCreateWithFlags(&h->hp_in[i], cudaEventDisableTiming));
+      CU(h, cudaEventCreateWithFlags(&h->hp_out[i], cudaEventDisableTiming));
+    }
+    CU(h, cudaEventCreateWithFlags(&h->hp_fork, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->hp_done, cudaEventDisableTiming));
+  }
+  CU(h, cudaMemsetAsync(&h->d_res->epot, 0, offsetof(StepResults, fsum), h->stream));
+  // the uploads may not overtake earlier work of this handle that still reads d_u
+  CU(h, cudaEventRecord(h->hp_fork, h->stream));
+  CU(h, cudaStreamWaitEvent(h->hp_stream[0], h->hp_fork, 0));
+  for (int dof = 0; dof < g.d; ++dof) {
+    CU(h, cudaMemcpyAsync(h->d_u + dof * nxy, u_host + dof * nxy, nxy * sizeof(double), cudaMemcpyHostToDevice,
+                          h->hp_stream[0]));
+    CU(h, cudaEventRecord(h->hp_in[dof], h->hp_stream[0]));
+    CU(h, cudaStreamWaitEvent(h->stream, h->hp_in[dof], 0));
+    if (fast_rows_fwd(h->fast_rows, h->d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, dof, 1))
+      return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
+  }
+  if (h->fast_cols) {
+    const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
+    if (fast_cols_fused(h->fast_cols, h->cols_top, A, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
+                        h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches))
+      return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+  } else {
+#define LAUNCH_COLS(DT)                                                                          \
+  k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
+      A, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
+    switch (g.d) {
+      case 3: LAUNCH_COLS(3); break;
+      case 6: LAUNCH_COLS(6); break;
+      case 9: LAUNCH_COLS(9); break;
+      case 12: LAUNCH_COLS(12); break;
+      default: LAUNCH_COLS(0); break;
+    }
+#undef LAUNCH_COLS
+    h->launches++;
+  }
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
+  h->launches++;
+  for (int dof = 0; dof < g.d; ++dof) {
+    if (fast_rows_inv(h->fast_rows, A, h->d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, dof, 1))
+      return fail(h, GFMD_B200_ECUDA, "fast rows_inv launch failed");
+    CU(h, cudaEventRecord(h->hp_out[dof], h->stream));
+  }
+  CU(h, cudaGetLastError());
+  h->hp_pending = true;
   return 0;
 }
 
@@ -1128,6 +1195,14 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   free_fft(h->fft_sub);
   for (int i = 0; i <= GFMD_B200_NSTAGES; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->hp_stream[i]) cudaStreamDestroy(h->hp_stream[i]);
+  for (int i = 0; i < GFMD_B200_MAX_NDOF; ++i) {
+    if (h->hp_in[i]) cudaEventDestroy(h->hp_in[i]);
+    if (h->hp_out[i]) cudaEventDestroy(h->hp_out[i]);
+  }
+  if (h->hp_fork) cudaEventDestroy(h->hp_fork);
+  if (h->hp_done) cudaEventDestroy(h->hp_done);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1323,8 +1398,14 @@ int gfmd_b200_pre_force_async_host(gfmd_b200_t *h, const double *u)
   if (rc) return rc;
   const size_t bytes = sizeof(double) * (size_t) h->g.d * h->g.nx_loc * h->g.ny;
   try_pin(h, u, bytes);
-  CU(h, cudaMemcpyAsync(h->d_u, u, bytes, cudaMemcpyHostToDevice, h->stream));
-  rc = solver_step(h, h->d_u, h->d_f);
+  h->hp_pending = false;
+  if (h->hp_enabled && h->g.P == 1 && h->fast_rows && !h->want_graph && !h->profiling) {
+    if (!h->phi_set) return fail(h, GFMD_B200_ESTATE, "post_force before set_phi (set_kernel)");
+    rc = enqueue_solver_hostpipe(h, u);
+  } else {
+    CU(h, cudaMemcpyAsync(h->d_u, u, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = solver_step(h, h->d_u, h->d_f);
+  }
   if (rc) return rc;
   h->pending_u = u;
   return 0;
@@ -1342,7 +1423,20 @@ int gfmd_b200_post_force_host(gfmd_b200_t *h, const double *u, double *f, double
   }
   h->pending_u = nullptr;
   try_pin(h, f, bytes);
-  CU(h, cudaMemcpyAsync(f, h->d_f, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (h->hp_pending) {
+    // download each dof as soon as its rows are back in real space
+    const size_t nxy = (size_t) h->g.nx_loc * h->g.ny;
+    for (int dof = 0; dof < h->g.d; ++dof) {
+      CU(h, cudaStreamWaitEvent(h->hp_stream[1], h->hp_out[dof], 0));
+      CU(h, cudaMemcpyAsync(f + dof * nxy, h->d_f + dof * nxy, nxy * sizeof(double), cudaMemcpyDeviceToHost,
+                            h->hp_stream[1]));
+    }
+    CU(h, cudaEventRecord(h->hp_done, h->hp_stream[1]));
+    CU(h, cudaStreamWaitEvent(h->stream, h->hp_done, 0));
+    h->hp_pending = false;
+  } else {
+    CU(h, cudaMemcpyAsync(f, h->d_f, bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
   rc = fetch_results(h);
   if (rc) return rc;
   if (epot) *epot = h->h_res->epot;
@@ -1531,6 +1625,14 @@ int gfmd_b200_pin_host_buffers(gfmd_b200_t *h, int on)
     h->pinned.clear();
   }
   return 0;
+}
+
+int gfmd_b200_host_pipeline(gfmd_b200_t *h, int on)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  if (h->pending_u) return fail(h, GFMD_B200_ESTATE, "host_pipeline between pre_force and post_force");
+  if (on >= 0) h->hp_enabled = on != 0;
+  return h->hp_enabled ? 1 : 0;
 }
 
 int gfmd_b200_use_graph(gfmd_b200_t *h, int on)

@@ -63,6 +63,7 @@ ABI = {
     "gfmd_b200_synchronize": (_i, [_vp]),
     "gfmd_b200_pin_host_buffers": (_i, [_vp, _i]),
     "gfmd_b200_use_graph": (_i, [_vp, _i]),
+    "gfmd_b200_host_pipeline": (_i, [_vp, _i]),
     "gfmd_b200_launch_count": (ctypes.c_longlong, [_vp]),
     "gfmd_b200_profile": (_i, [_vp, _i]),
     "gfmd_b200_get_stage_times": (_i, [_vp, _vp, _vp]),
@@ -339,6 +340,14 @@ class GFMDSolverB200:
 
     def pin_host_buffers(self, on=True):
         self._check(self.lib.gfmd_b200_pin_host_buffers(self.h, int(on)))
+
+    def host_pipeline(self, on=None):
+        """Per-dof upload / download pipeline of the host path (see include/gfmd_b200.h);
+        on=None only queries.  Returns the setting."""
+        rc = self.lib.gfmd_b200_host_pipeline(self.h, -1 if on is None else int(bool(on)))
+        if rc > 1:
+            self._check(rc)
+        return bool(rc)
 
     def use_graph(self, on=True):
         self._check(self.lib.gfmd_b200_use_graph(self.h, int(on)))
