@@ -209,8 +209,8 @@ int gfmd_b200_pin_host_buffers(gfmd_b200_t *h, int on);
  * with the specialised row kernels, i.e. ny a power of two >= 2048; otherwise ignored): u is
  * uploaded and f downloaded dof by dof on two copy streams, so that the row transforms of one
  * dof overlap the PCIe transfer of the next.  Same kernels, bit-identical results.
- * on = 1 / 0 sets it, on < 0 only queries; returns the setting (0 / 1) -- NOT an error code --
- * or GFMD_B200_EINVAL (>1) for a null handle.  Environment GFMD_B200_HOST_PIPE=0 disables it
+ * on = 1 / 0 sets it, on < 0 only queries; returns whether it takes effect for this handle
+ * (0 / 1) -- NOT an error code -- or GFMD_B200_EINVAL (>1) for a null handle.  Environment GFMD_B200_HOST_PIPE=0 disables it
  * at creation. */
 int gfmd_b200_host_pipeline(gfmd_b200_t *h, int on);
 

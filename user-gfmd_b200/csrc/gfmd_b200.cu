@@ -1632,7 +1632,7 @@ int gfmd_b200_host_pipeline(gfmd_b200_t *h, int on)
   if (!h) return GFMD_B200_EINVAL;
   if (h->pending_u) return fail(h, GFMD_B200_ESTATE, "host_pipeline between pre_force and post_force");
   if (on >= 0) h->hp_enabled = on != 0;
-  return h->hp_enabled ? 1 : 0;
+  return (h->hp_enabled && h->g.P == 1 && h->fast_rows) ? 1 : 0;     // whether it takes effect
 }
 
 int gfmd_b200_use_graph(gfmd_b200_t *h, int on)
