@@ -416,6 +416,11 @@ def main_b200(args):
                "cpu_baseline": cpu, "nvlink": nvlink,
                "solver_only": {"value": 1e3 / ms_solver, "unit": UNIT, "ms_per_step": ms_solver},
                "stage_ms": stage_ms, "epot": res["epot"]}
+        # full-size check: the energy of this exact workload computed independently on the CPU
+        # (tools/epot_reference_4096.py: numpy rfft2 + np.linalg.solve recursion, ~16 min)
+        if world == 1 and (nx, ny, d) == (4096, 4096, 3):
+            out["epot_reference"] = 442.2815166173698
+            out["epot_rel_err"] = abs(res["epot"] - 442.2815166173698) / 442.2815166173698
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     s.close()

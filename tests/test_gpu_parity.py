@@ -296,10 +296,11 @@ def test_async_pre_force_and_errors(B):
     s.close()
 
 
-@pytest.mark.parametrize("nx,ny,variant", [(64, 4096, 4097), (64, 4096, 4099), (32, 8192, 8195)])
+@pytest.mark.parametrize("nx,ny,variant", [(64, 4096, 4097), (64, 4096, 4099), (32, 8192, 8195),
+                                            (64, 2048, 2053), (128, 4096, 4101), (32, 8192, 8197), (16, 16384, 16389)])
 def test_row_kernel_variants_against_oracle(B, nx, ny, variant, oracle_libs, monkeypatch):
     """Experimental row-kernel variants (GFMD_B200_ROWS_VARIANT, csrc/kernels_fast.cuh: 256-bit
-    transposed accesses, four rows per CTA) keep the same parity bar."""
+    transposed accesses, four rows per CTA, last pass fused with the real/complex (un)mixing) keep the same parity bar."""
     O = oracle_libs
     d = 3
     rng = np.random.default_rng(variant)

@@ -74,6 +74,20 @@ __host__ __device__ inline int p2_freq_to_pos(int log, int k)
   return pos;
 }
 
+// inverse of p2_freq_to_pos
+__host__ __device__ inline int p2_pos_to_freq(int log, int pos)
+{
+  const int np = (log + 2) / 3;
+  const int lr0 = log - 3 * (np - 1);
+  int k = pos >> (3 * (np - 1));
+  int sh = lr0;
+  for (int p = 1; p < np; ++p) {
+    k |= ((pos >> (3 * (np - 1 - p))) & 7) << sh;
+    sh += 3;
+  }
+  return k;
+}
+
 // Where plane c of wavevector kx lives inside one column's block of d*d*nx doubles:
 // off + c * cstride.  Generic kernels: plane-major [c][kx].  Specialised column kernels:
 // the spectrum is digit-reversed (pos) and the planes are interleaved item by item,

@@ -148,10 +148,45 @@ template <int NR> __device__ __forceinline__ int rows256_ky(int i)
   return (i & ~((8 << L0) - 1)) | ((i & 7) << L0) | ((i >> 3) & ((1 << L0) - 1));
 }
 
+// ---- fused last pass + real/complex (un)mixing of the row kernels (FUSE variants) ----
+// The packed half-length transform Z (length h = NR) and the spectrum X of the real row are
+// related pairwise, k <-> h - k.  The last radix-8 pass (stride 1) of butterfly `klow`
+// (frequencies klow + q S, S = NR / 8) therefore pairs with the one of butterfly S - klow, output
+// q with output 7 - q: a thread that runs BOTH butterflies has every pair in registers and can
+// un-mix and store straight to global memory (forward), or load, pre-mix and run the first
+// inverse butterflies (backward) -- the spectrum never goes through shared memory a second
+// time: 3 (forward) and 4 (backward) of the ~10 sweeps over the tile disappear, with two block
+// barriers.  Butterflies 0 and S / 2 pair with themselves and form one unit together, so a row
+// has exactly NR / 16 units.  Arithmetic per element is that of the unfused code (bit-identical).
+
+// unit p in [1, NR/16) -> klow in [1, NR/16): the eight lanes of a quarter warp take eight values
+// of the SECOND spectrum digit, so that both butterflies they load sit in different
+// shared-memory columns (cf. rows256_ky)
+template <int NR> __device__ __forceinline__ int rowsfuse_klow(int p) { return rows256_ky<NR>(p); }
+
+// X[k] = A - i w B,  A = (Z[k] + conj Z[h-k]) / 2,  B = (Z[k] - conj Z[h-k]) / 2
+__device__ __forceinline__ double2 rows_unmix(double2 zk, double2 zpartner, double2 w)
+{
+  const double2 zc = cconj(zpartner);
+  const double2 A = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
+  const double2 B = make_double2(0.5 * (zk.x - zc.x), 0.5 * (zk.y - zc.y));
+  const double2 t = cmul(w, B);
+  return make_double2(A.x + t.y, A.y - t.x);
+}
+
+// Z'[k] = (Y[k] + conj Y[h-k]) + i conj(w) (Y[k] - conj Y[h-k])
+__device__ __forceinline__ double2 rows_premix(double2 yk, double2 ypartner, double2 w)
+{
+  const double2 c2 = cconj(ypartner);
+  const double2 S = cadd(yk, c2), Dv = csub(yk, c2);
+  const double2 t = cmulc(Dv, w);
+  return make_double2(S.x - t.y, S.y + t.x);
+}
+
 // RB rows (same dof) of ny = 2 NR reals per CTA; array a = row a of the tile.
 // MB = CTAs per SM the register allocation aims at; W256 = the transposed stores move the
 // two rows of a pair with one 256-bit instruction per wavevector (RB even).
-template <int NR, int RB, int T, int MB = 0, bool W256 = false>
+template <int NR, int RB, int T, int MB = 0, bool W256 = false, bool FUSE = false>
 __global__ void __launch_bounds__(T, MB)
 k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
@@ -173,6 +208,42 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   p2_groupA_rest_blk<NR, T, -1, RB, AX>(sm, tw, tws);
 #pragma unroll 1
   for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_seq<NR, -1, RB, AX>(sm, tws, idx);
+  if constexpr (FUSE) {
+    constexpr int S = NR / 8, HU = NR / 16;
+    __syncthreads();
+#pragma unroll 1
+    for (int ui = threadIdx.x; ui < RB * HU; ui += T) {
+      const int r = ui / HU, p = ui - r * HU;
+      const int rx = (r * AX) & 7;
+      const double2 *row = sm + r * NR;
+      const int klow = p == 0 ? 0 : rowsfuse_klow<NR>(p);
+      const int klow2 = p == 0 ? S / 2 : S - klow;
+      const int b1 = p2_freq_to_pos(LOG, klow), b2 = p2_freq_to_pos(LOG, klow2);
+      double2 v1[8], v2[8];
+      p2_last_fwd_load(row, b1, swz_key(b1) ^ rx, v1);
+      p2_last_fwd_load(row, b2, swz_key(b2) ^ rx, v2);
+      if (p == 0) {
+        // butterflies 0 and S/2 pair with themselves: k = q S <-> (8 - q) S, and S/2 + q S <-> S/2 + (7 - q) S
+        stage[stage_index(g, 0, dof, ix0 + r)] = rows_unmix(v1[0], v1[0], __ldg(tw_ny));
+        stage[stage_index(g, NR, dof, ix0 + r)] = rows_unmix(v1[0], v1[0], __ldg(tw_ny + NR));
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+          stage[stage_index(g, q * S, dof, ix0 + r)] = rows_unmix(v1[q], v1[8 - q], __ldg(tw_ny + q * S));
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          stage[stage_index(g, S / 2 + q * S, dof, ix0 + r)] =
+              rows_unmix(v2[q], v2[7 - q], __ldg(tw_ny + S / 2 + q * S));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = klow + q * S, k2 = klow2 + q * S;
+          stage[stage_index(g, k, dof, ix0 + r)] = rows_unmix(v1[q], v2[7 - q], __ldg(tw_ny + k));
+          stage[stage_index(g, k2, dof, ix0 + r)] = rows_unmix(v2[q], v1[7 - q], __ldg(tw_ny + k2));
+        }
+      }
+    }
+    return;
+  }
   __syncwarp();
 #pragma unroll 1
   for (int idx = threadIdx.x; idx < NR / 8; idx += T) {
@@ -232,7 +303,7 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   }
 }
 
-template <int NR, int RB, int T, int MB = 0, bool W256 = false>
+template <int NR, int RB, int T, int MB = 0, bool W256 = false, bool FUSE = false>
 __global__ void __launch_bounds__(T, MB)
 k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
@@ -249,6 +320,48 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   constexpr int h = NR;
   p2_fill_tws<NR>(tws, tw);
 
+  if constexpr (FUSE) {
+    // transposed load of both butterflies of a unit (16 independent 16-byte loads), pre-mix in
+    // registers, first inverse butterflies, one store sweep to shared memory
+    constexpr int S = NR / 8, HU = NR / 16;
+#pragma unroll 1
+    for (int ui = threadIdx.x; ui < RB * HU; ui += T) {
+      const int r = ui / HU, p = ui - r * HU;
+      const int rx = (r * AX) & 7;
+      double2 *row = sm + r * NR;
+      const int klow = p == 0 ? 0 : rowsfuse_klow<NR>(p);
+      const int klow2 = p == 0 ? S / 2 : S - klow;
+      const int b1 = p2_freq_to_pos(LOG, klow), b2 = p2_freq_to_pos(LOG, klow2);
+      double2 y1[8], y2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        y1[q] = stage[stage_index(g, klow + q * S, dof, ix0 + r)];
+        y2[q] = stage[stage_index(g, klow2 + q * S, dof, ix0 + r)];
+      }
+      if (p == 0) {
+        const double2 yh0 = stage[stage_index(g, NR, dof, ix0 + r)];
+        double2 z[8];
+        z[0] = rows_premix(y1[0], yh0, __ldg(tw_ny));
+#pragma unroll
+        for (int q = 1; q < 8; ++q) z[q] = rows_premix(y1[q], y1[8 - q], __ldg(tw_ny + q * S));
+        p2_last_inv_store(row, b1, swz_key(b1) ^ rx, z);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z[q] = rows_premix(y2[q], y2[7 - q], __ldg(tw_ny + S / 2 + q * S));
+        p2_last_inv_store(row, b2, swz_key(b2) ^ rx, z);
+      } else {
+        // the pair (y1[q], y2[7-q]) yields (z1[q], z2[7-q]): in place
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double2 a = y1[q], b = y2[7 - q];
+          y1[q] = rows_premix(a, b, __ldg(tw_ny + klow + q * S));
+          y2[7 - q] = rows_premix(b, a, __ldg(tw_ny + klow2 + (7 - q) * S));
+        }
+        p2_last_inv_store(row, b1, swz_key(b1) ^ rx, y1);
+        p2_last_inv_store(row, b2, swz_key(b2) ^ rx, y2);
+      }
+    }
+    __syncthreads();
+  } else {
   if constexpr (W256) {
     // transposed load, 4 independent 32-byte loads (both rows of a pair) in flight per thread
     static_assert(RB % 2 == 0, "256-bit loads pair two rows");
@@ -345,6 +458,7 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
     }
   }
   __syncwarp();
+  }   // !FUSE
 #pragma unroll 1
   for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_seq<NR, +1, RB, AX>(sm, tws, idx);
   p2_groupA_rest_blk<NR, T, +1, RB, AX>(sm, tw, tws);
@@ -359,7 +473,8 @@ struct FastRowsCfg { int nr, rb, t; };
 
 // variant id = ny + k: k = 0 the default; experimental variants, selected with the environment
 // variable GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
-//   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise.
+//   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise;
+//   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above).
 // Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
 // rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
 // three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
@@ -367,24 +482,28 @@ struct FastRowsCfg { int nr, rb, t; };
 inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
   switch (variant) {
-    case 2048: c = {1024, 4, 128}; return true;
-    case 4096: case 4099: c = {2048, 2, 256}; return true;
+    case 2048: case 2053: c = {1024, 4, 128}; return true;
+    case 4096: case 4099: case 4101: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
-    case 8192: case 8195: c = {4096, 2, 512}; return true;
-    case 16384: c = {8192, 1, 512}; return true;
+    case 8192: case 8195: case 8197: c = {4096, 2, 512}; return true;
+    case 16384: case 16389: c = {8192, 1, 512}; return true;
     default: return false;
   }
 }
 
-// X(id, NR, RB, T, MB, W256) for every instantiated row-kernel variant
-#define ROWS_VARIANTS(X)            \
-  X(2048, 1024, 4, 128, 0, false)   \
-  X(4096, 2048, 2, 256, 0, false)   \
-  X(4097, 2048, 4, 512, 0, false)   \
-  X(4099, 2048, 2, 256, 0, true)    \
-  X(8192, 4096, 2, 512, 0, false)   \
-  X(8195, 4096, 2, 512, 0, true)    \
-  X(16384, 8192, 1, 512, 0, false)
+// X(id, NR, RB, T, MB, W256, FUSE) for every instantiated row-kernel variant
+#define ROWS_VARIANTS(X)                   \
+  X(2048, 1024, 4, 128, 0, false, false)   \
+  X(2053, 1024, 4, 128, 0, false, true)    \
+  X(4096, 2048, 2, 256, 0, false, false)   \
+  X(4097, 2048, 4, 512, 0, false, false)   \
+  X(4099, 2048, 2, 256, 0, true, false)    \
+  X(4101, 2048, 2, 256, 2, false, true)    \
+  X(8192, 4096, 2, 512, 0, false, false)   \
+  X(8195, 4096, 2, 512, 0, true, false)    \
+  X(8197, 4096, 2, 512, 0, false, true)    \
+  X(16384, 8192, 1, 512, 0, false, false)  \
+  X(16389, 8192, 1, 512, 0, false, true)
 
 inline size_t fast_rows_smem(const FastRowsCfg &c)
 {
@@ -417,12 +536,12 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     fast_rows = rv;
     cudaError_t e = cudaSuccess;
     switch (rv) {
-#define ROWS_ATTR(ID, NR, RB, T, MB, W)                                                                       \
+#define ROWS_ATTR(ID, NR, RB, T, MB, W, F)                                                                      \
   case ID:                                                                                                    \
-    e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T, MB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+    e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T, MB, W, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                              (int) fast_rows_smem(rc));                                                       \
     if (e == cudaSuccess)                                                                                     \
-      e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T, MB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+      e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T, MB, W, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                (int) fast_rows_smem(rc));                                                     \
     break;
       ROWS_VARIANTS(ROWS_ATTR)
@@ -468,8 +587,8 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-#define ROWS_LAUNCH(ID, NR, RB, T, MB, W) \
-  case ID: k_rows_fwd_p2<NR, RB, T, MB, W><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+#define ROWS_LAUNCH(ID, NR, RB, T, MB, W, F) \
+  case ID: k_rows_fwd_p2<NR, RB, T, MB, W, F><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
     default: return 1;
@@ -487,8 +606,8 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-#define ROWS_LAUNCH(ID, NR, RB, T, MB, W) \
-  case ID: k_rows_inv_p2<NR, RB, T, MB, W><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+#define ROWS_LAUNCH(ID, NR, RB, T, MB, W, F) \
+  case ID: k_rows_inv_p2<NR, RB, T, MB, W, F><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
     default: return 1;
