@@ -158,6 +158,11 @@ template <int NR> __device__ __forceinline__ int rows256_ky(int i)
 // time: 3 (forward) and 4 (backward) of the ~10 sweeps over the tile disappear, with two block
 // barriers.  Butterflies 0 and S / 2 pair with themselves and form one unit together, so a row
 // has exactly NR / 16 units.  Arithmetic per element is that of the unfused code (bit-identical).
+// Measured at 4096 x 4096 (profiles/r1_rows_variants.txt): with one row per warp (16-byte stores
+// to 32 different lines per instruction) the forward kernel LOST 32 % (0.361 vs 0.273 ms) and the
+// backward one 4 %: half-written 32-byte sectors cost more than three shared-memory sweeps save.
+// The unit -> (row, pair) map now keeps the RB rows of a pair in adjacent lanes, i.e. the same
+// sector pattern as the unfused kernels.
 
 // unit p in [1, NR/16) -> klow in [1, NR/16): the eight lanes of a quarter warp take eight values
 // of the SECOND spectrum digit, so that both butterflies they load sit in different
@@ -213,7 +218,7 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
     __syncthreads();
 #pragma unroll 1
     for (int ui = threadIdx.x; ui < RB * HU; ui += T) {
-      const int r = ui / HU, p = ui - r * HU;
+      const int r = ui % RB, p = ui / RB;      // adjacent lanes = adjacent rows: 32-byte sectors stay whole
       const int rx = (r * AX) & 7;
       const double2 *row = sm + r * NR;
       const int klow = p == 0 ? 0 : rowsfuse_klow<NR>(p);
@@ -326,7 +331,7 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
     constexpr int S = NR / 8, HU = NR / 16;
 #pragma unroll 1
     for (int ui = threadIdx.x; ui < RB * HU; ui += T) {
-      const int r = ui / HU, p = ui - r * HU;
+      const int r = ui % RB, p = ui / RB;      // adjacent lanes = adjacent rows: 32-byte sectors stay whole
       const int rx = (r * AX) & 7;
       double2 *row = sm + r * NR;
       const int klow = p == 0 ? 0 : rowsfuse_klow<NR>(p);
