@@ -536,7 +536,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (h->fast_rows && fast_rows_cfg(h->fast_rows, frc))
     snprintf(rows, sizeof(rows), "k_rows_*_p2 half-length len %d, %d rows/CTA, %d threads, smem %zu [fast%s]",
              frc.nr, frc.rb, frc.t, fast_rows_smem(frc),
-             h->fast_rows == h->g.ny ? "" : (", variant " + std::to_string(h->fast_rows)).c_str());
+             h->fast_rows == fast_rows_default(h->g.ny) ? "" : (", variant " + std::to_string(h->fast_rows)).c_str());
   else
     snprintf(rows, sizeof(rows), "k_rows_* %s len %d%s, %d rows/CTA, %d threads, smem %zu",
              h->even ? "half-length" : "full-length", h->fft_rows.desc.n,

@@ -479,7 +479,8 @@ struct FastRowsCfg { int nr, rb, t; };
 // variant id = ny + k: k = 0 the default; experimental variants, selected with the environment
 // variable GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
 //   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise;
-//   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above).
+//   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above) in both
+//   directions;  ny = 4096: +6 fused backward, unfused forward (the default there).
 // Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
 // rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
 // three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
@@ -488,7 +489,7 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
   switch (variant) {
     case 2048: case 2053: c = {1024, 4, 128}; return true;
-    case 4096: case 4099: case 4101: c = {2048, 2, 256}; return true;
+    case 4096: case 4099: case 4101: case 4102: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
     case 8192: case 8195: case 8197: c = {4096, 2, 512}; return true;
     case 16384: case 16389: c = {8192, 1, 512}; return true;
@@ -496,19 +497,26 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
   }
 }
 
-// X(id, NR, RB, T, MB, W256, FUSE) for every instantiated row-kernel variant
-#define ROWS_VARIANTS(X)                   \
-  X(2048, 1024, 4, 128, 0, false, false)   \
-  X(2053, 1024, 4, 128, 0, false, true)    \
-  X(4096, 2048, 2, 256, 0, false, false)   \
-  X(4097, 2048, 4, 512, 0, false, false)   \
-  X(4099, 2048, 2, 256, 0, true, false)    \
-  X(4101, 2048, 2, 256, 2, false, true)    \
-  X(8192, 4096, 2, 512, 0, false, false)   \
-  X(8195, 4096, 2, 512, 0, true, false)    \
-  X(8197, 4096, 2, 512, 0, false, true)    \
-  X(16384, 8192, 1, 512, 0, false, false)  \
-  X(16389, 8192, 1, 512, 0, false, true)
+// X(id, NR, RB, T, MB, W256, FUSE_FWD, FUSE_INV) for every instantiated row-kernel variant
+#define ROWS_VARIANTS(X)                          \
+  X(2048, 1024, 4, 128, 0, false, false, false)   \
+  X(2053, 1024, 4, 128, 0, false, true, true)     \
+  X(4096, 2048, 2, 256, 0, false, false, false)   \
+  X(4097, 2048, 4, 512, 0, false, false, false)   \
+  X(4099, 2048, 2, 256, 0, true, false, false)    \
+  X(4101, 2048, 2, 256, 2, false, true, true)     \
+  X(4102, 2048, 2, 256, 2, false, false, true)    \
+  X(8192, 4096, 2, 512, 0, false, false, false)   \
+  X(8195, 4096, 2, 512, 0, true, false, false)    \
+  X(8197, 4096, 2, 512, 0, false, true, true)     \
+  X(16384, 8192, 1, 512, 0, false, false, false)  \
+  X(16389, 8192, 1, 512, 0, false, true, true)
+
+// the variant a grid gets when GFMD_B200_ROWS_VARIANT does not say otherwise: for ny = 4096 the
+// unfused forward kernel with the FUSED backward kernel (measured: rows_inv 0.263 instead of
+// 0.308 ms, rows_fwd 0.291 fused against 0.273 unfused); the other lengths are unmeasured and
+// keep the unfused pair
+inline int fast_rows_default(int ny) { return ny == 4096 ? 4102 : ny; }
 
 inline size_t fast_rows_smem(const FastRowsCfg &c)
 {
@@ -531,7 +539,7 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
   fast_cols = 0;
   if (getenv("GFMD_B200_NO_FAST")) return 0;
   FastRowsCfg rc;
-  int rv = g.ny;
+  int rv = fast_rows_default(g.ny);
   if (g.ny == 4096 && getenv("GFMD_B200_ROWS_RB4") && g.nx_loc % 4 == 0) rv = 4097;
   if (const char *e = getenv("GFMD_B200_ROWS_VARIANT")) {
     const int want = atoi(e);
@@ -541,12 +549,12 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     fast_rows = rv;
     cudaError_t e = cudaSuccess;
     switch (rv) {
-#define ROWS_ATTR(ID, NR, RB, T, MB, W, F)                                                                      \
+#define ROWS_ATTR(ID, NR, RB, T, MB, W, FF, FI)                                                                      \
   case ID:                                                                                                    \
-    e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T, MB, W, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+    e = cudaFuncSetAttribute(k_rows_fwd_p2<NR, RB, T, FF ? MB : 0, W, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                              (int) fast_rows_smem(rc));                                                       \
     if (e == cudaSuccess)                                                                                     \
-      e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T, MB, W, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+      e = cudaFuncSetAttribute(k_rows_inv_p2<NR, RB, T, FI ? MB : 0, W, FI>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                (int) fast_rows_smem(rc));                                                     \
     break;
       ROWS_VARIANTS(ROWS_ATTR)
@@ -592,8 +600,8 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-#define ROWS_LAUNCH(ID, NR, RB, T, MB, W, F) \
-  case ID: k_rows_fwd_p2<NR, RB, T, MB, W, F><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+#define ROWS_LAUNCH(ID, NR, RB, T, MB, W, FF, FI) \
+  case ID: k_rows_fwd_p2<NR, RB, T, FF ? MB : 0, W, FF><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
     default: return 1;
@@ -611,8 +619,8 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
   switch (variant) {
-#define ROWS_LAUNCH(ID, NR, RB, T, MB, W, F) \
-  case ID: k_rows_inv_p2<NR, RB, T, MB, W, F><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+#define ROWS_LAUNCH(ID, NR, RB, T, MB, W, FF, FI) \
+  case ID: k_rows_inv_p2<NR, RB, T, FI ? MB : 0, W, FI><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
     default: return 1;
