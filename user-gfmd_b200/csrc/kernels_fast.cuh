@@ -188,10 +188,63 @@ __device__ __forceinline__ double2 rows_premix(double2 yk, double2 ypartner, dou
   return make_double2(S.x - t.y, S.y + t.x);
 }
 
+// exp(-2 pi i q / 16): the frequencies of one last-pass butterfly are klow + q S with S = ny / 16,
+// so their un-mixing twiddles are exp(-2 pi i klow / ny) times these constants (FUSE == 2: one
+// table load per unit instead of sixteen scattered ones; not bit-identical to the table values,
+// the products carry one more rounding)
+__device__ __forceinline__ double2 rot16(int q)
+{
+  constexpr double c1 = 0.92387953251128673848, s1 = 0.38268343236508978178, h = 0.70710678118654752440;
+  switch (q & 7) {
+    case 0: return make_double2(1.0, 0.0);
+    case 1: return make_double2(c1, -s1);
+    case 2: return make_double2(h, -h);
+    case 3: return make_double2(s1, -c1);
+    case 4: return make_double2(0.0, -1.0);
+    case 5: return make_double2(-s1, -c1);
+    case 6: return make_double2(-h, -h);
+    default: return make_double2(-c1, -s1);
+  }
+}
+
+// twiddles of a fused unit: base values of its two butterflies (klow, klow2)
+template <int NR, int FUSE>
+struct RowsFuseTw {
+  double2 wa, wb;
+  const double2 *tw_ny;
+  int klow, klow2;
+  __device__ __forceinline__ RowsFuseTw(const double2 *__restrict__ t, int k1, int k2, bool special)
+      : tw_ny(t), klow(k1), klow2(k2)
+  {
+    if (FUSE == 2) {
+      if (special) {                                   // klow = 0, klow2 = S / 2: exp(-2 pi i / 32)
+        wa = make_double2(1.0, 0.0);
+        wb = make_double2(0.98078528040323044913, -0.19509032201612826785);
+      } else {
+        wa = __ldg(t + k1);
+        wb = cmul(rot16(1), cconj(wa));                // exp(-2 pi i (S - klow) / ny)
+      }
+    }
+  }
+  // twiddle of frequency klow + q S (which = 0) or klow2 + q S (which = 1)
+  __device__ __forceinline__ double2 get(int which, int q) const
+  {
+    constexpr int S = NR / 8;
+    if (FUSE == 2) return cmul(which ? wb : wa, rot16(q));
+    return __ldg(tw_ny + (which ? klow2 : klow) + q * S);
+  }
+  // twiddle of frequency ny / 2
+  __device__ __forceinline__ double2 nyquist() const
+  {
+    if (FUSE == 2) return make_double2(-1.0, 0.0);
+    return __ldg(tw_ny + NR);
+  }
+};
+
 // RB rows (same dof) of ny = 2 NR reals per CTA; array a = row a of the tile.
 // MB = CTAs per SM the register allocation aims at; W256 = the transposed stores move the
 // two rows of a pair with one 256-bit instruction per wavevector (RB even).
-template <int NR, int RB, int T, int MB = 0, bool W256 = false, bool FUSE = false>
+template <int NR, int RB, int T, int MB = 0, bool W256 = false, int FUSE = 0>
 __global__ void __launch_bounds__(T, MB)
 k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
@@ -213,7 +266,43 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   p2_groupA_rest_blk<NR, T, -1, RB, AX>(sm, tw, tws);
 #pragma unroll 1
   for (int idx = threadIdx.x; idx < NR / 8; idx += T) p2_groupB_first_seq<NR, -1, RB, AX>(sm, tws, idx);
-  if constexpr (FUSE) {
+  if constexpr (FUSE == 2) {
+    constexpr int S = NR / 8, HU = NR / 16;
+    __syncthreads();
+#pragma unroll 1
+    for (int ui = threadIdx.x; ui < RB * HU; ui += T) {
+      const int r = ui % RB, p = ui / RB;      // adjacent lanes = adjacent rows: 32-byte sectors stay whole
+      const int rx = (r * AX) & 7;
+      const double2 *row = sm + r * NR;
+      const int klow = p == 0 ? 0 : rowsfuse_klow<NR>(p);
+      const int klow2 = p == 0 ? S / 2 : S - klow;
+      const int b1 = p2_freq_to_pos(LOG, klow), b2 = p2_freq_to_pos(LOG, klow2);
+      double2 v1[8], v2[8];
+      p2_last_fwd_load(row, b1, swz_key(b1) ^ rx, v1);
+      p2_last_fwd_load(row, b2, swz_key(b2) ^ rx, v2);
+      const RowsFuseTw<NR, FUSE> w(tw_ny, klow, klow2, p == 0);
+      if (p == 0) {
+        // butterflies 0 and S/2 pair with themselves: k = q S <-> (8 - q) S, and S/2 + q S <-> S/2 + (7 - q) S
+        stage[stage_index(g, 0, dof, ix0 + r)] = rows_unmix(v1[0], v1[0], w.get(0, 0));
+        stage[stage_index(g, NR, dof, ix0 + r)] = rows_unmix(v1[0], v1[0], w.nyquist());
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+          stage[stage_index(g, q * S, dof, ix0 + r)] = rows_unmix(v1[q], v1[8 - q], w.get(0, q));
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          stage[stage_index(g, S / 2 + q * S, dof, ix0 + r)] = rows_unmix(v2[q], v2[7 - q], w.get(1, q));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = klow + q * S, k2 = klow2 + q * S;
+          stage[stage_index(g, k, dof, ix0 + r)] = rows_unmix(v1[q], v2[7 - q], w.get(0, q));
+          stage[stage_index(g, k2, dof, ix0 + r)] = rows_unmix(v2[q], v1[7 - q], w.get(1, q));
+        }
+      }
+    }
+    return;
+  }
+  if constexpr (FUSE == 1) {
     constexpr int S = NR / 8, HU = NR / 16;
     __syncthreads();
 #pragma unroll 1
@@ -308,7 +397,7 @@ k_rows_fwd_p2(const double *__restrict__ u, double2 *__restrict__ stage, GridDes
   }
 }
 
-template <int NR, int RB, int T, int MB = 0, bool W256 = false, bool FUSE = false>
+template <int NR, int RB, int T, int MB = 0, bool W256 = false, int FUSE = 0>
 __global__ void __launch_bounds__(T, MB)
 k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
@@ -325,7 +414,49 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
   constexpr int h = NR;
   p2_fill_tws<NR>(tws, tw);
 
-  if constexpr (FUSE) {
+  if constexpr (FUSE == 2) {
+    // transposed load of both butterflies of a unit (16 independent 16-byte loads), pre-mix in
+    // registers, first inverse butterflies, one store sweep to shared memory
+    constexpr int S = NR / 8, HU = NR / 16;
+#pragma unroll 1
+    for (int ui = threadIdx.x; ui < RB * HU; ui += T) {
+      const int r = ui % RB, p = ui / RB;      // adjacent lanes = adjacent rows: 32-byte sectors stay whole
+      const int rx = (r * AX) & 7;
+      double2 *row = sm + r * NR;
+      const int klow = p == 0 ? 0 : rowsfuse_klow<NR>(p);
+      const int klow2 = p == 0 ? S / 2 : S - klow;
+      const int b1 = p2_freq_to_pos(LOG, klow), b2 = p2_freq_to_pos(LOG, klow2);
+      double2 y1[8], y2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        y1[q] = stage[stage_index(g, klow + q * S, dof, ix0 + r)];
+        y2[q] = stage[stage_index(g, klow2 + q * S, dof, ix0 + r)];
+      }
+      const RowsFuseTw<NR, FUSE> w(tw_ny, klow, klow2, p == 0);
+      if (p == 0) {
+        const double2 yh0 = stage[stage_index(g, NR, dof, ix0 + r)];
+        double2 z[8];
+        z[0] = rows_premix(y1[0], yh0, w.get(0, 0));
+#pragma unroll
+        for (int q = 1; q < 8; ++q) z[q] = rows_premix(y1[q], y1[8 - q], w.get(0, q));
+        p2_last_inv_store(row, b1, swz_key(b1) ^ rx, z);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z[q] = rows_premix(y2[q], y2[7 - q], w.get(1, q));
+        p2_last_inv_store(row, b2, swz_key(b2) ^ rx, z);
+      } else {
+        // the pair (y1[q], y2[7-q]) yields (z1[q], z2[7-q]): in place
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double2 a = y1[q], b = y2[7 - q];
+          y1[q] = rows_premix(a, b, w.get(0, q));
+          y2[7 - q] = rows_premix(b, a, w.get(1, 7 - q));
+        }
+        p2_last_inv_store(row, b1, swz_key(b1) ^ rx, y1);
+        p2_last_inv_store(row, b2, swz_key(b2) ^ rx, y2);
+      }
+    }
+    __syncthreads();
+  } else if constexpr (FUSE == 1) {
     // transposed load of both butterflies of a unit (16 independent 16-byte loads), pre-mix in
     // registers, first inverse butterflies, one store sweep to shared memory
     constexpr int S = NR / 8, HU = NR / 16;
@@ -480,7 +611,8 @@ struct FastRowsCfg { int nr, rb, t; };
 // variable GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
 //   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise;
 //   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above) in both
-//   directions;  ny = 4096: +6 fused backward, unfused forward (the default there).
+//   directions;  ny = 4096, 8192: +6 fused backward, unfused forward (the default at 4096),
+//   +7 fused both ways with closed-form twiddles (one table load per unit; unmeasured).
 // Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
 // rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
 // three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
@@ -489,28 +621,32 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
   switch (variant) {
     case 2048: case 2053: c = {1024, 4, 128}; return true;
-    case 4096: case 4099: case 4101: case 4102: c = {2048, 2, 256}; return true;
+    case 4096: case 4099: case 4101: case 4102: case 4103: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
-    case 8192: case 8195: case 8197: c = {4096, 2, 512}; return true;
+    case 8192: case 8195: case 8197: case 8198: case 8199: c = {4096, 2, 512}; return true;
     case 16384: case 16389: c = {8192, 1, 512}; return true;
     default: return false;
   }
 }
 
-// X(id, NR, RB, T, MB, W256, FUSE_FWD, FUSE_INV) for every instantiated row-kernel variant
-#define ROWS_VARIANTS(X)                          \
-  X(2048, 1024, 4, 128, 0, false, false, false)   \
-  X(2053, 1024, 4, 128, 0, false, true, true)     \
-  X(4096, 2048, 2, 256, 0, false, false, false)   \
-  X(4097, 2048, 4, 512, 0, false, false, false)   \
-  X(4099, 2048, 2, 256, 0, true, false, false)    \
-  X(4101, 2048, 2, 256, 2, false, true, true)     \
-  X(4102, 2048, 2, 256, 2, false, false, true)    \
-  X(8192, 4096, 2, 512, 0, false, false, false)   \
-  X(8195, 4096, 2, 512, 0, true, false, false)    \
-  X(8197, 4096, 2, 512, 0, false, true, true)     \
-  X(16384, 8192, 1, 512, 0, false, false, false)  \
-  X(16389, 8192, 1, 512, 0, false, true, true)
+// X(id, NR, RB, T, MB, W256, FUSE_FWD, FUSE_INV) for every instantiated row-kernel variant;
+// FUSE: 0 unfused, 1 fused with table twiddles (bit-identical to 0), 2 fused with closed-form twiddles
+#define ROWS_VARIANTS(X)                  \
+  X(2048, 1024, 4, 128, 0, false, 0, 0)   \
+  X(2053, 1024, 4, 128, 0, false, 1, 1)   \
+  X(4096, 2048, 2, 256, 0, false, 0, 0)   \
+  X(4097, 2048, 4, 512, 0, false, 0, 0)   \
+  X(4099, 2048, 2, 256, 0, true, 0, 0)    \
+  X(4101, 2048, 2, 256, 2, false, 1, 1)   \
+  X(4102, 2048, 2, 256, 2, false, 0, 1)   \
+  X(4103, 2048, 2, 256, 2, false, 2, 2)   \
+  X(8192, 4096, 2, 512, 0, false, 0, 0)   \
+  X(8195, 4096, 2, 512, 0, true, 0, 0)    \
+  X(8197, 4096, 2, 512, 0, false, 1, 1)   \
+  X(8198, 4096, 2, 512, 0, false, 0, 1)   \
+  X(8199, 4096, 2, 512, 0, false, 2, 2)   \
+  X(16384, 8192, 1, 512, 0, false, 0, 0)  \
+  X(16389, 8192, 1, 512, 0, false, 1, 1)
 
 // the variant a grid gets when GFMD_B200_ROWS_VARIANT does not say otherwise: for ny = 4096 the
 // unfused forward kernel with the FUSED backward kernel (measured: rows_inv 0.263 instead of
