@@ -35,17 +35,29 @@ def make_layer_atoms(nx, ny, nu):
 def test_energy_conservation_two_layers():
     import torch
     import gfmd_b200
+    run_energy_conservation_two_layers(gfmd_b200, torch.device("cuda"), 100000, 1000)
+
+
+def bind_stream(s, dev):
+    """On a GPU the library's work is ordered with torch's current stream; under the CPU
+    emulation build (tests/test_emulated_kernels.py) everything is synchronous."""
+    import torch
+    if dev.type == "cuda":
+        s.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
+def run_energy_conservation_two_layers(gfmd_b200, dev, nsteps, every):
+    import torch
     g = load_golden("C3_fcc100_two_layers_10x10")
     nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
     gid, xeq = make_layer_atoms(nx, ny, d // 3)
     n = gid.shape[0]
     rng = np.random.default_rng(12472634)
     x0 = xeq + rng.uniform(-0.1, 0.1, size=(n, 3))           # displace_atoms all random 0.1 0.1 0.1
-    dev = torch.device("cuda")
     s = gfmd_b200.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
     s.set_kernel(g["phi"], g["linf"])
-    s.set_stream(torch.cuda.current_stream().cuda_stream)     # library work is ordered with torch's
+    bind_stream(s, dev)                                       # library work is ordered with torch's
     x = torch.tensor(x0, device=dev)
     dxeq = torch.tensor(xeq, device=dev)
     dgid = torch.tensor(gid, device=dev)
@@ -76,7 +88,6 @@ def test_energy_conservation_two_layers():
     force()
     etot, com = [], []
     nshifts = 0
-    nsteps, every = 100000, 1000
     for step in range(nsteps + 1):
         if step % every == 0:
             r = s.results()                                   # synchronises
@@ -93,7 +104,9 @@ def test_energy_conservation_two_layers():
     e = np.array(etot)
     de = np.max(np.abs(e - e.mean()))
     # the layer oscillates by more than half a lattice constant: the re-indexing path ran
-    assert max(abs(c) for c in com) > 0.5 and nshifts > 0
+    # (it first crosses half a lattice constant after about 500 steps)
+    if nsteps >= 1000:
+        assert max(abs(c) for c in com) > 0.5 and nshifts > 0
     assert e.mean() > 0
     assert de / e.mean() <= 1e-4, (de, e.mean())
     s.close()
@@ -169,15 +182,19 @@ def hertz_profile(r, N, E, R):
 def test_hertz_sc100_128x128():
     import torch
     import gfmd_b200
+    run_hertz_sc100_128x128(gfmd_b200, torch.device("cuda"))
+
+
+def run_hertz_sc100_128x128(gfmd_b200, dev):
+    import torch
     g = load_golden("C1_sc100_128x128")
     nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
     gid, xeq = make_layer_atoms(nx, ny, 1)
     n = gid.shape[0]
-    dev = torch.device("cuda")
     s = gfmd_b200.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
     s.set_kernel(g["phi"], g["linf"])
-    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(s, dev)
     dxeq = torch.tensor(xeq, device=dev)
     dgid = torch.tensor(gid, device=dev)
     dmask = torch.ones(n, dtype=torch.int32, device=dev)
@@ -205,6 +222,11 @@ def test_hertz_fcc111_64x37():
     (eval.py:33-34, :94-106)."""
     import torch
     import gfmd_b200
+    run_hertz_fcc111_64x37(gfmd_b200, torch.device("cuda"))
+
+
+def run_hertz_fcc111_64x37(gfmd_b200, dev):
+    import torch
     g = load_golden("C2_fcc111_64x37")
     nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
     s3 = math.sqrt(3.0)
@@ -213,11 +235,10 @@ def test_hertz_fcc111_64x37():
     xeq = np.stack([gid[:, 0] + 0.5 * gid[:, 2], (gid[:, 1] + 0.5 * gid[:, 2]) * s3,
                     np.zeros(len(gid))], axis=1)
     n = gid.shape[0]
-    dev = torch.device("cuda")
     s = gfmd_b200.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
     s.set_kernel(g["phi"], g["linf"])
-    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(s, dev)
     dxeq = torch.tensor(xeq, device=dev)
     dgid = torch.tensor(gid, device=dev)
     dmask = torch.ones(n, dtype=torch.int32, device=dev)

@@ -342,3 +342,13 @@ def test_host_pipeline_is_bit_identical(B, nx, ny, d, oracle_libs, monkeypatch):
     assert np.array_equal(out["0"][2], out["1"][2])
     assert rel_err(out["1"][0].reshape(d, nx, ny), f_ref) < TOL
     assert abs(out["1"][1] - e_ref) <= TOL * abs(e_ref)
+
+
+def test_energy_conservation_two_layers_short(B):
+    """The reference's TEST_energy_conservation_two_layers criterion (tests/test_compound.py runs
+    all 100 000 steps on the GPU) on the first 1500 velocity-Verlet steps: gather -> solver ->
+    scatter every step, lattice re-indexing included; torch CPU tensors stand in for device
+    memory.  max|E - <E>| / <E> <= 1e-4."""
+    import torch
+    import test_compound
+    test_compound.run_energy_conservation_two_layers(B, torch.device("cpu"), 1500, 100)
