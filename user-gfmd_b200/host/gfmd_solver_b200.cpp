@@ -14,6 +14,7 @@
  *                             host only, from the stiffness kernel of the last set_kernel
  */
 #include <numeric>
+#include <vector>
 #include <string.h>
 #include <stdlib.h>
 
@@ -212,72 +213,57 @@ void GFMDSolverB200::dump(char *dump_prefix, double *u)
   if (nprocs > 1)
     error->all(FLERR,"Can only dump from single processor run.");
 
-  size_t nq = (size_t) nx*ny;
-  double_complex *uq = new double_complex[nq*ndof];
-  double_complex *fq = new double_complex[nq*ndof];
-  check(gfmd_b200_spectrum_host(handle_, u, reinterpret_cast<double*>(uq), reinterpret_cast<double*>(fq)),
+  /* u~(q) and Phi(q).u~(q) in the q_buffer layout [ix*ny + iy][idof] */
+  const size_t nq = (size_t) nx*ny;
+  std::vector<double_complex> uq(nq*ndof), fq(nq*ndof);
+  check(gfmd_b200_spectrum_host(handle_, u, reinterpret_cast<double*>(&uq[0]), reinterpret_cast<double*>(&fq[0])),
         "gfmd_b200_spectrum_host");
 
-  char fn[1024];
-  FILE *fur[MAX_NDOF], *ffr[MAX_NDOF], *fui[MAX_NDOF], *ffi[MAX_NDOF];
+  /* one file per field; columns of a text row run over ix, rows over iy */
+  enum { UR, UI, FR, FI, NPER };
+  const char *per_dof[NPER] = { "u%i.real", "u%i.imag", "f%i.real", "f%i.imag" };
+  const char *sums[3] = { "uP", "fP", "e" };
+  std::vector<FILE*> out(NPER*ndof + 3);
+  char stem[64], fn[1024];
   for (int idof = 0; idof < ndof; idof++) {
-    sprintf(fn, "%s.q.u%i.real.out", dump_prefix, idof);
-    fur[idof] = fopen(fn, "w");
-    sprintf(fn, "%s.q.u%i.imag.out", dump_prefix, idof);
-    fui[idof] = fopen(fn, "w");
-    sprintf(fn, "%s.q.f%i.real.out", dump_prefix, idof);
-    ffr[idof] = fopen(fn, "w");
-    sprintf(fn, "%s.q.f%i.imag.out", dump_prefix, idof);
-    ffi[idof] = fopen(fn, "w");
+    for (int k = 0; k < NPER; k++) {
+      snprintf(stem, sizeof(stem), per_dof[k], idof);
+      snprintf(fn, sizeof(fn), "%s.q.%s.out", dump_prefix, stem);
+      out[NPER*idof + k] = fopen(fn, "w");
+    }
   }
-  sprintf(fn, "%s.q.uP.out", dump_prefix);
-  FILE *fuP = fopen(fn, "w");
-  sprintf(fn, "%s.q.fP.out", dump_prefix);
-  FILE *ffP = fopen(fn, "w");
-  sprintf(fn, "%s.q.e.out", dump_prefix);
-  FILE *fe = fopen(fn, "w");
+  for (int k = 0; k < 3; k++) {
+    snprintf(fn, sizeof(fn), "%s.q.%s.out", dump_prefix, sums[k]);
+    out[NPER*ndof + k] = fopen(fn, "w");
+  }
+  for (size_t k = 0; k < out.size(); k++) {
+    if (!out[k]) error->one(FLERR,"fix gfmd solver static/b200: cannot open q-space dump file.");
+  }
 
+  const char *fmt = " %20.10e ";
   for (int iy = 0; iy < ny; iy++) {
     for (int ix = 0; ix < nx; ix++) {
-      const double_complex *uv = uq + ((size_t) ix*ny + iy)*ndof;
-      const double_complex *fv = fq + ((size_t) ix*ny + iy)*ndof;
-      double_complex uP = 0.0, fP = 0.0, e = 0.0;
+      const double_complex *uv = &uq[((size_t) ix*ny + iy)*ndof];
+      const double_complex *fv = &fq[((size_t) ix*ny + iy)*ndof];
+      double u2 = 0.0, f2 = 0.0, uf = 0.0;
       for (int idof = 0; idof < ndof; idof++) {
-        fprintf(fur[idof], " %20.10e ", creal(uv[idof]));
-        fprintf(fui[idof], " %20.10e ", cimag(uv[idof]));
-        fprintf(ffr[idof], " %20.10e ", creal(fv[idof]));
-        fprintf(ffi[idof], " %20.10e ", cimag(fv[idof]));
-        uP += uv[idof]*conj(uv[idof]);
-        fP += fv[idof]*conj(fv[idof]);
-        e  += uv[idof]*conj(fv[idof]);
+        const double ur = creal(uv[idof]), ui = cimag(uv[idof]);
+        const double fr = creal(fv[idof]), fi = cimag(fv[idof]);
+        fprintf(out[NPER*idof + UR], fmt, ur);
+        fprintf(out[NPER*idof + UI], fmt, ui);
+        fprintf(out[NPER*idof + FR], fmt, fr);
+        fprintf(out[NPER*idof + FI], fmt, fi);
+        u2 += ur*ur + ui*ui;
+        f2 += fr*fr + fi*fi;
+        uf += ur*fr + ui*fi;          /* Re(u conj(F)) */
       }
-      fprintf(fuP, " %20.10e ", creal(uP));
-      fprintf(ffP, " %20.10e ", creal(fP));
-      fprintf(fe, " %20.10e ", creal(e));
+      fprintf(out[NPER*ndof + 0], fmt, u2);
+      fprintf(out[NPER*ndof + 1], fmt, f2);
+      fprintf(out[NPER*ndof + 2], fmt, uf);
     }
-    for (int idof = 0; idof < ndof; idof++) {
-      fputc('\n', fur[idof]);
-      fputc('\n', fui[idof]);
-      fputc('\n', ffr[idof]);
-      fputc('\n', ffi[idof]);
-    }
-    fputc('\n', fuP);
-    fputc('\n', ffP);
-    fputc('\n', fe);
+    for (size_t k = 0; k < out.size(); k++) fputc('\n', out[k]);
   }
-
-  for (int idof = 0; idof < ndof; idof++) {
-    fclose(fur[idof]);
-    fclose(fui[idof]);
-    fclose(ffr[idof]);
-    fclose(ffi[idof]);
-  }
-  fclose(fuP);
-  fclose(ffP);
-  fclose(fe);
-
-  delete [] uq;
-  delete [] fq;
+  for (size_t k = 0; k < out.size(); k++) fclose(out[k]);
 }
 
 
@@ -308,62 +294,55 @@ void GFMDSolverB200::dump_table(const char *stem, bool invert)
   }
   if (!kernel_)
     error->all(FLERR,"fix gfmd solver static/b200: dump requested before set_kernel.");
+  if (me != 0) return;
 
-  if (me == 0) {
-    FILE *freal[MAX_NDOF][MAX_NDOF], *fimag[MAX_NDOF][MAX_NDOF];
-    for (int idim = 0; idim < ndof; idim++) {
-      for (int jdim = 0; jdim < ndof; jdim++) {
-        char fn[1024];
-        sprintf(fn, "%s%i%i.real.out", stem, idim, jdim);
-        freal[idim][jdim] = fopen(fn, "w");
-        sprintf(fn, "%s%i%i.imag.out", stem, idim, jdim);
-        fimag[idim][jdim] = fopen(fn, "w");
-      }
-    }
-    char fn[1024];
-    sprintf(fn, "%str.real.out", stem);
-    FILE *ftrreal = fopen(fn, "w");
-    sprintf(fn, "%str.imag.out", stem);
-    FILE *ftrimag = fopen(fn, "w");
-
-    double_complex **phi = NULL;
-    double_complex *G = new double_complex[ndof_sq];
-    size_t n = 0, nlines = 0;
-    for (int ix = 0; ix < nx; ix++) {
-      memory->create(phi, ny, ndof_sq, "GFMDSolverB200::phi");
-      fill_phi_buffer(ndof, nx, ix, ix, ny, 0, ny-1, kernel_, phi, normalize_, error);
-      for (int iy = 0; iy < ny; iy++) {
-        memcpy(G, phi[iy], ndof_sq*sizeof(double_complex));
-        if (invert) GaussJordan(ndof, G, error);
-        for (int k = 0; k < ndof_sq; k++) {
-          fprintf(freal[k/ndof][k%ndof], " %e ", creal(G[k]));
-          fprintf(fimag[k/ndof][k%ndof], " %e ", cimag(G[k]));
-        }
-        if (++n % nx == 0) {
-          for (int idim = 0; idim < ndof; idim++) {
-            for (int jdim = 0; jdim < ndof; jdim++) {
-              fputc('\n', freal[idim][jdim]);
-              fputc('\n', fimag[idim][jdim]);
-            }
-          }
-          fputc('\n', ftrreal);
-          fputc('\n', ftrimag);
-          nlines++;
-        }
-      }
-      memory->destroy(phi);
-    }
-    delete [] G;
-
-    for (int idim = 0; idim < ndof; idim++) {
-      for (int jdim = 0; jdim < ndof; jdim++) {
-        fclose(freal[idim][jdim]);
-        fclose(fimag[idim][jdim]);
-      }
-    }
-    fclose(ftrreal);
-    fclose(ftrimag);
+  /* <stem><i><j>.real.out / .imag.out for every matrix element, plus the two trace files the
+     reference opens and only ever writes line breaks to */
+  char fn[1024];
+  std::vector<FILE*> re(ndof_sq), im(ndof_sq);
+  for (int k = 0; k < ndof_sq; k++) {
+    snprintf(fn, sizeof(fn), "%s%i%i.real.out", stem, k/ndof, k%ndof);
+    re[k] = fopen(fn, "w");
+    snprintf(fn, sizeof(fn), "%s%i%i.imag.out", stem, k/ndof, k%ndof);
+    im[k] = fopen(fn, "w");
   }
+  snprintf(fn, sizeof(fn), "%str.real.out", stem);
+  FILE *trre = fopen(fn, "w");
+  snprintf(fn, sizeof(fn), "%str.imag.out", stem);
+  FILE *trim = fopen(fn, "w");
+
+  /* storage order n = ix*ny + iy, a line break after every nx entries */
+  double_complex **phi = NULL;
+  std::vector<double_complex> G(ndof_sq);
+  size_t n = 0;
+  for (int ix = 0; ix < nx; ix++) {
+    memory->create(phi, ny, ndof_sq, "GFMDSolverB200::phi");
+    fill_phi_buffer(ndof, nx, ix, ix, ny, 0, ny-1, kernel_, phi, normalize_, error);
+    for (int iy = 0; iy < ny; iy++) {
+      memcpy(&G[0], phi[iy], ndof_sq*sizeof(double_complex));
+      if (invert) GaussJordan(ndof, &G[0], error);
+      for (int k = 0; k < ndof_sq; k++) {
+        fprintf(re[k], " %e ", creal(G[k]));
+        fprintf(im[k], " %e ", cimag(G[k]));
+      }
+      if (++n % nx == 0) {
+        for (int k = 0; k < ndof_sq; k++) {
+          fputc('\n', re[k]);
+          fputc('\n', im[k]);
+        }
+        fputc('\n', trre);
+        fputc('\n', trim);
+      }
+    }
+    memory->destroy(phi);
+  }
+
+  for (int k = 0; k < ndof_sq; k++) {
+    fclose(re[k]);
+    fclose(im[k]);
+  }
+  fclose(trre);
+  fclose(trim);
 }
 
 
