@@ -352,3 +352,87 @@ def test_energy_conservation_two_layers_short(B):
     import torch
     import test_compound
     test_compound.run_energy_conservation_two_layers(B, torch.device("cpu"), 1500, 100)
+
+
+def test_random_call_sequences(B, oracle_libs):
+    """Host logic under interleaving: several live handles of different grid sizes (generic and
+    specialised kernels), random sequences of post_force / pre_force + post_force / device step /
+    spectrum / prec_gradient / new tables (whole or column blocks in random order) / new linf /
+    pipeline toggles / close, every result checked against the oracle."""
+    import random
+    O = oracle_libs
+    rnd = random.Random(20261017)
+
+    def table(nx, ny, d, rng):
+        Dr = rng.standard_normal((nx, ny, d, d))
+        Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+        Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+        Dr[0, 0] += 4 * d * np.eye(d)                      # well-conditioned Phi + C
+        return np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+
+    shapes = [(8, 7, 6), (16, 12, 3), (5, 9, 3), (37, 8, 3), (6, 2048, 3), (2048, 2, 3), (12, 10, 9), (10, 10, 12)]
+    ops = ["new", "new", "step", "step", "step", "pre", "spec", "prec", "retable", "linf", "close", "pipe", "devstep"]
+    handles = []
+    for _ in range(400):
+        op = rnd.choice(ops)
+        if op == "new" or not handles:
+            if len(handles) > 3:
+                continue
+            nx, ny, d = rnd.choice(shapes)
+            rng = np.random.default_rng(rnd.randrange(1 << 30))
+            s = B.GFMDSolverB200()
+            s.set_grid_size(nx, ny, d)
+            h = dict(s=s, nx=nx, ny=ny, d=d, phi=table(nx, ny, d, rng), linf=rng.standard_normal(d // 3), rng=rng)
+            s.set_kernel(h["phi"], h["linf"])
+            handles.append(h)
+            continue
+        h = rnd.choice(handles)
+        s, nx, ny, d, rng = h["s"], h["nx"], h["ny"], h["d"], h["rng"]
+        u = rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+        uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+        if op in ("step", "pre", "devstep"):
+            f = np.full_like(uu, np.nan)
+            if op == "pre":
+                s.pre_force(uu, f)
+            if op == "devstep":
+                s.post_force_device(uu.copy(), f)
+                r = s.results()
+                e, u0 = r["epot"], r["u0"]
+            else:
+                e, u0 = s.post_force(uu, f), s.get_u0()
+            fr, er, u0r = O.post_force(u, h["phi"], h["linf"])
+            assert rel_err(f.reshape(d, nx, ny), fr) < TOL, (op, nx, ny, d)
+            assert abs(e - er) <= TOL * abs(er), (op, nx, ny, d)
+            assert np.abs(u0 - u0r).max() <= TOL * max(1.0, np.abs(u0r).max())
+        elif op == "spec":
+            uq, fq = s.spectrum(uu)
+            uqr, fqr = O.spectrum(u, h["phi"])
+            assert rel_err(uq, uqr) < TOL and rel_err(fq, fqr) < TOL
+        elif op == "prec" and d in (3, 6, 9, 12):
+            cavg = (2.0 * np.eye(d) + 0.1 * rng.standard_normal((d, d))) / (nx * ny)
+            quirk = rnd.random() < 0.5
+            gP = np.full_like(uu, np.nan)
+            s.prec_gradient(cavg, uu, gP, reference_quirk=quirk)
+            ref = O.prec_gradient(u, h["phi"], cavg, reference_quirk=quirk)
+            assert rel_err(gP.reshape(d, nx, ny), ref) < 10 * TOL, (nx, ny, d)
+        elif op == "retable":
+            h["phi"], h["linf"] = table(nx, ny, d, rng), rng.standard_normal(d // 3)
+            if rnd.random() < 0.5:
+                s.set_kernel(h["phi"], h["linf"])
+            else:
+                P = h["phi"].reshape(nx, ny, d, d)
+                blocks = list(range(0, s.nky, 3))
+                rnd.shuffle(blocks)
+                for k0 in blocks:
+                    s.set_kernel_columns(np.ascontiguousarray(P[:, k0:k0 + min(3, s.nky - k0)]), k0)
+                s.set_linf(h["linf"])
+        elif op == "linf":
+            h["linf"] = rng.standard_normal(d // 3)
+            s.set_linf(h["linf"])
+        elif op == "pipe":
+            s.host_pipeline(rnd.random() < 0.5)
+        elif op == "close":
+            s.close()
+            handles.remove(h)
+    for h in handles:
+        h["s"].close()
