@@ -52,10 +52,44 @@ void switch_to(int next)
   threadIdx = g_fib[g_cur].tidx;
 }
 
+// Scheduling order of the fibers of a block: g_order is a permutation of the thread indices, the
+// scheduler walks it round robin.  GFMD_EMU_SCHED = "reverse" or "random[:seed]" (default: thread
+// order) -- CUDA promises no order between barriers, so every order must give the same results;
+// running the tests under several orders exposes missing barriers.
+std::vector<int> g_order, g_pos;
+int g_sched_mode = -1;        // 0 thread order, 1 reverse, 2 random
+unsigned long long g_sched_state = 0x9E3779B97F4A7C15ull;
+
+void make_order(int n)
+{
+  if (g_sched_mode < 0) {
+    const char *e = getenv("GFMD_EMU_SCHED");
+    g_sched_mode = 0;
+    if (e && !strncmp(e, "reverse", 7)) g_sched_mode = 1;
+    if (e && !strncmp(e, "random", 6)) {
+      g_sched_mode = 2;
+      if (e[6] == ':') g_sched_state ^= strtoull(e + 7, nullptr, 10) * 0xD1342543DE82EF95ull;
+    }
+  }
+  g_order.resize(n);
+  g_pos.resize(n);
+  for (int i = 0; i < n; ++i) g_order[i] = g_sched_mode == 1 ? n - 1 - i : i;
+  if (g_sched_mode == 2)
+    for (int i = n - 1; i > 0; --i) {                      // Fisher-Yates with xorshift64*
+      g_sched_state ^= g_sched_state >> 12;
+      g_sched_state ^= g_sched_state << 25;
+      g_sched_state ^= g_sched_state >> 27;
+      const int j = (int) ((g_sched_state * 0x2545F4914F6CDD1Dull >> 33) % (unsigned) (i + 1));
+      const int t = g_order[i]; g_order[i] = g_order[j]; g_order[j] = t;
+    }
+  for (int i = 0; i < n; ++i) g_pos[g_order[i]] = i;
+}
+
 int next_live(int from)
 {
+  const int p = g_pos[from];
   for (int k = 1; k <= g_n; ++k) {
-    const int c = (from + k) % g_n;
+    const int c = g_order[(p + k) % g_n];
     if (!g_fib[c].done) return c;
   }
   return -1;
@@ -179,9 +213,10 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
           makecontext(&f.ctx, fiber_main, 0);
         }
         g_live = n;
-        g_cur = 0;
-        threadIdx = g_fib[0].tidx;
-        swapcontext(&g_main, &g_fib[0].ctx);
+        make_order(n);
+        g_cur = g_order[0];
+        threadIdx = g_fib[g_cur].tidx;
+        swapcontext(&g_main, &g_fib[g_cur].ctx);
       }
   g_dyn = nullptr;
   free(dyn);

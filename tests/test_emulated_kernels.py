@@ -436,3 +436,21 @@ def test_random_call_sequences(B, oracle_libs):
             handles.remove(h)
     for h in handles:
         h["s"].close()
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:7"])
+def test_results_do_not_depend_on_thread_order(order):
+    """CUDA promises no execution order between barriers.  The emulation runs the threads of a
+    block in thread order by default; GFMD_EMU_SCHED re-runs them in reverse / a random
+    permutation (tests/emu/emu_runtime.cpp), which turns a missing __syncthreads / __syncwarp
+    into a wrong result.  The order is fixed per process, hence the sub-process."""
+    import os
+    import subprocess
+    import sys
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    env = dict(os.environ, GFMD_EMU_SCHED=order)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "random_tables or row_kernel_variants or device_table_builder or prec_gradient"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
