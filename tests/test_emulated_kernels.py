@@ -454,3 +454,23 @@ def test_results_do_not_depend_on_thread_order(order):
                         "-k", "random_tables or row_kernel_variants or device_table_builder or prec_gradient"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nx,ny,height", [(6, 5, 3), (4, 7, 1)])
+def test_explicit_spring_network(B, nx, ny, height):
+    """Reference-independent physical anchor of the whole CUDA path (tests/spring_network.py):
+    closed-form per-q matrices -> transfer-matrix recursion on the "device" -> FFT, contraction,
+    inverse FFT, against an explicit spring network relaxed by a dense solve."""
+    import spring_network
+    from gfmd_b200 import synthetic
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, 3)
+    s.build_kernel_columns(synthetic.sc100_dynamical_matrices(nx, ny, 0, s.nky), 0, height=height)
+    s.set_linf(np.zeros(1))
+    u0 = np.random.default_rng(4).uniform(-0.1, 0.1, size=(3, nx, ny))
+    f = np.full((3, nx * ny), np.nan)
+    e = s.post_force(np.ascontiguousarray(u0.reshape(3, nx * ny)), f)
+    s.close()
+    fs = spring_network.surface_force(u0, height)
+    assert rel_err(f.reshape(3, nx, ny), fs) < 1e-12
+    assert abs(e + 0.5 * float((fs * u0).sum())) <= 1e-12 * abs(e)

@@ -185,3 +185,30 @@ def test_reference_sources_reproduce_recorded_prec_gradient(oracle_libs):
         else:
             assert rel_err(full, gP) > 1e-3
         s.close()
+
+
+# ---- FFT-free physical anchor -------------------------------------------------------------
+
+@pytest.mark.parametrize("nx,ny,height", [(6, 5, 3), (4, 7, 1), (5, 5, 0)])
+def test_explicit_spring_network_pins_sign_convention_and_table(nx, ny, height, oracle_libs):
+    """tests/spring_network.py: the explicit harmonic network behind the `sc100` kernel, relaxed
+    by a dense solve, against the reference plugin's table pushed through the oracle path.  The
+    transposed FFT sign convention must NOT fit (that is what makes this a sign KAT)."""
+    import spring_network
+    O = oracle_libs
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    k = O.RefKernel("sc100 height %d" % height)
+    phi = k.phi(nx, ny)
+    u0 = np.random.default_rng(4).uniform(-0.1, 0.1, size=(3, nx, ny))
+    f, e, _ = O.post_force(u0, phi, np.zeros(1))
+    fs = spring_network.surface_force(u0, height)
+    assert rel_err(f, fs) < 1e-13
+    assert abs(e + 0.5 * float((fs * u0).sum())) <= 1e-13 * abs(e)
+    # the same table with e^{+i q r} forward / e^{-i q r} backward transforms
+    uq = np.fft.ifft2(u0, axes=(1, 2)) * (nx * ny)
+    F = -np.einsum("qij,qj->qi", phi, np.moveaxis(uq.reshape(3, nx * ny), 0, 1))
+    f_wrong = np.fft.fft2(np.moveaxis(F, 0, 1).reshape(3, nx, ny), axes=(1, 2)).real
+    if height > 0:
+        assert rel_err(f_wrong, fs) > 1e-2
+    k.close()

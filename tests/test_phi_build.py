@@ -63,3 +63,26 @@ def test_device_built_table_equals_plugin_table(kernel, nx, ny, oracle_libs):
     assert rel_err(out[1][0], out[0][0]) < TOL
     assert abs(out[1][1] - out[0][1]) <= TOL * abs(out[0][1])
     k.close()
+
+
+@pytest.mark.parametrize("nx,ny,height", [(6, 5, 3), (16, 12, 2)])
+def test_explicit_spring_network(nx, ny, height):
+    """Reference-independent physical anchor of the whole CUDA path (tests/spring_network.py):
+    closed-form per-q matrices -> transfer-matrix recursion on the device -> FFT, contraction,
+    inverse FFT, against an explicit spring network relaxed by a dense solve.  Pins the FFT
+    sign convention, the substrate orientation and the meaning of `height` without any table
+    or FFT library."""
+    import gfmd_b200
+    import spring_network
+    from gfmd_b200 import synthetic
+    s = gfmd_b200.GFMDSolverB200()
+    s.set_grid_size(nx, ny, 3)
+    s.build_kernel_columns(synthetic.sc100_dynamical_matrices(nx, ny, 0, s.nky), 0, height=height)
+    s.set_linf(np.zeros(1))
+    u0 = np.random.default_rng(4).uniform(-0.1, 0.1, size=(3, nx, ny))
+    f = np.full((3, nx * ny), np.nan)
+    e = s.post_force(np.ascontiguousarray(u0.reshape(3, nx * ny)), f)
+    s.close()
+    fs = spring_network.surface_force(u0, height)
+    assert rel_err(f.reshape(3, nx, ny), fs) < 1e-12
+    assert abs(e + 0.5 * float((fs * u0).sum())) <= 1e-12 * abs(e)
