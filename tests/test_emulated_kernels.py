@@ -474,3 +474,20 @@ def test_explicit_spring_network(B, nx, ny, height):
     fs = spring_network.surface_force(u0, height)
     assert rel_err(f.reshape(3, nx, ny), fs) < 1e-12
     assert abs(e + 0.5 * float((fs * u0).sum())) <= 1e-12 * abs(e)
+
+
+def test_pipelined_column_kernel_variant():
+    """Experimental k_cols_fused_p2_lr<..., PIPE> (compiled with -DGFMD_EXPERIMENTAL_COLS_PIPE, which
+    the emulation build always sets; GFMD_B200_COLS_PIPE=1 selects it, read once per process):
+    the last backward pass of a column fused with pass 0 of the next one.  Same tests as the
+    default kernel, in a sub-process, under a random thread order."""
+    import os
+    import subprocess
+    import sys
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    env = dict(os.environ, GFMD_B200_COLS_PIPE="1", GFMD_EMU_SCHED="random:11")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "random_tables and (4096 or 8192 or 16384)"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -505,6 +505,41 @@ __device__ __forceinline__ void p2_pass0_inv_blk(const double2 *sm, const double
   }
 }
 
+// Last backward pass of one data set fused with pass 0 (forward) of the NEXT one, block-wide item
+// mapping: per array the thread reads its R elements of the finished set from shared memory,
+// issues the R global loads of the next set, finishes and stores the old elements while those
+// loads are in flight, then transforms the new elements into the very same shared-memory slots.
+// No barrier between the two uses (same thread, same slots).  The caller needs a __syncthreads
+// before (towards the previous backward pass) and after (towards the next forward pass).
+template <int N, int T, int A, int AX, typename Store, typename Load>
+__device__ __forceinline__ void p2_pass0_inv_fwd_blk(double2 *sm, const double2 *__restrict__ tw,
+                                                     const double2 *tws, Store store, Load load)
+{
+  constexpr int lr = P2<N>::lr(0), ls = P2<N>::ls(0), R = 1 << lr;
+#pragma unroll 1
+  for (int base = threadIdx.x; base < (N >> lr); base += T) {
+    const int sb = base ^ swz_key(base);
+    double2 w[8];
+    p2_get_tw<N, 0>(w, base, tw, tws);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      double2 v[R], nv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = sm[a * N + (p2_elem<ls>(sb, r) ^ ((a * AX) & 7))];
+#pragma unroll
+      for (int r = 0; r < R; ++r) nv[r] = load(a, base, r << ls);
+      p2_apply_tw<R, +1>(v, w);
+      Butterfly<R, +1>::run(v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) store(a, base, r << ls, v[r]);
+      Butterfly<R, -1>::run(nv);
+      p2_apply_tw<R, -1>(nv, w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[a * N + (p2_elem<ls>(sb, r) ^ ((a * AX) & 7))] = nv[r];
+    }
+  }
+}
+
 // In-place group-A pass P with the block-wide item mapping (item j of N/R: the digit of
 // pass P is spliced out of j).  Needs __syncthreads before and after.
 template <int N, int P, int T, int DIR, int A, int AX>

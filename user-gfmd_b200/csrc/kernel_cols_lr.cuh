@@ -39,7 +39,12 @@ __device__ long long g_phase_cycles[16];
 // x = x0 + xi of dof a lives in source-rank piece p = x / nx_loc at
 // ((p*D + a)*kyb + kl) * nx_loc + x % nx_loc.  The piece of a butterfly element relative to
 // the first one is known at compile time (offset >> LNXLC).
-template <int N, int T, int LP>
+// PIPE (experimental; compiled only with -DGFMD_EXPERIMENTAL_COLS_PIPE, then selected at run time
+// with GFMD_B200_COLS_PIPE=1; the CPU emulation build of tests/emu always compiles it): the last
+// backward pass of column c is fused with
+// pass 0 of column c + gridDim.x (p2_pass0_inv_fwd_blk): the loads of the next column are in
+// flight while the finished column is transformed and stored, instead of after it.
+template <int N, int T, int LP, bool PIPE = false>
 __global__ void __launch_bounds__(T, 1)
 k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, int lnxl, int ltop,
                    int kl0, int kl1,   // local ky range of this launch (chunked multi-GPU pipeline)
@@ -79,6 +84,9 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     const double *ph = phi + (size_t) vc * D * D * N;
 
     // ---- pass 0 straight from global memory (block-wide mapping: full 128-byte lines)
+#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
+    if (!PIPE || vc == (kl0 << ltop) + (int) blockIdx.x)
+#endif
     p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) { return sin[addr(a, base, off)]; });
     __syncthreads();
     PHASE_MARK(0);
@@ -187,6 +195,16 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     p2_groupA_rest_seq<N, NW, +1, D, 0>(sm, tw, tws, lane, warp);
     __syncthreads();
     PHASE_MARK(7);
+#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
+    if (PIPE && vc + (int) gridDim.x < nvc) {
+      const size_t ncol = column_base(vc + gridDim.x);
+      p2_pass0_inv_fwd_blk<N, T, D, 0>(
+          sm, tw, tws, [&](int a, int base, int off, double2 v) { sout[addr(a, base, off)] = v; },
+          [&](int a, int base, int off) {
+            return sin[ncol + a * dstride + (size_t) (off >> LNXLC) * pstride + (size_t) ((off & XMASK) + base)];
+          });
+    } else
+#endif
     p2_pass0_inv_blk<N, T, D, 0>(sm, tw, tws,
                                  [&](int a, int base, int off, double2 v) { sout[addr(a, base, off)] = v; });
     PHASE_MARK(8);

@@ -713,10 +713,19 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     const int lp = lnxl >= 12 ? 0 : 12 - lnxl;
     cudaError_t e = cudaSuccess;
     switch (lp) {
+#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
+#define LR_ATTR_PIPE(LP)                                                                                     \
+  if (e == cudaSuccess)                                                                                      \
+    e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP, true>,                                        \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fast_cols_smem(3, 4096));
+#else
+#define LR_ATTR_PIPE(LP)
+#endif
 #define LR_ATTR(LP)                                                                                          \
   case LP:                                                                                                   \
     e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int) fast_cols_smem(3, 4096));                                                 \
+    LR_ATTR_PIPE(LP)                                                                                         \
     break;
       LR_ATTR(0) LR_ATTR(1) LR_ATTR(2) LR_ATTR(3)
 #undef LR_ATTR
@@ -779,6 +788,10 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   if (variant != 4096 && (kl0 != 0 || kl1 != g.nky_loc)) return 1;
   const int nvc = (kl1 - kl0) << top;
   const int grid = nvc < num_sms ? nvc : num_sms;
+#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
+  // experimental: software-pipelined column kernel (kernel_cols_lr.cuh)
+  static const bool cols_pipe = getenv("GFMD_B200_COLS_PIPE") && atoi(getenv("GFMD_B200_COLS_PIPE")) != 0;
+#endif
   const int lnxl = ilog2_rt(g.nx_loc);
   const size_t smem = fast_cols_smem(3, variant);
   const long long top_items = (long long) g.d * (kl1 - kl0) * (g.nx >> top);
@@ -797,8 +810,19 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
       break;
     case 4096:
       switch (lnxl >= 12 ? 0 : 12 - lnxl) {
+#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
+#define LR_LAUNCH_PIPE(LP)                                                                                  \
+  if (cols_pipe) {                                                                                          \
+    k_cols_fused_p2_lr<4096, 512, LP, true><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, kl0, kl1,      \
+                                                                    tw_sub, phi, linf, epart, res);         \
+    break;                                                                                                  \
+  }
+#else
+#define LR_LAUNCH_PIPE(LP)
+#endif
 #define LR_LAUNCH(LP)                                                                                       \
   case LP:                                                                                                  \
+    LR_LAUNCH_PIPE(LP)                                                                                      \
     k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, kl0, kl1, tw_sub,    \
                                                               phi, linf, epart, res);                       \
     break;
