@@ -491,3 +491,15 @@ def test_pipelined_column_kernel_variant():
                         "-k", "random_tables and (4096 or 8192 or 16384)"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("which", ["hertz_fcc111_64x37", "hertz_sc100_128x128"])
+def test_hertz_contact_long(B, which):
+    """The two Hertz acceptance tests of tests/test_compound.py on the emulation build: thousands
+    of FIRE steps, 17 and 22 minutes on one core (both pass), so only with GFMD_EMU_LONG=1."""
+    import os
+    if not os.environ.get("GFMD_EMU_LONG"):
+        pytest.skip("long: set GFMD_EMU_LONG=1")
+    import torch
+    import test_compound
+    getattr(test_compound, "run_" + which)(B, torch.device("cpu"))
