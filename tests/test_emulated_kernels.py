@@ -138,33 +138,37 @@ def test_device_built_table_equals_plugin_table(B, kernel, nx, ny, oracle_libs):
     k.close()
 
 
-def make_atoms(nx, ny, nu, rng):
+def make_atoms(nx, ny, nu, rng, a0=1.0):
     n = nx * ny * nu
     gid = np.array([(ix, iy, iu) for ix in range(nx) for iy in range(ny) for iu in range(nu)], dtype=np.int32)
     gid = gid[rng.permutation(n)]
-    xeq = np.stack([gid[:, 0] + 0.5, gid[:, 1] + 0.5, -gid[:, 2].astype(float)], axis=1)
-    x = xeq + rng.uniform(-0.3, 0.3, size=(n, 3))
-    x[:, 0] = np.mod(x[:, 0], nx)
-    x[:, 1] = np.mod(x[:, 1], ny)
+    xeq = a0 * np.stack([gid[:, 0] + 0.5, gid[:, 1] + 0.5, -gid[:, 2].astype(float)], axis=1)
+    x = xeq + a0 * rng.uniform(-0.3, 0.3, size=(n, 3))
+    x[:, 0] = np.mod(x[:, 0], nx * a0)                    # atoms wrapped into the periodic box
+    x[:, 1] = np.mod(x[:, 1], ny * a0)
     mask = np.where(rng.random(n) < 0.95, 3, 1).astype(np.int32)
     return x, xeq, gid, mask
 
 
-@pytest.mark.parametrize("nx,ny,nu,shift", [(6, 5, 2, (0, 0)), (37, 16, 1, (3, -2))])
-def test_gather_scatter_against_oracle(B, nx, ny, nu, shift, oracle_libs):
-    """Under emulation "device" pointers are host pointers: numpy arrays stand in for them."""
+@pytest.mark.parametrize("nx,ny,nu,shift,a0", [(6, 5, 2, (0, 0), 1.0), (37, 16, 1, (3, -2), 1.0),
+                                               (9, 8, 1, (0, 0), 1.3), (7, 6, 2, (-1, 2), 0.77)])
+def test_gather_scatter_against_oracle(B, nx, ny, nu, shift, a0, oracle_libs):
+    """Under emulation "device" pointers are host pointers: numpy arrays stand in for them.
+    a0 != 1: lattice constant of the reference's TEST_Hertz_sc100_128x128_a0_1.3 (the minimum-image
+    wrap works in box lengths, not in grid units)."""
     O = oracle_libs
     rng = np.random.default_rng(11)
     d = 3 * nu
-    x, xeq, gid, mask = make_atoms(nx, ny, nu, rng)
+    x, xeq, gid, mask = make_atoms(nx, ny, nu, rng, a0)
     n = x.shape[0]
     g_ref = gid.copy()
-    u_ref, n_ref = O.gather(x, xeq, g_ref, mask, 2, nx, ny, d, float(nx), float(ny), *shift)
+    u_ref, n_ref = O.gather(x, xeq, g_ref, mask, 2, nx, ny, d, nx * a0, ny * a0, *shift)
+    assert np.abs(u_ref).max() <= 0.3 * a0 + 1e-12            # every displacement was un-wrapped
     s = B.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
     dgid = gid.copy()
     du = np.zeros((d, nx * ny))
-    s.gather(x, xeq, dgid, mask, 2, n, float(nx), float(ny), shift[0], shift[1], du)
+    s.gather(x, xeq, dgid, mask, 2, n, nx * a0, ny * a0, shift[0], shift[1], du)
     r = s.results()
     assert r["natoms_gathered"] == n_ref and r["n_out_of_range"] == 0
     assert np.array_equal(du, u_ref)
