@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "user-gfmd_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libgfmd_b200_emu.so")
+FAKE_NCCL = os.path.join(OUT, "libgfmd_fake_nccl.so")
 
 sys.path.insert(0, HERE)
 import preprocess  # noqa: E402
@@ -22,7 +23,7 @@ def sources():
 
 
 def up_to_date():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(FAKE_NCCL):
         return False
     t = os.path.getmtime(LIB)
     deps = sources() + glob.glob(os.path.join(HERE, "*.py")) + glob.glob(os.path.join(HERE, "*.cpp")) + \
@@ -54,6 +55,9 @@ def build(force=False):
            "-I", os.path.join(HERE, "include"), "-o", LIB,
            os.path.join(src, "gfmd_b200.cpp"), os.path.join(HERE, "emu_runtime.cpp"), "-ldl"]
     subprocess.check_call(cmd)
+    # in-process stand-in for NCCL (ranks = host threads), see fake_nccl.cpp
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-I", os.path.join(HERE, "include"),
+                           "-o", FAKE_NCCL, os.path.join(HERE, "fake_nccl.cpp"), "-lpthread"])
     return LIB
 
 

@@ -13,6 +13,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <mutex>
 #include <vector>
 
 uint3 threadIdx, blockIdx;
@@ -171,6 +172,10 @@ void *dyn_smem() { return g_dyn; }
 
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
+  // one launch at a time: several host threads (the ranks of an emulated multi-GPU run, see
+  // tests/test_emulated_multi_rank.py) share the one fiber scheduler
+  static std::mutex launch_mutex;
+  std::lock_guard<std::mutex> lock(launch_mutex);
   const int n = (int) (block.x * block.y * block.z);
   if (n < 1 || n > 1024 || smem_bytes > 232448) {
     fprintf(stderr, "cuda emu: block of %d threads, %zu B of dynamic shared memory\n", n, smem_bytes);
@@ -287,6 +292,16 @@ cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long l
 cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+/* "inter-process" handles inside one process: the handle carries the pointer */
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+  memset(h, 0, sizeof(*h));
+  memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned)
+{
+  memcpy(p, h.reserved, sizeof(*p));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

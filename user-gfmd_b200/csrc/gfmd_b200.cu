@@ -57,8 +57,10 @@ bool nccl_load()
 {
   NcclApi &a = nccl();
   if (a.lib) return true;
-  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  // GFMD_B200_NCCL_LIB names a specific build (path or soname) to try first
+  const char *names[] = {getenv("GFMD_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char *n : names) {
+    if (!n || !*n) continue;
     a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (a.lib) break;
   }
