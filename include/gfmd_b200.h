@@ -23,6 +23,14 @@
  *          q ordering of fill_phi_buffer (src/main/gfmd_misc.cpp:32-101)
  *   x, xeq [nall][3] double;  gid [nall][3] int (ix, iy, iu);  mask [nall] int
  *          (atom_style gfmd, src/main/atom_vec_gfmd.cpp:55-66)
+ *
+ * Environment variables, read when a handle is created (tuning and debugging only; none of
+ * them changes results beyond rounding):
+ *   GFMD_B200_NO_FAST=1          generic (any-size) kernels even where specialised ones exist
+ *   GFMD_B200_ROWS_VARIANT=<id>  a specific row-kernel variant (csrc/kernels_fast.cuh)
+ *   GFMD_B200_CHUNKS=<n>         column chunks of the multi-GPU pipeline (default 4)
+ *   GFMD_B200_HOST_PIPE=0        no per-dof upload / download pipeline on the host path
+ *   GFMD_B200_NCCL_LIB=<path>    the NCCL build to dlopen before libnccl.so.2
  */
 #ifndef GFMD_B200_H
 #define GFMD_B200_H
@@ -210,8 +218,8 @@ int gfmd_b200_pin_host_buffers(gfmd_b200_t *h, int on);
  * uploaded and f downloaded dof by dof on two copy streams, so that the row transforms of one
  * dof overlap the PCIe transfer of the next.  Same kernels, bit-identical results.
  * on = 1 / 0 sets it, on < 0 only queries; returns whether it takes effect for this handle
- * (0 / 1) -- NOT an error code -- or GFMD_B200_EINVAL (>1) for a null handle.  Environment GFMD_B200_HOST_PIPE=0 disables it
- * at creation. */
+ * (0 / 1) -- NOT an error code -- or GFMD_B200_EINVAL (>1) for a null handle.  Environment
+ * GFMD_B200_HOST_PIPE=0 disables it at creation. */
 int gfmd_b200_host_pipeline(gfmd_b200_t *h, int on);
 
 /* replay the solver step through a captured CUDA graph (single GPU) */
