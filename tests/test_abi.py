@@ -81,3 +81,13 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\".*oracle", src, flags=re.M), fn
                 assert "gfmd_oracle" not in src and "libgfmd_ref" not in src, fn
+
+
+def test_integration_doc_covers_every_entry_point():
+    """INTEGRATION.md maps every declared entry point to the reference interface it replaces."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "gfmd_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(gfmd_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(syms) >= 38
+    assert [s for s in syms if s not in doc] == []
