@@ -118,7 +118,7 @@ def run_rank(rank, world, peer_copy, comm, results):
         good = bool(err < TOL and eerr < TOL and u0err < TOL)
         ok = ok and good
         log.append("rank %d %dx%d [%s] slab vs single force err %.2e epot err %.2e u0 err %.2e %s"
-                   % (rank, nx, ny, s.describe().split("|", 1)[1][:70], err, eerr, u0err, "ok" if good else "FAIL"))
+                   % (rank, nx, ny, " |".join(part[:46] for part in s.describe().split("|")[1:]), err, eerr, u0err, "ok" if good else "FAIL"))
         s.close()
     results[rank] = (ok, log)
 

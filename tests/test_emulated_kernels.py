@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import aux_checks
+import split_checks
 from conftest import golden_cases, golden_names, load_golden, rel_err
 
 TOL = 1e-11
@@ -287,6 +288,64 @@ def test_row_kernel_variants(B, nx, ny, variant, oracle_libs, monkeypatch):
     assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
     assert abs(e - e_ref) <= TOL * abs(e_ref)
     s.close()
+
+
+
+# ndof * nx * 16 B > 227 KB and no specialised kernel: the three-phase column stage
+# (kernel_cols_split.cuh) is chosen by plan(); GFMD_B200_COLS_SPLIT=<dofs per CTA> forces it on
+# grids that would fit, which also covers dof groups with a ragged last group and Bluestein columns
+@pytest.mark.parametrize("nx,ny,d,force", [
+    (2048, 2, 12, 0), (4096, 1, 6, 0), (2000, 2, 9, 0), (1331, 3, 12, 0),      # chosen by plan()
+    (37, 16, 6, 4), (64, 37, 6, 1), (30, 42, 9, 2), (11, 13, 15, 7), (1100, 3, 3, 2), (1, 1, 3, 1),
+])
+def test_split_column_stage(B, nx, ny, d, force, oracle_libs, monkeypatch):
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    if force:
+        monkeypatch.setenv("GFMD_B200_COLS_SPLIT", str(force))
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    assert "k_cols_split_fft" in s.describe(), s.describe()
+    s.set_kernel(phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(s.get_u0() - u0_ref).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+    # a second step on the same handle (stale staging data must not matter)
+    f2 = np.full_like(uu, np.nan)
+    assert s.post_force(uu, f2) == e and np.array_equal(f, f2)
+    s.close()
+
+
+def test_split_column_stage_equals_fused_bitwise_in_forces(B, monkeypatch):
+    """Same transforms and the same per-q arithmetic: forces are bit-identical to the fused kernel's;
+    only the grouping of the energy partials differs."""
+    nx, ny, d = 48, 20, 6
+    phi, linf, u = random_case(nx, ny, d)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    out = []
+    for force in (None, "4"):
+        if force:
+            monkeypatch.setenv("GFMD_B200_COLS_SPLIT", force)
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        s.set_kernel(phi, linf)
+        f = np.full_like(uu, np.nan)
+        e = s.post_force(uu, f)
+        out.append((f, e, s.get_u0().copy(), s.describe()))
+        s.close()
+    assert "k_cols_fused" in out[0][3] and "k_cols_split_fft" in out[1][3]
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][2], out[1][2])
+    assert abs(out[0][1] - out[1][1]) <= 1e-14 * abs(out[0][1])
+
+
+def test_split_column_stage_energy_identity_and_linearity(B, monkeypatch):
+    """Small version of the full-size GPU property test (tests/test_zz_split_columns_gpu.py)."""
+    monkeypatch.setenv("GFMD_B200_COLS_SPLIT", "4")
+    split_checks.energy_identity_and_linearity(B, 96, 40, 6, expect=("k_cols_split_fft",))
 
 
 def test_sweep_of_small_grids(B, oracle_libs):

@@ -33,3 +33,13 @@ def test_chunked_pipeline_emulated():
     env = dict(os.environ, GFMD_EMU_GRIDS="4096x2048")
     r = subprocess.run([sys.executable, WORKER, "2"], env=env, capture_output=True, text=True, timeout=2400)
     assert "EMU_MGPU_PARITY_OK" in r.stdout and "4096x2048" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_slab_parity_emulated_split_columns():
+    """The three-phase column stage (kernel_cols_split.cuh, forced with GFMD_B200_COLS_SPLIT) behind
+    the exchange: columns arrive in P pieces and are transformed in place in the receive buffer."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    env = dict(os.environ, GFMD_B200_COLS_SPLIT="2", GFMD_EMU_GRIDS="8x4096,16x2048,48x36")
+    r = subprocess.run([sys.executable, WORKER, "2"], env=env, capture_output=True, text=True, timeout=1200)
+    assert "EMU_MGPU_PARITY_OK" in r.stdout and "k_cols_split_fft" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -21,6 +21,7 @@
 #include "kernels_fast.cuh"
 #include "kernel_phi_build.cuh"
 #include "kernel_cols_aux.cuh"
+#include "kernel_cols_split.cuh"
 
 using namespace gfmd;
 
@@ -262,6 +263,8 @@ struct gfmd_b200 {
   int cols_ld = 0, cols_T = 64;
   size_t cols_smem = 0;
   int fast_rows = 0, fast_cols = 0;   // specialised kernels selected
+  int cols_split_db = 0;              // > 0: column set too large for one CTA, three-phase column stage
+                                      // with this many dofs per CTA (kernel_cols_split.cuh)
   int cols_top = 0;                   // log2(nx / 4096): top-digit pass of long columns
   DevFft fft_sub;                     // twiddles of the 4096 sub-columns (long columns only)
   int num_sms = 148;
@@ -418,17 +421,30 @@ int plan(gfmd_b200 *h)
   if (cld < g.nx) cld = g.nx;
   h->cols_ld = cld;
   h->cols_smem = (size_t) g.d * cld * sizeof(double2);
-  if (h->cols_smem > kMaxSmem && !h->fast_cols)
-    return fail(h, GFMD_B200_EUNSUPPORTED,
-                "nx = %d with ndof = %d: a column set (%zu B) exceeds the %zu B of shared memory per "
-                "CTA (long columns are supported for ndof 3 and nx = 8192 or 16384 only)",
-                g.nx, g.d, h->cols_smem, kMaxSmem);
   tmin = min_threads_for(h->fft_cols.desc.core);
-  h->aux_cols_smem = (h->cols_smem <= kMaxSmem && tmin <= 512 && g.P == 1) ? h->cols_smem : 0;
   if (tmin > 512 && !h->fast_cols)
     return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d: column transform too long for one CTA", g.nx);
+  h->aux_cols_smem = (h->cols_smem <= kMaxSmem && tmin <= 512 && g.P == 1) ? h->cols_smem : 0;
+  int cols_nb = g.d;                     // transforms a column CTA holds
+  if (!h->fast_cols) {
+    // GFMD_B200_COLS_SPLIT=<n> forces the three-phase column stage with at most n dofs per CTA
+    int force_db = 0;
+    if (const char *e = getenv("GFMD_B200_COLS_SPLIT")) force_db = atoi(e);
+    if (h->cols_smem > kMaxSmem || force_db > 0) {
+      const size_t one = (size_t) cld * sizeof(double2);
+      if (one > kMaxSmem)
+        return fail(h, GFMD_B200_EUNSUPPORTED,
+                    "nx = %d: one column (%zu B) exceeds the %zu B of shared memory per CTA", g.nx, one, kMaxSmem);
+      int db = (int) (kMaxSmem / one);
+      if (db > g.d) db = g.d;
+      if (force_db > 0 && force_db < db) db = force_db;
+      h->cols_split_db = db;
+      h->cols_smem = (size_t) db * one;
+      cols_nb = db;
+    }
+  }
   if (h->fast_cols) h->cols_smem = fast_cols_smem(3, h->fast_cols);
-  t = round_up_pow2(g.d * h->fft_cols.desc.core.len / 8);
+  t = round_up_pow2(cols_nb * h->fft_cols.desc.core.len / 8);
   if (t < tmin) t = round_up_pow2(tmin);
   if (t < 64) t = 64;
   if (t > 512) t = 512;
@@ -442,7 +458,10 @@ int plan(gfmd_b200 *h)
     SET_SMEM(k_rows_fwd<false>, h->rows_smem);
     SET_SMEM(k_rows_inv<false>, h->rows_smem);
   }
-  if (!h->fast_cols) switch (g.d) {
+  if (h->cols_split_db) {
+    SET_SMEM(k_cols_split_fft<-1>, h->cols_smem);
+    SET_SMEM(k_cols_split_fft<+1>, h->cols_smem);
+  } else if (!h->fast_cols) switch (g.d) {
     case 3: SET_SMEM(k_cols_fused<3>, h->cols_smem); break;
     case 6: SET_SMEM(k_cols_fused<6>, h->cols_smem); break;
     case 9: SET_SMEM(k_cols_fused<9>, h->cols_smem); break;
@@ -549,6 +568,10 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   else if (h->fast_cols)
     snprintf(cols, sizeof(cols), "k_cols_fused_p2 len %d, 256 threads, smem %zu [fast]", h->fast_cols,
              h->cols_smem);
+  else if (h->cols_split_db)
+    snprintf(cols, sizeof(cols), "k_cols_split_fft len %d%s (%d dofs/CTA, %d threads, smem %zu) + k_cols_contract",
+             h->fft_cols.desc.n, h->fft_cols.desc.bluestein ? " (bluestein)" : "", h->cols_split_db, h->cols_T,
+             h->cols_smem);
   else
     snprintf(cols, sizeof(cols), "k_cols_fused len %d%s, %d threads, smem %zu", h->fft_cols.desc.n,
              h->fft_cols.desc.bluestein ? " (bluestein)" : "", h->cols_T, h->cols_smem);
@@ -618,6 +641,52 @@ int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
     NC(h, a.Recv(dst + r * blk, blk * 2, ncclDouble, r, h->comm, h->stream));
   }
   NC(h, a.GroupEnd());
+  return 0;
+}
+
+// Column stage of the generic kernels: `in` holds the received columns, the result goes to `out`
+// (in == out on a single rank).  Either the fused kernel (a column set fits one CTA) or the
+// three-phase form of kernel_cols_split.cuh.  Returns the number of energy partials written.
+int launch_generic_cols(gfmd_b200 *h, double2 *in, double2 *out, int *nepart)
+{
+  const GridDesc &g = h->g;
+  *nepart = g.nky_loc;
+  if (g.nky_loc <= 0) return 0;
+  if (h->cols_split_db) {
+    const int db = h->cols_split_db;
+    const int ngrp = (g.d + db - 1) / db;
+    const int ntile = (g.nx + kContractTile - 1) / kContractTile;
+    k_cols_split_fft<-1><<<g.nky_loc * ngrp, h->cols_T, h->cols_smem, h->stream>>>(in, in, g, h->fft_cols.desc,
+                                                                                  h->cols_ld, db);
+#define LAUNCH_CONTRACT(DT)                                                                   \
+  k_cols_contract<DT><<<g.nky_loc * ntile, kContractThreads, 0, h->stream>>>(in, g, h->d_phi, \
+                                                                             h->d_linf, h->d_epart, h->d_res)
+    switch (g.d) {
+      case 3: LAUNCH_CONTRACT(3); break;
+      case 6: LAUNCH_CONTRACT(6); break;
+      case 9: LAUNCH_CONTRACT(9); break;
+      case 12: LAUNCH_CONTRACT(12); break;
+      default: LAUNCH_CONTRACT(0); break;
+    }
+#undef LAUNCH_CONTRACT
+    k_cols_split_fft<+1><<<g.nky_loc * ngrp, h->cols_T, h->cols_smem, h->stream>>>(in, out, g, h->fft_cols.desc,
+                                                                                  h->cols_ld, db);
+    h->launches += 3;
+    *nepart = g.nky_loc * ntile;
+    return 0;
+  }
+#define LAUNCH_COLS(DT)                                                                          \
+  k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
+      in, out, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
+  switch (g.d) {
+    case 3: LAUNCH_COLS(3); break;
+    case 6: LAUNCH_COLS(6); break;
+    case 9: LAUNCH_COLS(9); break;
+    case 12: LAUNCH_COLS(12); break;
+    default: LAUNCH_COLS(0); break;
+  }
+#undef LAUNCH_COLS
+  h->launches++;
   return 0;
 }
 
@@ -723,26 +792,16 @@ int enqueue_solver_hostpipe(gfmd_b200 *h, const double *u_host)
     if (fast_rows_fwd(h->fast_rows, h->d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, dof, 1))
       return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
   }
+  int nepart = (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1);
   if (h->fast_cols) {
     const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
     if (fast_cols_fused(h->fast_cols, h->cols_top, A, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
                         h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches))
       return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
   } else {
-#define LAUNCH_COLS(DT)                                                                          \
-  k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
-      A, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
-    switch (g.d) {
-      case 3: LAUNCH_COLS(3); break;
-      case 6: LAUNCH_COLS(6); break;
-      case 9: LAUNCH_COLS(9); break;
-      case 12: LAUNCH_COLS(12); break;
-      default: LAUNCH_COLS(0); break;
-    }
-#undef LAUNCH_COLS
-    h->launches++;
+    launch_generic_cols(h, A, A, &nepart);
   }
-  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, nepart, h->d_res);
   h->launches++;
   for (int dof = 0; dof < g.d; ++dof) {
     if (fast_rows_inv(h->fast_rows, A, h->d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, dof, 1))
@@ -790,6 +849,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
       if (rc) return rc;
     }
     stage_mark(h, 3);
+    int nepart = (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1);
     if (g.nky_loc > 0) {
       if (h->fast_cols) {
         const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
@@ -797,21 +857,10 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
                                  h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches);
         if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
       } else {
-  #define LAUNCH_COLS(DT)                                                                          \
-    k_cols_fused<DT><<<g.nky_loc, h->cols_T, h->cols_smem, h->stream>>>(                           \
-        B, A, g, h->fft_cols.desc, h->d_phi, h->d_linf, h->d_epart, h->d_res, h->cols_ld)
-        switch (g.d) {
-          case 3: LAUNCH_COLS(3); break;
-          case 6: LAUNCH_COLS(6); break;
-          case 9: LAUNCH_COLS(9); break;
-          case 12: LAUNCH_COLS(12); break;
-          default: LAUNCH_COLS(0); break;
-        }
-  #undef LAUNCH_COLS
-        h->launches++;
+        launch_generic_cols(h, B, A, &nepart);
       }
     }
-    k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1), h->d_res);
+    k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, nepart, h->d_res);
     h->launches++;
     stage_mark(h, 4);
     if (g.P > 1) {
