@@ -1,0 +1,80 @@
+"""GPU parity of the radix-16 row kernels (user-gfmd_b200/csrc/kernels_rows_r16.cuh, experimental
+variant ids ny + 8 of GFMD_B200_ROWS_VARIANT).  Written after the round's GPU budget was spent:
+emulator-verified (tests/test_emulated_kernels.py::test_row_kernel_variants, also under other
+thread orders), first run on a B200 by the driver -- the file name sorts last so that nothing
+else hides behind it.  The variants are opt-in; the default kernels are unchanged.
+Tolerance: <= 1e-11 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def B():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import gfmd_b200
+    gfmd_b200.load_library()          # raises if the CUDA library is missing: no fallback
+    return gfmd_b200
+
+
+def random_case(nx, ny, d):
+    rng = np.random.default_rng(1000 * nx + ny + d)
+    Dr = rng.standard_normal((nx, ny, d, d)) * np.exp(-0.3 * rng.random((nx, ny, 1, 1)) * 10)
+    Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+    Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+    phi = np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+    return phi, rng.standard_normal(d // 3), rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+
+
+VARIANTS = [(64, 4096, 3, 4104), (6, 4096, 6, 4104)]
+
+
+@pytest.mark.parametrize("nx,ny,d,variant", VARIANTS)
+def test_r16_rows_against_oracle(B, nx, ny, d, variant, oracle_libs, monkeypatch):
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(variant))
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    assert "variant %d" % variant in s.describe(), s.describe()
+    s.set_kernel(phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(s.get_u0() - u0_ref).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+    s.close()
+
+
+@pytest.mark.parametrize("ny,variant", [(4096, 4104)])
+def test_r16_rows_match_default_at_full_width(B, ny, variant, monkeypatch):
+    """4096-wide surface (the bench's column length): the radix-16 rows against the default rows on
+    the same handle configuration, all three dofs, to rounding."""
+    from gfmd_b200 import synthetic
+    nx, d = 4096, 3
+    rng = np.random.default_rng(3)
+    u = rng.uniform(-1e-3, 1e-3, size=(d, nx * ny))
+    out = []
+    for v in (None, variant):
+        if v:
+            monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(v))
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        for k0 in range(0, s.nky, 128):
+            nk = min(128, s.nky - k0)
+            s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+        s.set_linf(np.array([0.25]))
+        f = np.full_like(u, np.nan)
+        e = s.post_force(u, f)
+        out.append((f, e))
+        s.close()
+    assert rel_err(out[1][0], out[0][0]) < 1e-12
+    assert abs(out[1][1] - out[0][1]) <= 1e-12 * abs(out[0][1])

@@ -603,6 +603,12 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
                                   [&](int a, int base, int off, double2 v) { dst[(size_t) a * NR + base + off] = v; });
 }
 
+}  // namespace gfmd
+
+#include "kernels_rows_r16.cuh"
+
+namespace gfmd {
+
 // ---------------------------------------------------------------- selection ---
 
 struct FastRowsCfg { int nr, rb, t; };
@@ -612,7 +618,8 @@ struct FastRowsCfg { int nr, rb, t; };
 //   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise;
 //   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above) in both
 //   directions;  ny = 4096, 8192: +6 fused backward, unfused forward (the default at 4096),
-//   +7 fused both ways with closed-form twiddles (one table load per unit; unmeasured).
+//   +7 fused both ways with closed-form twiddles (one table load per unit; unmeasured);
+//   ny = 4096: +8 radix-16 passes, four shared-memory sweeps (kernels_rows_r16.cuh; unmeasured).
 // Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
 // rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
 // three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
@@ -621,7 +628,7 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
 {
   switch (variant) {
     case 2048: case 2053: c = {1024, 4, 128}; return true;
-    case 4096: case 4099: case 4101: case 4102: case 4103: c = {2048, 2, 256}; return true;
+    case 4096: case 4099: case 4101: case 4102: case 4103: case 4104: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
     case 8192: case 8195: case 8197: case 8198: case 8199: c = {4096, 2, 512}; return true;
     case 16384: case 16389: c = {8192, 1, 512}; return true;
@@ -679,7 +686,7 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
   if (g.ny == 4096 && getenv("GFMD_B200_ROWS_RB4") && g.nx_loc % 4 == 0) rv = 4097;
   if (const char *e = getenv("GFMD_B200_ROWS_VARIANT")) {
     const int want = atoi(e);
-    if (want >= g.ny && want < g.ny + 8 && fast_rows_cfg(want, rc) && 2 * rc.nr == g.ny) rv = want;
+    if (want >= g.ny && want < g.ny + 16 && fast_rows_cfg(want, rc) && 2 * rc.nr == g.ny) rv = want;
   }
   if (fast_rows_cfg(rv, rc) && g.nx_loc % rc.rb == 0) {
     fast_rows = rv;
@@ -695,6 +702,13 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     break;
       ROWS_VARIANTS(ROWS_ATTR)
 #undef ROWS_ATTR
+      case 4104:
+        e = cudaFuncSetAttribute(k_rows_fwd_r16<2048, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) fast_rows_smem(rc));
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(k_rows_inv_r16<2048, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) fast_rows_smem(rc));
+        break;
     }
     if (e != cudaSuccess) return 1;
   }
@@ -749,6 +763,7 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   case ID: k_rows_fwd_p2<NR, RB, T, FF ? MB : 0, W, FF><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
+    case 4104: k_rows_fwd_r16<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     default: return 1;
   }
   ++*launches;
@@ -768,6 +783,7 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   case ID: k_rows_inv_p2<NR, RB, T, FI ? MB : 0, W, FI><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
+    case 4104: k_rows_inv_r16<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     default: return 1;
   }
   ++*launches;

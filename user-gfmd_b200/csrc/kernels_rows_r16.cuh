@@ -1,0 +1,262 @@
+// Row kernels with radix-16 passes (experimental variant ids ny + 8, GFMD_B200_ROWS_VARIANT):
+// the same transforms as k_rows_fwd_p2 / k_rows_inv_p2 (kernels_fast.cuh) -- a real row of
+// ny = 2 NR values as NR packed complex numbers, half-length FFT, real/complex (un)mixing,
+// transposed access to the staging buffer -- with FOUR shared-memory sweeps over the tile
+// instead of about ten, because that is what bounds the radix-8 kernels (profiles/README.md:
+// l1tex 82 %, DRAM 34 %).
+//
+//   NR = 16 * 16 * 8 (ny = 4096).  Forward, decimation in frequency, frequency
+//   k = q0 + 16 q1 + 256 q2:
+//     pass 1  thread t < NR/16:  z[t + (NR/16) j], j < 16, straight from global memory ->
+//             16-point DFT -> times w_NR^(q0 t) -> shared Y[q0][t]                       (1 write)
+//     pass 2  thread (q0, t1 < 8): Y[q0][t1 + 8 j] -> 16-point DFT -> times w_128^(q1 t1)
+//             -> shared Y[q0][q1][t1]                                                    (1 read, 1 write)
+//     pass 3  one thread runs the 8-point DFTs of BOTH groups klow = q0 + 16 q1 and 256 - klow:
+//             output q2 of one pairs with output 7 - q2 of the other (k <-> NR - k), so the
+//             real/complex un-mixing happens in registers and X goes straight to the staging
+//             buffer (1 read); groups 0 and 128 pair with themselves and form one unit.
+//   Backward: the transposed flow (decimation in time, conjugate twiddles).
+//
+// Shared memory is [row][q0][q1][t1 ^ s], s = (q1 & 3) | (row & 1) << 2: passes 1 and 2 touch 8
+// consecutive 16-byte words per quarter warp; in pass 3 the quarter warp is 4 units x 2 rows whose
+// groups differ in q1 & 3 (unit -> group map r16_klow), so every access is conflict-free.
+// Twiddles: one table load per thread and pass, powers by squaring (depth 4); the un-mixing
+// twiddles in closed form (RowsFuseTw<NR, 2>).  Results agree with the default kernels to
+// rounding (not bit for bit: other radix, other twiddle roundings).
+//
+// Reference: GFMDSolverFFT::fft_forward / fft_reverse, y part
+// (src/solvers/gfmd_solver_fft.cpp:96-147, :150-195).
+//
+// Emulator-verified (tests/test_emulated_kernels.py); NOT yet run or timed on a GPU.
+//
+// Included by kernels_fast.cuh after the helpers it shares with the FUSE variants
+// (rows_unmix, rows_premix, RowsFuseTw).
+#pragma once
+
+namespace gfmd {
+
+// 16-point DFT, in place.  Output X[q] is left at v[4 * (q & 3) + (q >> 2)] (see r16_out).
+template <int DIR> __device__ __forceinline__ void dft16(double2 *v)
+{
+  constexpr double c1 = 0.92387953251128673848, s1 = 0.38268343236508978178, h = 0.70710678118654752440;
+  // columns: j = j0 + 4 j1 -> y[j0][q1] at v[j0 + 4 q1]
+#pragma unroll
+  for (int j0 = 0; j0 < 4; ++j0) bf4<DIR>(v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12]);
+  // twiddles w16^(j0 q1), w16 = exp(DIR * 2 pi i / 16)
+  auto rot = [&](double2 a, double c, double s) {      // a * (c + i DIR s)
+    return DIR < 0 ? make_double2(fma(a.x, c, a.y * s), fma(a.y, c, -(a.x * s)))
+                   : make_double2(fma(a.x, c, -(a.y * s)), fma(a.y, c, a.x * s));
+  };
+  v[1 + 4 * 1] = rot(v[1 + 4 * 1], c1, s1);            // w^1
+  v[2 + 4 * 1] = rot(v[2 + 4 * 1], h, h);              // w^2
+  v[3 + 4 * 1] = rot(v[3 + 4 * 1], s1, c1);            // w^3
+  v[1 + 4 * 2] = rot(v[1 + 4 * 2], h, h);              // w^2
+  v[2 + 4 * 2] = mul_mi<DIR>(v[2 + 4 * 2]);            // w^4
+  v[3 + 4 * 2] = rot(v[3 + 4 * 2], -h, h);             // w^6
+  v[1 + 4 * 3] = rot(v[1 + 4 * 3], s1, c1);            // w^3
+  v[2 + 4 * 3] = rot(v[2 + 4 * 3], -h, h);             // w^6
+  v[3 + 4 * 3] = rot(v[3 + 4 * 3], -c1, -s1);          // w^9
+  // rows: X[q1 + 4 q0] = sum_j0 y[j0][q1] w4^(j0 q0), left at v[4 q1 + q0]
+#pragma unroll
+  for (int q1 = 0; q1 < 4; ++q1) bf4<DIR>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+}
+__host__ __device__ constexpr int r16_out(int q) { return 4 * (q & 3) + (q >> 2); }
+
+// v[r16_out(q)] *= w1^q (DIR < 0) or conj(w1)^q, q = 1..15; powers by squaring, depth 4
+template <int DIR, bool OUT_ORDER> __device__ __forceinline__ void r16_twiddle(double2 *v, double2 w1)
+{
+  double2 w[16];
+  w[1] = w1;
+  w[2] = csqr(w[1]);
+  w[3] = cmul(w[2], w[1]);
+  w[4] = csqr(w[2]);
+  w[5] = cmul(w[4], w[1]);
+  w[6] = csqr(w[3]);
+  w[7] = cmul(w[4], w[3]);
+  w[8] = csqr(w[4]);
+#pragma unroll
+  for (int q = 9; q < 16; ++q) w[q] = cmul(w[8], w[q - 8]);
+#pragma unroll
+  for (int q = 1; q < 16; ++q) {
+    const int i = OUT_ORDER ? r16_out(q) : q;
+    v[i] = DIR < 0 ? cmul(v[i], w[q]) : cmulc(v[i], w[q]);
+  }
+}
+
+// unit p in [0, 128) -> klow in [0, 128), 0 -> 0: the four units of a quarter warp take four
+// values of q1 & 3 (q1 = klow >> 4); their partner groups 256 - klow then do too
+__device__ __forceinline__ int r16_klow(int p) { return ((p >> 2) & 15) | ((p & 3) << 4) | ((p >> 6) << 6); }
+
+// shared-memory index of element t1 of group (q0, q1) = klow of row r (rows are NR apart)
+__device__ __forceinline__ int r16_slot(int klow, int t1, int r)
+{
+  const int q1 = klow >> 4;
+  return ((klow & 15) << 7) + (q1 << 3) + (t1 ^ ((q1 & 3) | ((r & 1) << 2)));
+}
+
+template <int NR, int RB, int T>
+__global__ void __launch_bounds__(T, 2)
+k_rows_fwd_r16(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
+               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+{
+  static_assert(NR == 2048 && RB * (NR / 16) == T, "k_rows_fwd_r16: NR = 16 * 16 * 8, one pass-1 item per thread");
+  constexpr int M1 = NR / 16;                 // 128: pass-1 threads per row = length of a pass-2 block
+  constexpr int S = NR / 8;                   // 256: frequency stride of the last pass
+  extern __shared__ double2 sm[];
+  const int nblk = g.nx_loc / RB;
+  const int dof = dof0 + blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x % nblk) * RB;
+  const int r = threadIdx.x / M1, m = threadIdx.x % M1;
+  double2 *row = sm + r * NR;
+
+  // ---- pass 1: 16 independent 16-byte loads per thread, coalesced over the threads of a row
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+    dft16<-1>(v);
+    r16_twiddle<-1, true>(v, __ldg(tw + m));
+#pragma unroll
+    for (int q0 = 0; q0 < 16; ++q0) row[q0 * M1 + m] = v[r16_out(q0)];
+  }
+  __syncthreads();
+
+  // ---- pass 2: thread (q0, t1); the 8 threads of a q0 block sit in one quarter warp
+  {
+    const int q0 = m >> 3, t1 = m & 7;
+    double2 *blk = row + q0 * M1;
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = blk[t1 + 8 * j];
+    dft16<-1>(v);
+    r16_twiddle<-1, true>(v, __ldg(tw + 16 * t1));
+    __syncwarp();                             // the swizzled slots below belong to the other threads of the block
+#pragma unroll
+    for (int q1 = 0; q1 < 16; ++q1) blk[(q1 << 3) + (t1 ^ ((q1 & 3) | ((r & 1) << 2)))] = v[r16_out(q1)];
+  }
+  __syncthreads();
+
+  // ---- pass 3 + un-mixing + transposed store: adjacent lanes = adjacent rows (whole 32-byte sectors)
+  {
+    const int rr = threadIdx.x % RB, p = threadIdx.x / RB;
+    const double2 *rw = sm + rr * NR;
+    const int klow = r16_klow(p);
+    const int klow2 = p == 0 ? S / 2 : S - klow;
+    double2 v1[8], v2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v1[e] = rw[r16_slot(klow, e, rr)];
+      v2[e] = rw[r16_slot(klow2, e, rr)];
+    }
+    Butterfly<8, -1>::run(v1);
+    Butterfly<8, -1>::run(v2);
+    const RowsFuseTw<NR, 2> w(tw_ny, klow, klow2, p == 0);
+    if (p == 0) {
+      // groups 0 and S/2 pair with themselves: k = q S <-> (8 - q) S, and S/2 + q S <-> S/2 + (7 - q) S
+      stage[stage_index(g, 0, dof, ix0 + rr)] = rows_unmix(v1[0], v1[0], w.get(0, 0));
+      stage[stage_index(g, NR, dof, ix0 + rr)] = rows_unmix(v1[0], v1[0], w.nyquist());
+#pragma unroll
+      for (int q = 1; q < 8; ++q)
+        stage[stage_index(g, q * S, dof, ix0 + rr)] = rows_unmix(v1[q], v1[8 - q], w.get(0, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        stage[stage_index(g, S / 2 + q * S, dof, ix0 + rr)] = rows_unmix(v2[q], v2[7 - q], w.get(1, q));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        stage[stage_index(g, klow + q * S, dof, ix0 + rr)] = rows_unmix(v1[q], v2[7 - q], w.get(0, q));
+        stage[stage_index(g, klow2 + q * S, dof, ix0 + rr)] = rows_unmix(v2[q], v1[7 - q], w.get(1, q));
+      }
+    }
+  }
+}
+
+template <int NR, int RB, int T>
+__global__ void __launch_bounds__(T, 2)
+k_rows_inv_r16(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
+               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+{
+  static_assert(NR == 2048 && RB * (NR / 16) == T, "k_rows_inv_r16: NR = 16 * 16 * 8, one pass-1 item per thread");
+  constexpr int M1 = NR / 16;
+  constexpr int S = NR / 8;
+  extern __shared__ double2 sm[];
+  const int nblk = g.nx_loc / RB;
+  const int dof = dof0 + blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x % nblk) * RB;
+
+  // ---- transposed load of both groups of a unit (16 independent loads), pre-mix, inverse 8-point DFTs
+  {
+    const int rr = threadIdx.x % RB, p = threadIdx.x / RB;
+    double2 *rw = sm + rr * NR;
+    const int klow = r16_klow(p);
+    const int klow2 = p == 0 ? S / 2 : S - klow;
+    double2 y1[8], y2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      y1[q] = stage[stage_index(g, klow + q * S, dof, ix0 + rr)];
+      y2[q] = stage[stage_index(g, klow2 + q * S, dof, ix0 + rr)];
+    }
+    const RowsFuseTw<NR, 2> w(tw_ny, klow, klow2, p == 0);
+    if (p == 0) {
+      const double2 yh0 = stage[stage_index(g, NR, dof, ix0 + rr)];
+      double2 z[8];
+      z[0] = rows_premix(y1[0], yh0, w.get(0, 0));
+#pragma unroll
+      for (int q = 1; q < 8; ++q) z[q] = rows_premix(y1[q], y1[8 - q], w.get(0, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y1[q] = z[q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) z[q] = rows_premix(y2[q], y2[7 - q], w.get(1, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y2[q] = z[q];
+    } else {
+      // the pair (y1[q], y2[7-q]) yields (z1[q], z2[7-q]): in place
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double2 a = y1[q], b = y2[7 - q];
+        y1[q] = rows_premix(a, b, w.get(0, q));
+        y2[7 - q] = rows_premix(b, a, w.get(1, 7 - q));
+      }
+    }
+    Butterfly<8, +1>::run(y1);
+    Butterfly<8, +1>::run(y2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      rw[r16_slot(klow, e, rr)] = y1[e];
+      rw[r16_slot(klow2, e, rr)] = y2[e];
+    }
+  }
+  __syncthreads();
+
+  const int r = threadIdx.x / M1, m = threadIdx.x % M1;
+  double2 *row = sm + r * NR;
+  // ---- pass 2 backward: conjugate twiddles, inverse 16-point DFT over q1
+  {
+    const int q0 = m >> 3, t1 = m & 7;
+    double2 *blk = row + q0 * M1;
+    double2 v[16];
+#pragma unroll
+    for (int q1 = 0; q1 < 16; ++q1) v[q1] = blk[(q1 << 3) + (t1 ^ ((q1 & 3) | ((r & 1) << 2)))];
+    r16_twiddle<+1, false>(v, __ldg(tw + 16 * t1));
+    dft16<+1>(v);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) blk[t1 + 8 * j] = v[r16_out(j)];
+  }
+  __syncthreads();
+
+  // ---- pass 1 backward, straight to global memory: packed complex = pairs of reals
+  {
+    double2 v[16];
+#pragma unroll
+    for (int q0 = 0; q0 < 16; ++q0) v[q0] = row[q0 * M1 + m];
+    r16_twiddle<+1, false>(v, __ldg(tw + m));
+    dft16<+1>(v);
+    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[m + M1 * j] = v[r16_out(j)];
+  }
+}
+
+}  // namespace gfmd
