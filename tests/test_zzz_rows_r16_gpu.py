@@ -32,7 +32,7 @@ def random_case(nx, ny, d):
     return phi, rng.standard_normal(d // 3), rng.uniform(-0.1, 0.1, size=(d, nx, ny))
 
 
-VARIANTS = [(64, 4096, 3, 4104), (6, 4096, 6, 4104)]
+VARIANTS = [(64, 4096, 3, 4104), (6, 4096, 6, 4104), (32, 8192, 3, 8200), (2, 8192, 6, 8200)]
 
 
 @pytest.mark.parametrize("nx,ny,d,variant", VARIANTS)
@@ -43,7 +43,7 @@ def test_r16_rows_against_oracle(B, nx, ny, d, variant, oracle_libs, monkeypatch
     monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(variant))
     s = B.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
-    assert "variant %d" % variant in s.describe(), s.describe()
+    assert "variant %d" % variant in s.describe() and "k_rows_*_r16" in s.describe(), s.describe()
     s.set_kernel(phi, linf)
     uu = np.ascontiguousarray(u.reshape(d, nx * ny))
     f = np.full_like(uu, np.nan)
@@ -54,12 +54,12 @@ def test_r16_rows_against_oracle(B, nx, ny, d, variant, oracle_libs, monkeypatch
     s.close()
 
 
-@pytest.mark.parametrize("ny,variant", [(4096, 4104)])
-def test_r16_rows_match_default_at_full_width(B, ny, variant, monkeypatch):
-    """4096-wide surface (the bench's column length): the radix-16 rows against the default rows on
-    the same handle configuration, all three dofs, to rounding."""
+@pytest.mark.parametrize("ny,variant", [(4096, 4104), (8192, 8200)])
+def test_r16_rows_match_default_rows(B, ny, variant, monkeypatch):
+    """Many row tiles (256 rows x 3 dofs, generic columns): radix-16 rows against the default rows
+    of the same grid, to rounding."""
     from gfmd_b200 import synthetic
-    nx, d = 4096, 3
+    nx, d = 256, 3
     rng = np.random.default_rng(3)
     u = rng.uniform(-1e-3, 1e-3, size=(d, nx * ny))
     out = []
@@ -68,8 +68,9 @@ def test_r16_rows_match_default_at_full_width(B, ny, variant, monkeypatch):
             monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(v))
         s = B.GFMDSolverB200()
         s.set_grid_size(nx, ny, d)
-        for k0 in range(0, s.nky, 128):
-            nk = min(128, s.nky - k0)
+        assert ("k_rows_*_r16" in s.describe()) == bool(v), s.describe()
+        for k0 in range(0, s.nky, 512):
+            nk = min(512, s.nky - k0)
             s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
         s.set_linf(np.array([0.25]))
         f = np.full_like(u, np.nan)

@@ -555,8 +555,8 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   char rows[160], cols[200], buf[512];
   FastRowsCfg frc;
   if (h->fast_rows && fast_rows_cfg(h->fast_rows, frc))
-    snprintf(rows, sizeof(rows), "k_rows_*_p2 half-length len %d, %d rows/CTA, %d threads, smem %zu [fast%s]",
-             frc.nr, frc.rb, frc.t, fast_rows_smem(frc),
+    snprintf(rows, sizeof(rows), "k_rows_*_%s half-length len %d, %d rows/CTA, %d threads, smem %zu [fast%s]",
+             h->fast_rows == h->g.ny + 8 ? "r16" : "p2", frc.nr, frc.rb, frc.t, fast_rows_smem(frc),
              h->fast_rows == fast_rows_default(h->g.ny) ? "" : (", variant " + std::to_string(h->fast_rows)).c_str());
   else
     snprintf(rows, sizeof(rows), "k_rows_* %s len %d%s, %d rows/CTA, %d threads, smem %zu",

@@ -259,4 +259,215 @@ k_rows_inv_r16(const double2 *__restrict__ stage, double *__restrict__ f, GridDe
   }
 }
 
+// ------------------------------------------------------------------ NR = 4096 ---
+// NR = 16 * 16 * 16 (ny = 8192).  Passes 1 and 2 as above (256 threads per row, blocks of 256,
+// groups of 16).  A last radix-16 pass with both groups of a pair in one thread would need 32
+// complex registers, so the pairs are cut by output parity instead ("half units"): of group
+// g = q0 + 16 q1 (frequencies g + 256 m, m < 16) the outputs m = e + 2 m' are the 8-point DFT of
+//   c[t] = (y[t] + (-1)^e y[t + 8]) w16^(t e),  t < 8,
+// i.e. frequencies (g + 256 e) + 512 m'.  A thread computes parity e of group klow and parity
+// 1 - e of group 256 - klow: exactly the frequencies kA + 512 m' and (512 - kA) + 512 m'' of ONE
+// fused unit of the radix-8 kernels (S = 512), so un-mixing and stores are the same code.  Groups
+// 0 and 128 pair with themselves; two threads take both parities of one of them each.  Cost: the
+// last pass reads the tile twice -- five sweeps instead of four (the radix-8 kernels: ~twelve).
+// Backward, each thread leaves d_e[t] = c'_e[t] conj(w16^(t e)) in slot t + 8 e of its groups and
+// pass 2 forms y[t1] = d_0[t1 & 7] +- d_1[t1 & 7] while loading.
+
+__device__ __forceinline__ int r16h_slot(int grp, int t, int r)
+{
+  const int q1 = grp >> 4;
+  return ((grp & 15) << 8) + (q1 << 4) + (t ^ ((q1 & 3) | ((r & 1) << 2)));
+}
+
+// thread p of a row -> (group, parity) of its two halves and the unit's base frequencies
+struct R16HalfUnit {
+  int gA, eA, gB, eB, kA, kB;
+  bool special;
+  __device__ __forceinline__ R16HalfUnit(int p)
+  {
+    const int e = p >> 7, pp = p & 127;
+    const int klow = r16_klow(pp);
+    special = p == 0;
+    if (pp == 0) {              // groups 0 (p = 0) and 128 (p = 128): both parities of one group
+      gA = gB = e ? 128 : 0;
+      eA = 0;
+    } else {
+      gA = klow;
+      gB = 256 - klow;
+      eA = e;
+    }
+    eB = 1 - eA;
+    kA = gA + 256 * eA;
+    kB = gB + 256 * eB;         // = 512 - kA, or 256 for p = 0
+  }
+};
+
+// 8 outputs of parity e of one group: loads 16 values, combines, 8-point DFT
+__device__ __forceinline__ void r16h_half_fwd(const double2 *rw, int grp, int e, int rr, double2 *c)
+{
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const double2 lo = rw[r16h_slot(grp, t, rr)], hi = rw[r16h_slot(grp, t + 8, rr)];
+    c[t] = e ? cmul(csub(lo, hi), rot16(t)) : cadd(lo, hi);
+  }
+  Butterfly<8, -1>::run(c);
+}
+
+// transposed step: inverse 8-point DFT, conjugate twiddle, slot t + 8 e of the group
+__device__ __forceinline__ void r16h_half_inv(double2 *rw, int grp, int e, int rr, double2 *z)
+{
+  Butterfly<8, +1>::run(z);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) rw[r16h_slot(grp, t + 8 * e, rr)] = e ? cmulc(z[t], rot16(t)) : z[t];
+}
+
+template <int NR, int RB, int T>
+__global__ void __launch_bounds__(T, 1)
+k_rows_fwd_r16h(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+{
+  static_assert(NR == 4096 && RB * (NR / 16) == T, "k_rows_fwd_r16h: NR = 16 * 16 * 16, one pass-1 item per thread");
+  constexpr int M1 = NR / 16;                 // 256
+  constexpr int S = NR / 8;                   // 512: frequency stride of a unit's outputs
+  extern __shared__ double2 sm[];
+  const int nblk = g.nx_loc / RB;
+  const int dof = dof0 + blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x % nblk) * RB;
+  const int r = threadIdx.x / M1, m = threadIdx.x % M1;
+  double2 *row = sm + r * NR;
+
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+    dft16<-1>(v);
+    r16_twiddle<-1, true>(v, __ldg(tw + m));
+#pragma unroll
+    for (int q0 = 0; q0 < 16; ++q0) row[q0 * M1 + m] = v[r16_out(q0)];
+  }
+  __syncthreads();
+
+  {
+    const int q0 = m >> 4, t1 = m & 15;      // the 16 threads of a q0 block sit in one warp
+    double2 *blk = row + q0 * M1;
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = blk[t1 + 16 * j];
+    dft16<-1>(v);
+    r16_twiddle<-1, true>(v, __ldg(tw + 16 * t1));
+    __syncwarp();
+#pragma unroll
+    for (int q1 = 0; q1 < 16; ++q1) blk[(q1 << 4) + (t1 ^ ((q1 & 3) | ((r & 1) << 2)))] = v[r16_out(q1)];
+  }
+  __syncthreads();
+
+  {
+    const int rr = threadIdx.x % RB;
+    const R16HalfUnit hu(threadIdx.x / RB);
+    const double2 *rw = sm + rr * NR;
+    double2 v1[8], v2[8];
+    r16h_half_fwd(rw, hu.gA, hu.eA, rr, v1);
+    r16h_half_fwd(rw, hu.gB, hu.eB, rr, v2);
+    const RowsFuseTw<NR, 2> w(tw_ny, hu.kA, hu.kB, hu.special);
+    if (hu.special) {
+      stage[stage_index(g, 0, dof, ix0 + rr)] = rows_unmix(v1[0], v1[0], w.get(0, 0));
+      stage[stage_index(g, NR, dof, ix0 + rr)] = rows_unmix(v1[0], v1[0], w.nyquist());
+#pragma unroll
+      for (int q = 1; q < 8; ++q)
+        stage[stage_index(g, q * S, dof, ix0 + rr)] = rows_unmix(v1[q], v1[8 - q], w.get(0, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        stage[stage_index(g, S / 2 + q * S, dof, ix0 + rr)] = rows_unmix(v2[q], v2[7 - q], w.get(1, q));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        stage[stage_index(g, hu.kA + q * S, dof, ix0 + rr)] = rows_unmix(v1[q], v2[7 - q], w.get(0, q));
+        stage[stage_index(g, hu.kB + q * S, dof, ix0 + rr)] = rows_unmix(v2[q], v1[7 - q], w.get(1, q));
+      }
+    }
+  }
+}
+
+template <int NR, int RB, int T>
+__global__ void __launch_bounds__(T, 1)
+k_rows_inv_r16h(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+{
+  static_assert(NR == 4096 && RB * (NR / 16) == T, "k_rows_inv_r16h: NR = 16 * 16 * 16, one pass-1 item per thread");
+  constexpr int M1 = NR / 16;
+  constexpr int S = NR / 8;
+  extern __shared__ double2 sm[];
+  const int nblk = g.nx_loc / RB;
+  const int dof = dof0 + blockIdx.x / nblk;
+  const int ix0 = (blockIdx.x % nblk) * RB;
+
+  {
+    const int rr = threadIdx.x % RB;
+    const R16HalfUnit hu(threadIdx.x / RB);
+    double2 *rw = sm + rr * NR;
+    double2 y1[8], y2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      y1[q] = stage[stage_index(g, hu.kA + q * S, dof, ix0 + rr)];
+      y2[q] = stage[stage_index(g, hu.kB + q * S, dof, ix0 + rr)];
+    }
+    const RowsFuseTw<NR, 2> w(tw_ny, hu.kA, hu.kB, hu.special);
+    if (hu.special) {
+      const double2 yh0 = stage[stage_index(g, NR, dof, ix0 + rr)];
+      double2 z[8];
+      z[0] = rows_premix(y1[0], yh0, w.get(0, 0));
+#pragma unroll
+      for (int q = 1; q < 8; ++q) z[q] = rows_premix(y1[q], y1[8 - q], w.get(0, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y1[q] = z[q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) z[q] = rows_premix(y2[q], y2[7 - q], w.get(1, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y2[q] = z[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double2 a = y1[q], b = y2[7 - q];
+        y1[q] = rows_premix(a, b, w.get(0, q));
+        y2[7 - q] = rows_premix(b, a, w.get(1, 7 - q));
+      }
+    }
+    r16h_half_inv(rw, hu.gA, hu.eA, rr, y1);
+    r16h_half_inv(rw, hu.gB, hu.eB, rr, y2);
+  }
+  __syncthreads();
+
+  const int r = threadIdx.x / M1, m = threadIdx.x % M1;
+  double2 *row = sm + r * NR;
+  {
+    const int q0 = m >> 4, t1 = m & 15;
+    double2 *blk = row + q0 * M1;
+    double2 v[16];
+#pragma unroll
+    for (int q1 = 0; q1 < 16; ++q1) {
+      const int sl = (q1 << 4) + ((t1 & 7) ^ ((q1 & 3) | ((r & 1) << 2)));
+      const double2 d0 = blk[sl], d1 = blk[sl + 8];
+      v[q1] = (t1 & 8) ? csub(d0, d1) : cadd(d0, d1);
+    }
+    r16_twiddle<+1, false>(v, __ldg(tw + 16 * t1));
+    dft16<+1>(v);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) blk[t1 + 16 * j] = v[r16_out(j)];
+  }
+  __syncthreads();
+
+  {
+    double2 v[16];
+#pragma unroll
+    for (int q0 = 0; q0 < 16; ++q0) v[q0] = row[q0 * M1 + m];
+    r16_twiddle<+1, false>(v, __ldg(tw + m));
+    dft16<+1>(v);
+    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[m + M1 * j] = v[r16_out(j)];
+  }
+}
+
 }  // namespace gfmd
