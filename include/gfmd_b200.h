@@ -125,8 +125,9 @@ int gfmd_b200_set_linf(gfmd_b200_t *h, const double *linf);
  * :493-548) on the GPU.  uuv holds, for kx in [0,nx) and ky in [ky_first, ky_first+nky), the three
  * matrices StiffnessKernel::get_dynamical_matrices returns (U0, U, V; each ndof*ndof complex128,
  * row-major): index (((ix*nky + j)*3 + m)*ndof*ndof + i*ndof + jdof).  height as in the kernel
- * arguments (`height N`): N-1 iterations, 0 means Phi = U0; negative (iterate to convergence)
- * is not supported.  normalise != 0 applies the 1/(nx*ny) of fill_phi_buffer.  ndof 3, 6, 9, 12. */
+ * arguments (`height N`): N-1 iterations, 0 means Phi = U0; negative: iterate to the reference's
+ * 1e-8 convergence, at most 100000 times -- a wavevector that does not converge fails the call with
+ * GFMD_B200_EPHI, where the reference aborts ("Out of iterations ...").  normalise != 0 applies the 1/(nx*ny) of fill_phi_buffer.  ndof 3, 6, 9, 12. */
 int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv_ri, int ky_first, int nky, int height,
                                 int normalise);
 

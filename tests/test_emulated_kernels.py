@@ -114,6 +114,8 @@ def test_device_table_builder(B):
 @pytest.mark.parametrize("kernel,nx,ny", [
     ("ft fcc111 1 1.0 pair-potential 1 1.0 height 16", 8, 7),
     ("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height 7", 2048, 2),     # specialised table layout
+    ("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height -1", 6, 5),      # iterate to convergence
+    ("ft fcc111 1 1.0 pair-potential 1 1.0 height -1", 4, 3),
 ])
 def test_device_built_table_equals_plugin_table(B, kernel, nx, ny, oracle_libs):
     O = oracle_libs

@@ -1386,9 +1386,6 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
   if (nky < 0 || ky_first < g.ky0 || ky_first + nky > g.ky0 + g.nky_loc)
     return fail(h, GFMD_B200_EINVAL, "build_phi_columns: ky range [%d,%d) outside this handle's [%d,%d)",
                 ky_first, ky_first + nky, g.ky0, g.ky0 + g.nky_loc);
-  if (height < 0)
-    return fail(h, GFMD_B200_EUNSUPPORTED, "build_phi_columns: height < 0 (iterate to convergence) is not "
-                "available on the device; use the host plugin table (gfmd_b200_set_phi_columns)");
   if (nky == 0) return 0;
   int rc = set_device(h);
   if (rc) return rc;
@@ -1397,8 +1394,11 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
   const size_t n = (size_t) nx * nky * 3 * dsq;
   double2 *d_uuv = nullptr;
   CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMalloc((void **) &d_uuv, n * sizeof(double2)));
+  CU(h, cudaMalloc((void **) &d_uuv, n * sizeof(double2) + sizeof(int)));
+  int *d_flag = reinterpret_cast<int *>(d_uuv + n);        // "out of iterations" flag (height < 0)
+  int flag = 0;
   cudaError_t e = h2d_blocking(d_uuv, uuv, n * sizeof(double2));
+  if (e == cudaSuccess) e = h2d_blocking(d_flag, &flag, sizeof(int));
   if (e == cudaSuccess) {
     const double scale = normalise ? 1.0 / ((double) nx * (double) g.ny) : 1.0;
     double *dst = h->d_phi + (size_t) (ky_first - g.ky0) * dsq * nx;
@@ -1406,19 +1406,23 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
     const int grid = (int) ((nq + 63) / 64);
     const int lognx = ilog2_rt(nx);
     switch (d) {
-      case 3: k_build_phi<3><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
-      case 6: k_build_phi<6><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
-      case 9: k_build_phi<9><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
-      case 12: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst); break;
+      case 3: k_build_phi<3><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
+      case 6: k_build_phi<6><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
+      case 9: k_build_phi<9><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
+      case 12: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
       default:
         cudaFree(d_uuv);
         return fail(h, GFMD_B200_EUNSUPPORTED, "build_phi_columns: ndof %d (3, 6, 9, 12 supported)", d);
     }
     h->launches++;
     e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
   }
   cudaFree(d_uuv);
   CU(h, e);
+  if (flag)      // the reference aborts here (iterate_Gnn, surface_stiffness.cpp:541-543)
+    return fail(h, GFMD_B200_EPHI, "build_phi_columns: out of iterations while evaluating the continued fraction "
+                "(height < 0, 100000 iterations, tolerance 1e-8)");
   for (int k = 0; k < nky; ++k) h->phi_cols_set[ky_first - g.ky0 + k] = 1;
   bool all = true;
   for (char c : h->phi_cols_set) all = all && c;

@@ -11,6 +11,11 @@
 // Hermitian-packed half-spectrum planes the column kernels stream.  The linear solves use
 // Gaussian elimination with partial pivoting (the reference inverts with full-pivot
 // Gauss-Jordan; the recursion is a contraction, so results agree to rounding).
+// height < 0 (semi-infinite substrate): iterate until sum |VT - VT_prev|^2 <= (1e-8)^2, at most
+// 100000 times (surface_stiffness.cpp:849-851, :514-539); a wavevector that runs out of iterations
+// raises *not_converged, which the host turns into the reference's "Out of iterations while
+// evaluating the continued fraction" error.  Near q = 0 the recursion converges like 1/n, so a few
+// threads run ~1e4 iterations while the rest of the grid is long done -- init-time cost only.
 #pragma once
 
 #include "fft_pow2.cuh"
@@ -60,7 +65,7 @@ __device__ __forceinline__ void csolve(double2 *M, double2 *B)
 template <int D>
 __global__ void __launch_bounds__(64)
 k_build_phi(const double2 *__restrict__ uuv, int nx, int nky, int height, double scale, int fast, int top,
-            int lognx, double *__restrict__ phi_cols)
+            int lognx, double *__restrict__ phi_cols, int *not_converged)
 {
   const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long) nx * nky) return;
@@ -75,12 +80,17 @@ k_build_phi(const double2 *__restrict__ uuv, int nx, int nky, int height, double
     for (int j = 0; j < D; ++j) Vd[i * D + j] = make_double2(-V[j * D + i].x, V[j * D + i].y);
 
   if (height != 0) {
-    for (int it = 0; it < (height > 0 ? height : 1); ++it) {
+    const int maxit = height > 0 ? height : 100001;      // 1 initial step + up to 100000 iterations
+    const double eps2 = 1e-8 * 1e-8;
+    double dnorm = 1.0;
+    int it = 0;
+    for (; it < maxit && (height > 0 || it == 0 || dnorm > eps2); ++it) {
       for (int i = 0; i < D * D; ++i) {
         M[i] = it == 0 ? U[i] : make_double2(U[i].x + VT[i].x, U[i].y + VT[i].y);
         Y[i] = Vd[i];
       }
       csolve<D>(M, Y);
+      if (it > 0) dnorm = 0.0;       // the step after the initial one always runs (iterate_Gnn starts at 1.0)
       for (int i = 0; i < D; ++i)
         for (int j = 0; j < D; ++j) {
           double2 acc = make_double2(0.0, 0.0);
@@ -89,9 +99,15 @@ k_build_phi(const double2 *__restrict__ uuv, int nx, int nky, int height, double
             acc.x += t.x;
             acc.y += t.y;
           }
-          VT[i * D + j] = acc;
+          if (it > 0) {
+            const double dx = acc.x - VT[i * D + j].x, dy = acc.y - VT[i * D + j].y;
+            dnorm += dx * dx + dy * dy;
+          }
+          M[i * D + j] = acc;        // M is free again: VT is still needed for the differences
         }
+      for (int i = 0; i < D * D; ++i) VT[i] = M[i];
     }
+    if (height < 0 && dnorm > eps2 && not_converged) *not_converged = 1;   // every writer stores 1
   }
   // Phi = U0 (+ VT), Hermitian part, scaled, packed
   size_t off, cstride;
