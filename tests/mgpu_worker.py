@@ -115,7 +115,7 @@ def main():
         ok = ok and good
         if rank == 0 or not good:
             print("rank %d %dx%d [%s] slab vs single force err %.2e epot err %.2e u0 err %.2e %s"
-                  % (rank, nx, ny, s.describe().split("|", 1)[1][:60], err, eerr, u0err,
+                  % (rank, nx, ny, " |".join(part[:46] for part in s.describe().split("|")[1:]), err, eerr, u0err,
                      "ok" if good else "FAIL"), flush=True)
         s.close()
         one.close()

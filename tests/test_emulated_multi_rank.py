@@ -43,3 +43,17 @@ def test_slab_parity_emulated_split_columns():
     env = dict(os.environ, GFMD_B200_COLS_SPLIT="2", GFMD_EMU_GRIDS="8x4096,16x2048,48x36")
     r = subprocess.run([sys.executable, WORKER, "2"], env=env, capture_output=True, text=True, timeout=1200)
     assert "EMU_MGPU_PARITY_OK" in r.stdout and "k_cols_split_fft" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_in_kernel_peer_stores_emulated(nranks):
+    """GFMD_B200_PEER_STORE=1: the last kernel of the column stage (the fused column kernel, or the
+    backward top-digit pass of long columns) stores each result piece straight into its owner's
+    return buffer; no return pushes.  nx = 4096 / 8192 / 16384 cover both kernels and 1-4 pieces
+    per sub-column; 4096 x 32 on two ranks also takes the chunked pipeline."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    env = dict(os.environ, GFMD_B200_PEER_STORE="1", GFMD_EMU_GRIDS="4096x8,4096x32,8192x8,16384x4")
+    r = subprocess.run([sys.executable, WORKER, str(nranks)], env=env, capture_output=True, text=True, timeout=1800)
+    assert "EMU_MGPU_PARITY_OK" in r.stdout and "in-kernel peer stores" in r.stdout, \
+        r.stdout[-3000:] + r.stderr[-3000:]

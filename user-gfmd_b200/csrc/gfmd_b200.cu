@@ -242,6 +242,8 @@ struct gfmd_b200 {
   // peer-copy exchange over CUDA IPC (gfmd_b200_ipc_export / _import)
   static constexpr int kMaxRanks = 16;
   bool ipc_on = false;
+  bool peer_store = false;                    // GFMD_B200_PEER_STORE=1: the column stage stores its result pieces
+                                              // straight into the peers' return buffers (no return pushes)
   double2 *peer_recv[2][kMaxRanks] = {};      // peers' receive buffers (forward, return), mapped here
   cudaStream_t copy_stream[kMaxRanks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxRanks] = {};
@@ -705,6 +707,9 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
   const size_t pitch = dblk * sizeof(double2);
   const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
   const int nc = h->nchunks, ck = h->chunk_kl;
+  PeerOut po{};
+  if (h->peer_store)
+    for (int r = 0; r < g.P; ++r) po.p[r] = (r == g.rank ? B2 : h->peer_recv[1][r]) + g.rank * blk;
 
   stage_mark(h, 1);
   for (int dof = 0; dof < g.d; ++dof) {
@@ -740,8 +745,10 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
     for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[c][(g.rank + k) % g.P], 0));
     NC(h, a.AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
     int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
-                             h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, k0, k1);
+                             h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, k0, k1,
+                             h->peer_store ? &po : nullptr);
     if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+    if (h->peer_store) continue;                 // the kernel has stored into the peers' buffers itself
     CU(h, cudaEventRecord(h->ev_k2[c], h->stream));
     for (int k = 1; k < g.P; ++k) {
       const int r = (g.rank + k) % g.P;
@@ -754,9 +761,11 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
   k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc << h->cols_top, h->d_res);
   h->launches++;
   stage_mark(h, 4);
-  CU(h, cudaMemcpyAsync(B2 + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
-                        h->stream));
-  for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[(g.rank + k) % g.P], 0));
+  if (!h->peer_store) {
+    CU(h, cudaMemcpyAsync(B2 + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
+                          h->stream));
+    for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[(g.rank + k) % g.P], 0));
+  }
   // u0 all-reduce (gfmd_solver_static.cpp:176) doubles as the barrier of the return pushes
   NC(h, a.AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm, h->stream));
   return 0;
@@ -850,11 +859,19 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
     }
     stage_mark(h, 3);
     int nepart = (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1);
+    // GFMD_B200_PEER_STORE: the column stage stores its result pieces straight into the owners' return buffers
+    const bool peer_store = g.P > 1 && h->ipc_on && h->peer_store && h->fast_cols == 4096;
+    PeerOut po{};
+    if (peer_store) {
+      const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;
+      for (int r = 0; r < g.P; ++r) po.p[r] = (r == g.rank ? B2 : h->peer_recv[1][r]) + g.rank * blk;
+    }
     if (g.nky_loc > 0) {
       if (h->fast_cols) {
         const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
         int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
-                                 h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches);
+                                 h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, 0, -1,
+                                 peer_store ? &po : nullptr);
         if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
       } else {
         launch_generic_cols(h, B, A, &nepart);
@@ -864,8 +881,10 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
     h->launches++;
     stage_mark(h, 4);
     if (g.P > 1) {
-      int rc = exchange(h, A, B2, 1);
-      if (rc) return rc;
+      if (!peer_store) {
+        int rc = exchange(h, A, B2, 1);
+        if (rc) return rc;
+      }
       NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
                              h->stream));
     }
@@ -1208,6 +1227,9 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     }
   }
   h->ipc_on = true;
+  if (const char *e = getenv("GFMD_B200_PEER_STORE")) h->peer_store = atoi(e) != 0;
+  if (h->peer_store && h->fast_cols == 4096 && h->desc.find("return: ") == std::string::npos)
+    h->desc += " | return: in-kernel peer stores";
   return 0;
 }
 

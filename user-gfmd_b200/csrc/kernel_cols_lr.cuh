@@ -35,6 +35,15 @@ __device__ long long g_phase_cycles[16];
 #define PHASE_MARK(i)
 #endif
 
+// Where the result pieces of a column go when the kernel stores them straight into the peers'
+// receive buffers over NVLink (PEER variants): p[r] = rank r's return buffer + this rank's
+// block offset (own rank: the local return buffer), so that piece r of local column kl, dof a,
+// lives at p[r][(a * kyb + kl) * nx_loc + x % nx_loc] -- the layout the copy-engine pushes
+// produce, without the staging write, the copy and its wait.
+struct PeerOut {
+  double2 *p[16];
+};
+
 // LP = log2(pieces per 4096-element sub-column) = max(0, 12 - log2(nx_loc)): element
 // x = x0 + xi of dof a lives in source-rank piece p = x / nx_loc at
 // ((p*D + a)*kyb + kl) * nx_loc + x % nx_loc.  The piece of a butterfly element relative to
@@ -44,13 +53,18 @@ __device__ long long g_phase_cycles[16];
 // backward pass of column c is fused with
 // pass 0 of column c + gridDim.x (p2_pass0_inv_fwd_blk): the loads of the next column are in
 // flight while the finished column is transformed and stored, instead of after it.
-template <int N, int T, int LP, bool PIPE = false>
+// PEER (experimental, GFMD_B200_PEER_STORE=1, slab mode with peer mappings, ltop == 0): the last
+// backward pass stores each piece straight into its owner's return buffer (`outp`) -- full
+// 128-byte lines over NVLink -- instead of the local staging buffer.
+template <int N, int T, int LP, bool PIPE = false, bool PEER = false>
 __global__ void __launch_bounds__(T, 1)
 k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, int lnxl, int ltop,
                    int kl0, int kl1,   // local ky range of this launch (chunked multi-GPU pipeline)
                    const double2 *__restrict__ tw, const double *__restrict__ phi,
-                   const double *__restrict__ linf, double *__restrict__ epart, StepResults *res)
+                   const double *__restrict__ linf, double *__restrict__ epart, StepResults *res,
+                   PeerOut outp = PeerOut())
 {
+  static_assert(!(PIPE && PEER), "the pipelined variant has no peer-store form");
   constexpr int D = 3;
   constexpr int NW = T / 32;
   constexpr int LNXLC = P2<N>::LOG - LP;                      // min(log2 N, lnxl)
@@ -205,6 +219,13 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
           });
     } else
 #endif
+    if constexpr (PEER) {
+      // ltop == 0: the sub-column is the column, piece = off >> LNXLC is a compile-time constant
+      const size_t rel0 = ((size_t) (vc >> ltop)) << lnxl;
+      p2_pass0_inv_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off, double2 v) {
+        outp.p[off >> LNXLC][rel0 + a * dstride + (size_t) ((off & XMASK) + base)] = v;
+      });
+    } else
     p2_pass0_inv_blk<N, T, D, 0>(sm, tw, tws,
                                  [&](int a, int base, int off, double2 v) { sout[addr(a, base, off)] = v; });
     PHASE_MARK(8);
@@ -214,11 +235,14 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 
 // Top-digit pass of a long column transform, in place in the staging buffer.
 // One thread per (dof, kl, n), n < S = nx >> LR; elements x = n + r*S, r < R = 2^LR.
-template <int LR, int DIR>
+// PEER (DIR = +1 only): the results go to the pieces' owners (`outp`, see PeerOut) instead of back
+// into `stage`.
+template <int LR, int DIR, bool PEER = false>
 __global__ void __launch_bounds__(256)
 k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx, int kl0,
-                int kl1)
+                int kl1, PeerOut outp = PeerOut())
 {
+  static_assert(!PEER || DIR > 0, "peer stores belong to the backward top pass");
   constexpr int R = 1 << LR;
   const int S = g.nx >> LR;
   const int xmask = (1 << lnxl) - 1;
@@ -245,8 +269,17 @@ k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2
 #pragma unroll
       for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw_nx + (size_t) q * n));
     }
+    if constexpr (PEER) {
+      const size_t rel = ((((size_t) dof) * g.kyb + kl) << lnxl);
 #pragma unroll
-    for (int r = 0; r < R; ++r) stage[a[r]] = v[r];
+      for (int r = 0; r < R; ++r) {
+        const int x = n + r * S;
+        outp.p[x >> lnxl][rel + (size_t) (x & xmask)] = v[r];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) stage[a[r]] = v[r];
+    }
   }
 }
 

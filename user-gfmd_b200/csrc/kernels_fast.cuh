@@ -747,6 +747,9 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
   case LP:                                                                                                   \
     e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int) fast_cols_smem(3, 4096));                                                 \
+    if (e == cudaSuccess && g.P > 1)                                                                         \
+      e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP, false, true>,                               \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fast_cols_smem(3, 4096));  \
     LR_ATTR_PIPE(LP)                                                                                         \
     break;
       LR_ATTR(0) LR_ATTR(1) LR_ATTR(2) LR_ATTR(3)
@@ -806,12 +809,14 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
 inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, const GridDesc &g,
                            const double2 *tw_sub, const double2 *tw_nx, const double *phi, const double *linf,
                            double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches,
-                           int kl0 = 0, int kl1 = -1)
+                           int kl0 = 0, int kl1 = -1, const PeerOut *peer_out = nullptr)
 {
+  // peer_out (variant 4096 in slab mode): the last kernel of the stage stores the result pieces
+  // straight into their owners' return buffers instead of sout
   if (kl1 < 0) kl1 = g.nky_loc;
   if (kl1 > g.nky_loc) kl1 = g.nky_loc;
   if (kl0 >= kl1) return 0;
-  if (variant != 4096 && (kl0 != 0 || kl1 != g.nky_loc)) return 1;
+  if (variant != 4096 && (kl0 != 0 || kl1 != g.nky_loc || peer_out)) return 1;
   const int nvc = (kl1 - kl0) << top;
   const int grid = nvc < num_sms ? nvc : num_sms;
 #ifdef GFMD_EXPERIMENTAL_COLS_PIPE
@@ -848,6 +853,11 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
 #endif
 #define LR_LAUNCH(LP)                                                                                       \
   case LP:                                                                                                  \
+    if (peer_out && top == 0) {                                                                             \
+      k_cols_fused_p2_lr<4096, 512, LP, false, true><<<grid, 512, smem, s>>>(                               \
+          sin, sout, g, lnxl, top, kl0, kl1, tw_sub, phi, linf, epart, res, *peer_out);                     \
+      break;                                                                                                \
+    }                                                                                                       \
     LR_LAUNCH_PIPE(LP)                                                                                      \
     k_cols_fused_p2_lr<4096, 512, LP><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, kl0, kl1, tw_sub,    \
                                                               phi, linf, epart, res);                       \
@@ -861,10 +871,12 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   }
   ++*launches;
   if (top == 1) {
-    k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
+    if (peer_out) k_cols_top_pass<1, +1, true><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1, *peer_out);
+    else k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   } else if (top == 2) {
-    k_cols_top_pass<2, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
+    if (peer_out) k_cols_top_pass<2, +1, true><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1, *peer_out);
+    else k_cols_top_pass<2, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   }
   return 0;
