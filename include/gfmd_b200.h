@@ -28,7 +28,11 @@
  * them changes results beyond rounding):
  *   GFMD_B200_NO_FAST=1          generic (any-size) kernels even where specialised ones exist
  *   GFMD_B200_ROWS_VARIANT=<id>  a specific row-kernel variant (csrc/kernels_fast.cuh)
+ *   GFMD_B200_COLS_SPLIT=<n>     three-phase column stage with at most n dofs per CTA even where a
+ *                                column set fits one CTA (csrc/kernel_cols_split.cuh; for tests)
  *   GFMD_B200_CHUNKS=<n>         column chunks of the multi-GPU pipeline (default 4)
+ *   GFMD_B200_PEER_STORE=1       read by gfmd_b200_ipc_import: the column stage stores its results
+ *                                straight into the peers' return buffers (experimental)
  *   GFMD_B200_HOST_PIPE=0        no per-dof upload / download pipeline on the host path
  *   GFMD_B200_NCCL_LIB=<path>    the NCCL build to dlopen before libnccl.so.2
  */
