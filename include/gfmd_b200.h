@@ -33,6 +33,8 @@
  *   GFMD_B200_CHUNKS=<n>         column chunks of the multi-GPU pipeline (default 4)
  *   GFMD_B200_PEER_STORE=1       read by gfmd_b200_ipc_import: the column stage stores its results
  *                                straight into the peers' return buffers (experimental)
+ *   GFMD_B200_PEER_DIRECT=1      likewise; with gfmd_b200_ipc_import_stage: no transposes at all, the
+ *                                column stage also loads its input from the peers (experimental)
  *   GFMD_B200_HOST_PIPE=0        no per-dof upload / download pipeline on the host path
  *   GFMD_B200_NCCL_LIB=<path>    the NCCL build to dlopen before libnccl.so.2
  */
@@ -85,6 +87,16 @@ int gfmd_b200_comm_init(gfmd_b200_t *h, const char id[GFMD_B200_UNIQUE_ID_BYTES]
 #define GFMD_B200_IPC_HANDLE_BYTES 64
 int gfmd_b200_ipc_export(gfmd_b200_t *h, char *handles /* [2][64] */);
 int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles /* [nranks][2][64] */);
+
+/* Optional third mapping, after gfmd_b200_ipc_import: every rank also exposes the buffer its row
+ * kernels write (one handle), gathered and imported the same way.  With it and
+ * GFMD_B200_PEER_DIRECT=1 the transposes disappear altogether: after a barrier the column stage
+ * loads its pieces straight from the ranks that produced them and stores its results straight
+ * into their return buffers, NVLink traffic issued by the kernels themselves (experimental;
+ * replaces, like the pushes, what MPI does inside the reference's FFT3d remap,
+ * src/solvers/gfmd_solver_fft.cpp:72-80). */
+int gfmd_b200_ipc_export_stage(gfmd_b200_t *h, char *handle /* [64] */);
+int gfmd_b200_ipc_import_stage(gfmd_b200_t *h, const char *all_handles /* [nranks][64] */);
 
 void gfmd_b200_destroy(gfmd_b200_t *h);
 

@@ -38,6 +38,26 @@ def test_energy_conservation_two_layers():
     run_energy_conservation_two_layers(gfmd_b200, torch.device("cuda"), 100000, 1000)
 
 
+def test_energy_conservation_fcc100(oracle_libs):
+    """tests/TEST_energy_conservation_fcc100: single layer, kernel `fcc100 1.0 1` (closed form, no
+    transfer matrix), 10 x 10, random displacements 0.1, no initial velocity, same criterion.  The
+    table comes from the reference plugin at test time (oracle/_ref)."""
+    import torch
+    import gfmd_b200
+    if not oracle_libs.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    run_energy_conservation(gfmd_b200, torch.device("cuda"), 100000, 1000,
+                            table=plugin_table(oracle_libs, "fcc100 1.0 1", 10, 10), vx=0.0, expect_shift=False)
+
+
+def plugin_table(O, kernel, nx, ny):
+    """Phi table and linf of a reference stiffness kernel (oracle/_ref, the plugin's own sources)."""
+    k = O.RefKernel(kernel)
+    t = {"nx": nx, "ny": ny, "ndof": k.ndof, "phi": k.phi(nx, ny), "linf": k.linf()}
+    k.close()
+    return t
+
+
 def bind_stream(s, dev):
     """On a GPU the library's work is ordered with torch's current stream; under the CPU
     emulation build (tests/test_emulated_kernels.py) everything is synchronous."""
@@ -47,8 +67,13 @@ def bind_stream(s, dev):
 
 
 def run_energy_conservation_two_layers(gfmd_b200, dev, nsteps, every):
+    run_energy_conservation(gfmd_b200, dev, nsteps, every, table=load_golden("C3_fcc100_two_layers_10x10"), vx=0.1,
+                            expect_shift=True)
+
+
+def run_energy_conservation(gfmd_b200, dev, nsteps, every, table, vx, expect_shift):
     import torch
-    g = load_golden("C3_fcc100_two_layers_10x10")
+    g = table
     nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
     gid, xeq = make_layer_atoms(nx, ny, d // 3)
     n = gid.shape[0]
@@ -63,7 +88,7 @@ def run_energy_conservation_two_layers(gfmd_b200, dev, nsteps, every):
     dgid = torch.tensor(gid, device=dev)
     dmask = torch.ones(n, dtype=torch.int32, device=dev)
     v = torch.zeros((n, 3), device=dev, dtype=torch.float64)
-    v[:, 0] = 0.1                                            # velocity all set 0.1 0.0 0.0
+    v[:, 0] = vx                                             # velocity all set 0.1 0.0 0.0 (two layers)
     f = torch.zeros((n, 3), device=dev, dtype=torch.float64)
     dt, mass = 0.01, 1.0
 
@@ -105,7 +130,7 @@ def run_energy_conservation_two_layers(gfmd_b200, dev, nsteps, every):
     de = np.max(np.abs(e - e.mean()))
     # the layer oscillates by more than half a lattice constant: the re-indexing path ran
     # (it first crosses half a lattice constant after about 500 steps)
-    if nsteps >= 1000:
+    if nsteps >= 1000 and expect_shift:
         assert max(abs(c) for c in com) > 0.5 and nshifts > 0
     assert e.mean() > 0
     assert de / e.mean() <= 1e-4, (de, e.mean())
@@ -185,11 +210,42 @@ def test_hertz_sc100_128x128():
     run_hertz_sc100_128x128(gfmd_b200, torch.device("cuda"))
 
 
-def run_hertz_sc100_128x128(gfmd_b200, dev):
+def test_hertz_fcc100_128x128(oracle_libs):
+    """tests/TEST_Hertz_fcc100_128x128: kernel `ft fcc100 1 1.0 pair-potential 1 1.0 height 128` on the
+    simple-cubic 128 x 128 layer, contact modulus E = 1.39 (eval.py:37), residual < 1e-2."""
     import torch
-    g = load_golden("C1_sc100_128x128")
+    import gfmd_b200
+    if not oracle_libs.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    run_hertz_cubic(gfmd_b200, torch.device("cuda"),
+                    plugin_table(oracle_libs, "ft fcc100 1 1.0 pair-potential 1 1.0 height 128", 128, 128), 1.0, 1.39)
+
+
+def test_hertz_sc100_128x128_a0_1_3(oracle_libs):
+    """tests/TEST_Hertz_sc100_128x128_a0_1.3: lattice constant 1.3 (`ft sc100 1.3 1 ...`; the atoms
+    sit at 1.3 i + 0.5), E* = 8/3 / 1.3, residual of the PRESSURE f / a0^2 < 1e-2 (eval.py:38-41, :82-84)."""
+    import torch
+    import gfmd_b200
+    if not oracle_libs.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    run_hertz_cubic(gfmd_b200, torch.device("cuda"),
+                    plugin_table(oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128),
+                    1.3, 8.0 / 3 / 1.3)
+
+
+def run_hertz_sc100_128x128(gfmd_b200, dev):
+    run_hertz_cubic(gfmd_b200, dev, load_golden("C1_sc100_128x128"), 1.0, 8.0 / 3)
+
+
+def run_hertz_cubic(gfmd_b200, dev, table, a0, E):
+    """One atom per cubic surface cell of lattice constant a0 (lattice sc a0; create_atoms;
+    displace_atoms all move 0.5 0.5 0.5 units box)."""
+    import torch
+    g = table
     nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])
     gid, xeq = make_layer_atoms(nx, ny, 1)
+    xeq[:, 0] = gid[:, 0] * a0 + 0.5
+    xeq[:, 1] = gid[:, 1] * a0 + 0.5
     n = gid.shape[0]
     s = gfmd_b200.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
@@ -200,17 +256,18 @@ def run_hertz_sc100_128x128(gfmd_b200, dev):
     dmask = torch.ones(n, dtype=torch.int32, device=dev)
     x = dxeq.clone()
     x[:, 2] -= 2.0                                           # displace_atoms all move 0 0 -2.0
-    fg = hertz_minimise(s, x, dxeq, dgid, dmask, n, float(nx), float(ny))
-    # eval.py: z-force of the GFMD layer (gfmd.*.r.f2.out = f_xy[2]) vs Hertz, E* = 8/3
+    fg = hertz_minimise(s, x, dxeq, dgid, dmask, n, nx * a0, ny * a0)
+    # eval.py: z-force of the GFMD layer (gfmd.*.r.f2.out = f_xy[2]) vs Hertz, contact modulus E;
+    # for a0 != 1 the comparison is in pressure, f / a0^2, at radii in box units
     f_xy = fg[:, 2].reshape(nx, ny).cpu().numpy()
     xs = np.arange(nx) + 0.5
-    xs = np.where(xs > nx / 2, xs - nx, xs)
+    xs = np.where(xs > nx / 2, xs - nx, xs) * a0
     ys = np.arange(ny) + 0.5
-    ys = np.where(ys > ny / 2, ys - ny, ys)
+    ys = np.where(ys > ny / 2, ys - ny, ys) * a0
     r_xy = np.sqrt((xs ** 2).reshape(-1, 1) + (ys ** 2).reshape(1, -1))
     N = np.sum(f_xy)
-    fa_xy, a, p0 = hertz_profile(r_xy, N, 8.0 / 3, 100.0)
-    res = np.sum((f_xy - fa_xy) ** 2)
+    fa_xy, a, p0 = hertz_profile(r_xy, N, E, 100.0)
+    res = np.sum((f_xy / (a0 * a0) - fa_xy) ** 2)
     assert N > 0 and a > 3
     assert res < 1e-2, (res, N, a, p0)
     s.close()

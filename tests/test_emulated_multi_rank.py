@@ -57,3 +57,16 @@ def test_in_kernel_peer_stores_emulated(nranks):
     r = subprocess.run([sys.executable, WORKER, str(nranks)], env=env, capture_output=True, text=True, timeout=1800)
     assert "EMU_MGPU_PARITY_OK" in r.stdout and "in-kernel peer stores" in r.stdout, \
         r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_no_transposes_emulated(nranks):
+    """GFMD_B200_PEER_DIRECT=1 with the row-output buffers mapped (gfmd_b200_ipc_import_stage): after a
+    barrier the column stage loads its pieces straight from the ranks that produced them (pass 0 of
+    the column kernel, or the forward top-digit pass of long columns) and stores its results straight
+    into their return buffers.  Two steps per grid, so a buffer reused too early would show."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    env = dict(os.environ, GFMD_B200_PEER_DIRECT="1", GFMD_EMU_GRIDS="4096x8,4096x32,8192x8,16384x4,16x2048")
+    r = subprocess.run([sys.executable, WORKER, str(nranks)], env=env, capture_output=True, text=True, timeout=1800)
+    assert "EMU_MGPU_PARITY_OK" in r.stdout and "transposes: none" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

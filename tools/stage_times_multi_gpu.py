@@ -7,9 +7,11 @@ Settings (AB=<comma separated names> restricts them, default all that apply to t
     default        peer pushes on copy engines + chunked pipeline
     peer_store     GFMD_B200_PEER_STORE=1: the column stage stores its results straight into the peers'
                    return buffers (kernel_cols_lr.cuh, PEER variants)
+    direct         GFMD_B200_PEER_DIRECT=1: no transposes, the column stage also LOADS its pieces from the peers
     rows_fused     GFMD_B200_ROWS_VARIANT=ny+6: fused backward row kernel
     rows_r16       GFMD_B200_ROWS_VARIANT=ny+8: radix-16 row kernels
-    r16_peer       both
+    r16_peer       rows_r16 + peer_store
+    r16_direct     rows_r16 + direct
     chunks8        GFMD_B200_CHUNKS=8
     nccl           grouped ncclSend/ncclRecv instead of the peer pushes
 Prints, per setting, the solver step (wall clock over 30 steps between barriers), the CUDA-event stage
@@ -28,15 +30,17 @@ nx, ny = grids[world]; d = 3
 SETTINGS = {
     'default': {},
     'peer_store': {'GFMD_B200_PEER_STORE': '1'},
+    'direct': {'GFMD_B200_PEER_DIRECT': '1'},
     'rows_fused': {'GFMD_B200_ROWS_VARIANT': str(ny + 6)},
     'rows_r16': {'GFMD_B200_ROWS_VARIANT': str(ny + 8)},
     'r16_peer': {'GFMD_B200_ROWS_VARIANT': str(ny + 8), 'GFMD_B200_PEER_STORE': '1'},
+    'r16_direct': {'GFMD_B200_ROWS_VARIANT': str(ny + 8), 'GFMD_B200_PEER_DIRECT': '1'},
     'chunks8': {'GFMD_B200_CHUNKS': '8'},
     'nccl': {'EXCH': 'nccl'},
 }
 names = os.environ['AB'].split(',') if os.environ.get('AB') else list(SETTINGS)
 if world == 1: names = [n for n in names if n in ('default', 'rows_fused', 'rows_r16')]
-KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH')
+KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_PEER_DIRECT', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH')
 nxl = nx // world
 u = torch.rand((d, nxl * ny), device=dev, dtype=torch.float64, generator=torch.Generator(dev).manual_seed(7 + rank)) - 0.5
 f0 = None

@@ -244,6 +244,9 @@ struct gfmd_b200 {
   bool ipc_on = false;
   bool peer_store = false;                    // GFMD_B200_PEER_STORE=1: the column stage stores its result pieces
                                               // straight into the peers' return buffers (no return pushes)
+  bool peer_direct = false;                   // GFMD_B200_PEER_DIRECT=1: it also loads its input pieces straight
+                                              // from the peers' row-kernel outputs (no transfers at all)
+  double2 *peer_stage[kMaxRanks] = {};        // peers' row-output buffers (d_stage), gfmd_b200_ipc_import_stage
   double2 *peer_recv[2][kMaxRanks] = {};      // peers' receive buffers (forward, return), mapped here
   cudaStream_t copy_stream[kMaxRanks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxRanks] = {};
@@ -833,7 +836,9 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
 
   CU(h, cudaMemsetAsync(&h->d_res->epot, 0, offsetof(StepResults, fsum), h->stream));
 
-  const bool pipelined = g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->fast_rows && h->nchunks > 1;
+  // GFMD_B200_PEER_DIRECT: no transposes -- the column stage loads and stores the pieces in the peers' memory
+  const bool direct = g.P > 1 && h->ipc_on && h->peer_direct && h->fast_cols == 4096 && h->peer_stage[(g.rank + 1) % g.P];
+  const bool pipelined = g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->fast_rows && h->nchunks > 1 && !direct;
   if (pipelined) {
     int rc = pipelined_step(h, d_u, A, B, B2);
     if (rc) return rc;
@@ -854,24 +859,31 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   {
     stage_mark(h, 2);
     if (g.P > 1) {
-      int rc = exchange(h, A, B, 0);
-      if (rc) return rc;
+      if (direct) {     // barrier: every rank's rows are complete before anyone loads them
+        NC(h, nccl().AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
+      } else {
+        int rc = exchange(h, A, B, 0);
+        if (rc) return rc;
+      }
     }
     stage_mark(h, 3);
     int nepart = (g.nky_loc << h->cols_top) * (h->fast_cols ? fast_cols_nw(h->fast_cols) : 1);
     // GFMD_B200_PEER_STORE: the column stage stores its result pieces straight into the owners' return buffers
-    const bool peer_store = g.P > 1 && h->ipc_on && h->peer_store && h->fast_cols == 4096;
-    PeerOut po{};
+    const bool peer_store = g.P > 1 && h->ipc_on && (h->peer_store || direct) && h->fast_cols == 4096;
+    PeerOut po{}, pin{};
     if (peer_store) {
       const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;
       for (int r = 0; r < g.P; ++r) po.p[r] = (r == g.rank ? B2 : h->peer_recv[1][r]) + g.rank * blk;
+      if (direct)
+        for (int r = 0; r < g.P; ++r) pin.p[r] = (r == g.rank ? A : h->peer_stage[r]) + g.rank * blk;
     }
     if (g.nky_loc > 0) {
       if (h->fast_cols) {
         const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
-        int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
-                                 h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, 0, -1,
-                                 peer_store ? &po : nullptr);
+        // direct: long columns are assembled in B by the pulling top-digit pass and transformed there in place
+        int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, direct ? B : A, g, tw_sub, h->fft_cols.desc.core.tw,
+                                 h->d_phi, h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, 0, -1,
+                                 peer_store ? &po : nullptr, direct ? &pin : nullptr);
         if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
       } else {
         launch_generic_cols(h, B, A, &nepart);
@@ -1228,8 +1240,49 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
   }
   h->ipc_on = true;
   if (const char *e = getenv("GFMD_B200_PEER_STORE")) h->peer_store = atoi(e) != 0;
-  if (h->peer_store && h->fast_cols == 4096 && h->desc.find("return: ") == std::string::npos)
+  if (const char *e = getenv("GFMD_B200_PEER_DIRECT")) h->peer_direct = atoi(e) != 0;
+  if (h->peer_store && !h->peer_direct && h->fast_cols == 4096 && h->desc.find("return: ") == std::string::npos)
     h->desc += " | return: in-kernel peer stores";
+  return 0;
+}
+
+int gfmd_b200_ipc_export_stage(gfmd_b200_t *h, char *handle)
+{
+  if (!h || !handle) return fail(h, GFMD_B200_EINVAL, "ipc_export_stage: null argument");
+  if (h->g.P == 1) return fail(h, GFMD_B200_ESTATE, "ipc_export_stage: single-GPU handle has no exchange");
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaIpcMemHandle_t m;
+  CU(h, cudaIpcGetMemHandle(&m, h->d_stage));
+  memcpy(handle, &m, sizeof(m));
+  return 0;
+}
+
+int gfmd_b200_ipc_import_stage(gfmd_b200_t *h, const char *all_handles)
+{
+  if (!h || !all_handles) return fail(h, GFMD_B200_EINVAL, "ipc_import_stage: null argument");
+  if (h->g.P == 1) return 0;
+  if (!h->ipc_on) return fail(h, GFMD_B200_ESTATE, "ipc_import_stage before ipc_import");
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->g.P; ++r) {
+    if (r == h->g.rank) {
+      h->peer_stage[r] = h->d_stage;
+      continue;
+    }
+    if (h->peer_stage[r]) continue;
+    cudaIpcMemHandle_t m;
+    memcpy(&m, all_handles + (size_t) r * GFMD_B200_IPC_HANDLE_BYTES, sizeof(m));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, m, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return fail(h, GFMD_B200_ECUDA, "cudaIpcOpenMemHandle(rank %d, row output) failed: %s (the peer pushes stay "
+                  "in use)", r, cudaGetErrorString(e));
+    h->peer_stage[r] = (double2 *) p;
+  }
+  if (h->peer_direct && h->fast_cols == 4096 && h->desc.find("transposes: ") == std::string::npos)
+    h->desc += " | transposes: none, in-kernel peer loads and stores";
   return 0;
 }
 
@@ -1245,6 +1298,8 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   for (int w = 0; w < 2; ++w)
     for (int r = 0; r < gfmd_b200::kMaxRanks; ++r)
       if (h->peer_recv[w][r] && r != h->g.rank) cudaIpcCloseMemHandle(h->peer_recv[w][r]);
+  for (int r = 0; r < gfmd_b200::kMaxRanks; ++r)
+    if (h->peer_stage[r] && r != h->g.rank) cudaIpcCloseMemHandle(h->peer_stage[r]);
   for (int r = 0; r < gfmd_b200::kMaxRanks; ++r) {
     if (h->copy_stream[r]) cudaStreamDestroy(h->copy_stream[r]);
     if (h->ev_join[r]) cudaEventDestroy(h->ev_join[r]);

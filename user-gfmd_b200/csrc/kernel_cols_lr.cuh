@@ -35,11 +35,12 @@ __device__ long long g_phase_cycles[16];
 #define PHASE_MARK(i)
 #endif
 
-// Where the result pieces of a column go when the kernel stores them straight into the peers'
-// receive buffers over NVLink (PEER variants): p[r] = rank r's return buffer + this rank's
-// block offset (own rank: the local return buffer), so that piece r of local column kl, dof a,
-// lives at p[r][(a * kyb + kl) * nx_loc + x % nx_loc] -- the layout the copy-engine pushes
-// produce, without the staging write, the copy and its wait.
+// Where the pieces of this rank's columns live in the PEERS' memory (PEER variants, NVLink loads and
+// stores issued by the kernel itself): p[r] = a buffer of rank r + this rank's block offset (own
+// rank: the local buffer), so that piece r of local column kl, dof a, is
+// p[r][(a * kyb + kl) * nx_loc + x % nx_loc] -- the layout the copy-engine pushes produce,
+// without the staging write, the copy and its wait.  As destination (`outp`): the ranks' return
+// buffers, read by their backward row kernels.  As source (`inp`): the ranks' row-kernel outputs.
 struct PeerOut {
   double2 *p[16];
 };
@@ -53,18 +54,20 @@ struct PeerOut {
 // backward pass of column c is fused with
 // pass 0 of column c + gridDim.x (p2_pass0_inv_fwd_blk): the loads of the next column are in
 // flight while the finished column is transformed and stored, instead of after it.
-// PEER (experimental, GFMD_B200_PEER_STORE=1, slab mode with peer mappings, ltop == 0): the last
-// backward pass stores each piece straight into its owner's return buffer (`outp`) -- full
-// 128-byte lines over NVLink -- instead of the local staging buffer.
-template <int N, int T, int LP, bool PIPE = false, bool PEER = false>
+// PEER (experimental, slab mode with peer mappings, ltop == 0).  1 (GFMD_B200_PEER_STORE=1): the
+// last backward pass stores each piece straight into its owner's return buffer (`outp`) -- full
+// 128-byte lines over NVLink -- instead of the local staging buffer.  2 (GFMD_B200_PEER_DIRECT=1):
+// pass 0 also LOADS each piece straight from the row-kernel output of the rank that produced it
+// (`inp`), so the column stage has no transfer before or after it at all.
+template <int N, int T, int LP, bool PIPE = false, int PEER = 0>
 __global__ void __launch_bounds__(T, 1)
 k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, int lnxl, int ltop,
                    int kl0, int kl1,   // local ky range of this launch (chunked multi-GPU pipeline)
                    const double2 *__restrict__ tw, const double *__restrict__ phi,
                    const double *__restrict__ linf, double *__restrict__ epart, StepResults *res,
-                   PeerOut outp = PeerOut())
+                   PeerOut outp = PeerOut(), PeerOut inp = PeerOut())
 {
-  static_assert(!(PIPE && PEER), "the pipelined variant has no peer-store form");
+  static_assert(!(PIPE && PEER != 0), "the pipelined variant has no peer form");
   constexpr int D = 3;
   constexpr int NW = T / 32;
   constexpr int LNXLC = P2<N>::LOG - LP;                      // min(log2 N, lnxl)
@@ -101,6 +104,12 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 #ifdef GFMD_EXPERIMENTAL_COLS_PIPE
     if (!PIPE || vc == (kl0 << ltop) + (int) blockIdx.x)
 #endif
+    if constexpr (PEER == 2) {
+      const size_t rel0 = ((size_t) (vc >> ltop)) << lnxl;
+      p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) {
+        return inp.p[off >> LNXLC][rel0 + a * dstride + (size_t) ((off & XMASK) + base)];
+      });
+    } else
     p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) { return sin[addr(a, base, off)]; });
     __syncthreads();
     PHASE_MARK(0);
@@ -196,8 +205,8 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
       epart[vc] = a;
     }
     PHASE_MARK(6);
-    // next column's data -> L2 while the backward passes run
-    if (vc + (int) gridDim.x < nvc) {
+    // next column's data -> L2 while the backward passes run (not for data in a peer's memory)
+    if (PEER != 2 && vc + (int) gridDim.x < nvc) {
       const size_t ncol0 = column_base(vc + gridDim.x);
       for (int i = threadIdx.x; i < D * N / 8; i += T) {
         const int a = i / (N / 8), x = (i - a * (N / 8)) * 8;
@@ -219,7 +228,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
           });
     } else
 #endif
-    if constexpr (PEER) {
+    if constexpr (PEER != 0) {
       // ltop == 0: the sub-column is the column, piece = off >> LNXLC is a compile-time constant
       const size_t rel0 = ((size_t) (vc >> ltop)) << lnxl;
       p2_pass0_inv_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off, double2 v) {
@@ -235,14 +244,14 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 
 // Top-digit pass of a long column transform, in place in the staging buffer.
 // One thread per (dof, kl, n), n < S = nx >> LR; elements x = n + r*S, r < R = 2^LR.
-// PEER (DIR = +1 only): the results go to the pieces' owners (`outp`, see PeerOut) instead of back
-// into `stage`.
+// PEER, DIR = +1: the results go to the pieces' owners (`peer`, see PeerOut) instead of back into
+// `stage`.  PEER, DIR = -1: the inputs come from the ranks that produced them (`peer`) and the
+// results go to `stage`.
 template <int LR, int DIR, bool PEER = false>
 __global__ void __launch_bounds__(256)
 k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx, int kl0,
-                int kl1, PeerOut outp = PeerOut())
+                int kl1, PeerOut peer = PeerOut())
 {
-  static_assert(!PEER || DIR > 0, "peer stores belong to the backward top pass");
   constexpr int R = 1 << LR;
   const int S = g.nx >> LR;
   const int xmask = (1 << lnxl) - 1;
@@ -258,7 +267,8 @@ k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2
     for (int r = 0; r < R; ++r) {
       const int x = n + r * S;
       a[r] = ((((size_t) (x >> lnxl) * g.d + dof) * g.kyb + kl) << lnxl) + (size_t) (x & xmask);
-      v[r] = stage[a[r]];
+      if (PEER && DIR < 0) v[r] = peer.p[x >> lnxl][((((size_t) dof) * g.kyb + kl) << lnxl) + (size_t) (x & xmask)];
+      else v[r] = stage[a[r]];
     }
     if (DIR > 0) {
 #pragma unroll
@@ -269,12 +279,12 @@ k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2
 #pragma unroll
       for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw_nx + (size_t) q * n));
     }
-    if constexpr (PEER) {
+    if constexpr (PEER && DIR > 0) {
       const size_t rel = ((((size_t) dof) * g.kyb + kl) << lnxl);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int x = n + r * S;
-        outp.p[x >> lnxl][rel + (size_t) (x & xmask)] = v[r];
+        peer.p[x >> lnxl][rel + (size_t) (x & xmask)] = v[r];
       }
     } else {
 #pragma unroll

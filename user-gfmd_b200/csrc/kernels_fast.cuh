@@ -748,7 +748,10 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int) fast_cols_smem(3, 4096));                                                 \
     if (e == cudaSuccess && g.P > 1)                                                                         \
-      e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP, false, true>,                               \
+      e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP, false, 1>,                                  \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fast_cols_smem(3, 4096));  \
+    if (e == cudaSuccess && g.P > 1)                                                                         \
+      e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP, false, 2>,                                  \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fast_cols_smem(3, 4096));  \
     LR_ATTR_PIPE(LP)                                                                                         \
     break;
@@ -809,10 +812,14 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
 inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, const GridDesc &g,
                            const double2 *tw_sub, const double2 *tw_nx, const double *phi, const double *linf,
                            double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches,
-                           int kl0 = 0, int kl1 = -1, const PeerOut *peer_out = nullptr)
+                           int kl0 = 0, int kl1 = -1, const PeerOut *peer_out = nullptr,
+                           const PeerOut *peer_in = nullptr)
 {
   // peer_out (variant 4096 in slab mode): the last kernel of the stage stores the result pieces
-  // straight into their owners' return buffers instead of sout
+  // straight into their owners' return buffers instead of sout.  peer_in (only together with
+  // peer_out): the first kernel of the stage loads the pieces straight from the ranks that produced
+  // them instead of sin; with a top-digit pass, sin then receives the assembled columns.
+  if (peer_in && !peer_out) return 1;
   if (kl1 < 0) kl1 = g.nky_loc;
   if (kl1 > g.nky_loc) kl1 = g.nky_loc;
   if (kl0 >= kl1) return 0;
@@ -829,10 +836,12 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   const int top_grid = (int) ((top_items + 255) / 256 < (long long) num_sms * 8 ? (top_items + 255) / 256
                                                                                 : (long long) num_sms * 8);
   if (top == 1) {
-    k_cols_top_pass<1, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
+    if (peer_in) k_cols_top_pass<1, -1, true><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
+    else k_cols_top_pass<1, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   } else if (top == 2) {
-    k_cols_top_pass<2, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
+    if (peer_in) k_cols_top_pass<2, -1, true><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
+    else k_cols_top_pass<2, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   }
   switch (variant) {
@@ -854,8 +863,12 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
 #define LR_LAUNCH(LP)                                                                                       \
   case LP:                                                                                                  \
     if (peer_out && top == 0) {                                                                             \
-      k_cols_fused_p2_lr<4096, 512, LP, false, true><<<grid, 512, smem, s>>>(                               \
-          sin, sout, g, lnxl, top, kl0, kl1, tw_sub, phi, linf, epart, res, *peer_out);                     \
+      if (peer_in)                                                                                          \
+        k_cols_fused_p2_lr<4096, 512, LP, false, 2><<<grid, 512, smem, s>>>(                                \
+            sin, sout, g, lnxl, top, kl0, kl1, tw_sub, phi, linf, epart, res, *peer_out, *peer_in);         \
+      else                                                                                                  \
+        k_cols_fused_p2_lr<4096, 512, LP, false, 1><<<grid, 512, smem, s>>>(                                \
+            sin, sout, g, lnxl, top, kl0, kl1, tw_sub, phi, linf, epart, res, *peer_out);                   \
       break;                                                                                                \
     }                                                                                                       \
     LR_LAUNCH_PIPE(LP)                                                                                      \

@@ -38,6 +38,8 @@ ABI = {
     "gfmd_b200_comm_init": (_i, [_vp, ctypes.c_char_p]),
     "gfmd_b200_ipc_export": (_i, [_vp, ctypes.c_char_p]),
     "gfmd_b200_ipc_import": (_i, [_vp, ctypes.c_char_p]),
+    "gfmd_b200_ipc_export_stage": (_i, [_vp, ctypes.c_char_p]),
+    "gfmd_b200_ipc_import_stage": (_i, [_vp, ctypes.c_char_p]),
     "gfmd_b200_destroy": (None, [_vp]),
     "gfmd_b200_last_error": (ctypes.c_char_p, [_vp]),
     "gfmd_b200_get_brick": (_i, [_vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
@@ -192,9 +194,33 @@ class GFMDSolverB200:
         assert len(all_handles) == 2 * IPC_HANDLE_BYTES * self.nranks
         self._check(self.lib.gfmd_b200_ipc_import(self.h, all_handles))
 
+    def ipc_export_stage(self):
+        """Handle (64 bytes) of the buffer this rank's row kernels write (GFMD_B200_PEER_DIRECT)."""
+        buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self.lib.gfmd_b200_ipc_export_stage(self.h, buf))
+        return buf.raw
+
+    def ipc_import_stage(self, all_handles):
+        assert len(all_handles) == IPC_HANDLE_BYTES * self.nranks
+        self._check(self.lib.gfmd_b200_ipc_import_stage(self.h, all_handles))
+
     def enable_peer_copy(self, all_gather_bytes):
-        """Convenience: all_gather_bytes(b) -> list of every rank's bytes, in rank order."""
+        """Convenience: all_gather_bytes(b) -> list of every rank's bytes, in rank order.  Maps the
+        peers' receive buffers and their row-output buffers (the latter is only used with
+        GFMD_B200_PEER_DIRECT=1)."""
         self.ipc_import(b"".join(all_gather_bytes(self.ipc_export())))
+        # every rank takes part in the gather; a failed optional mapping only disables the direct mode
+        try:
+            mine = self.ipc_export_stage()
+        except GFMDError as e:
+            mine, self.peer_stage_error = b"\0" * IPC_HANDLE_BYTES, str(e)
+        everyone = all_gather_bytes(mine)
+        if any(h == b"\0" * IPC_HANDLE_BYTES for h in everyone):
+            return
+        try:
+            self.ipc_import_stage(b"".join(everyone))
+        except GFMDError as e:
+            self.peer_stage_error = str(e)
 
     def set_kernel(self, phi, linf=None, normalized=True):
         """phi: the table fill_phi_buffer produced for the whole grid,
