@@ -182,7 +182,8 @@ def main_reference(args):
     r = reference_run(nx, ny, d, args.steps, args.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+           "scaling": "strong" if args.grid > 0 else "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d" % (nx, ny, d),
                       "step": "GFMDSolver::post_force(u_xy, f_xy) on host arrays"},
@@ -404,7 +405,8 @@ def main_b200(args):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "scaling": "strong" if args.grid > 0 else "weak",   # --grid fixes the total work
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "synthetic surface %dx%d, stiffness kernel `sc100 height 128`, ndof %d, "
                                       "1 atom/cell" % (nx, ny, d),
                           "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",

@@ -38,18 +38,6 @@ def test_energy_conservation_two_layers():
     run_energy_conservation_two_layers(gfmd_b200, torch.device("cuda"), 100000, 1000)
 
 
-def test_energy_conservation_fcc100(oracle_libs):
-    """tests/TEST_energy_conservation_fcc100: single layer, kernel `fcc100 1.0 1` (closed form, no
-    transfer matrix), 10 x 10, random displacements 0.1, no initial velocity, same criterion.  The
-    table comes from the reference plugin at test time (oracle/_ref)."""
-    import torch
-    import gfmd_b200
-    if not oracle_libs.ref_available():
-        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
-    run_energy_conservation(gfmd_b200, torch.device("cuda"), 100000, 1000,
-                            table=plugin_table(oracle_libs, "fcc100 1.0 1", 10, 10), vx=0.0, expect_shift=False)
-
-
 def plugin_table(O, kernel, nx, ny):
     """Phi table and linf of a reference stiffness kernel (oracle/_ref, the plugin's own sources)."""
     k = O.RefKernel(kernel)
@@ -208,29 +196,6 @@ def test_hertz_sc100_128x128():
     import torch
     import gfmd_b200
     run_hertz_sc100_128x128(gfmd_b200, torch.device("cuda"))
-
-
-def test_hertz_fcc100_128x128(oracle_libs):
-    """tests/TEST_Hertz_fcc100_128x128: kernel `ft fcc100 1 1.0 pair-potential 1 1.0 height 128` on the
-    simple-cubic 128 x 128 layer, contact modulus E = 1.39 (eval.py:37), residual < 1e-2."""
-    import torch
-    import gfmd_b200
-    if not oracle_libs.ref_available():
-        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
-    run_hertz_cubic(gfmd_b200, torch.device("cuda"),
-                    plugin_table(oracle_libs, "ft fcc100 1 1.0 pair-potential 1 1.0 height 128", 128, 128), 1.0, 1.39)
-
-
-def test_hertz_sc100_128x128_a0_1_3(oracle_libs):
-    """tests/TEST_Hertz_sc100_128x128_a0_1.3: lattice constant 1.3 (`ft sc100 1.3 1 ...`; the atoms
-    sit at 1.3 i + 0.5), E* = 8/3 / 1.3, residual of the PRESSURE f / a0^2 < 1e-2 (eval.py:38-41, :82-84)."""
-    import torch
-    import gfmd_b200
-    if not oracle_libs.ref_available():
-        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
-    run_hertz_cubic(gfmd_b200, torch.device("cuda"),
-                    plugin_table(oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128),
-                    1.3, 8.0 / 3 / 1.3)
 
 
 def run_hertz_sc100_128x128(gfmd_b200, dev):

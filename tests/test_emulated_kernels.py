@@ -419,6 +419,18 @@ def test_energy_conservation_two_layers_short(B):
     test_compound.run_energy_conservation_two_layers(B, torch.device("cpu"), 1500, 100)
 
 
+def test_energy_conservation_fcc100_short(B, oracle_libs):
+    """TEST_energy_conservation_fcc100 (single layer, closed-form `fcc100 1.0 1` kernel, table from the
+    reference plugin): first 1500 steps; the full 100 000 emulated steps pass too (19 minutes)."""
+    import torch
+    import test_compound
+    if not oracle_libs.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    test_compound.run_energy_conservation(B, torch.device("cpu"), 1500, 100,
+                                          table=test_compound.plugin_table(oracle_libs, "fcc100 1.0 1", 10, 10),
+                                          vx=0.0, expect_shift=False)
+
+
 def test_random_call_sequences(B, oracle_libs):
     """Host logic under interleaving: several live handles of different grid sizes (generic and
     specialised kernels), random sequences of post_force / pre_force + post_force / device step /
@@ -558,13 +570,22 @@ def test_pipelined_column_kernel_variant():
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("which", ["hertz_fcc111_64x37", "hertz_sc100_128x128"])
-def test_hertz_contact_long(B, which):
-    """The two Hertz acceptance tests of tests/test_compound.py on the emulation build: thousands
-    of FIRE steps, 17 and 22 minutes on one core (both pass), so only with GFMD_EMU_LONG=1."""
+@pytest.mark.parametrize("which", ["hertz_fcc111_64x37", "hertz_sc100_128x128", "hertz_fcc100_128x128",
+                                   "hertz_sc100_128x128_a0_1_3"])
+def test_hertz_contact_long(B, which, oracle_libs):
+    """The Hertz acceptance tests of tests/test_compound.py on the emulation build: thousands of FIRE
+    steps, 17 to 30 minutes each on one core (all pass), so only with GFMD_EMU_LONG=1."""
     import os
     if not os.environ.get("GFMD_EMU_LONG"):
         pytest.skip("long: set GFMD_EMU_LONG=1")
     import torch
     import test_compound
-    getattr(test_compound, "run_" + which)(B, torch.device("cpu"))
+    dev = torch.device("cpu")
+    if which == "hertz_fcc100_128x128":
+        test_compound.run_hertz_cubic(B, dev, test_compound.plugin_table(
+            oracle_libs, "ft fcc100 1 1.0 pair-potential 1 1.0 height 128", 128, 128), 1.0, 1.39)
+    elif which == "hertz_sc100_128x128_a0_1_3":
+        test_compound.run_hertz_cubic(B, dev, test_compound.plugin_table(
+            oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128), 1.3, 8.0 / 3 / 1.3)
+    else:
+        getattr(test_compound, "run_" + which)(B, dev)

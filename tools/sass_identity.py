@@ -23,7 +23,7 @@ def sass_of(srcdir, out):
         if m:
             cur = m.group(1)
             d[cur] = []
-        elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             d[cur].append(re.sub(r"/\*[0-9a-f]+\*/", "", line).strip())
     return d
 
@@ -34,8 +34,17 @@ def demangle(names):
 
 
 def base(dem):
-    """kernel name with its template arguments, without the parameter list"""
-    return dem.split("(")[0].replace("void ", "")
+    """kernel name with its template arguments, without the parameter list (the first '(' outside
+    the template brackets; template arguments are printed as "(int)3")"""
+    depth = 0
+    for i, c in enumerate(dem):
+        if c == "<":
+            depth += 1
+        elif c == ">":
+            depth -= 1
+        elif c == "(" and depth == 0:
+            return dem[:i].replace("void ", "")
+    return dem.replace("void ", "")
 
 
 def main():
