@@ -105,6 +105,39 @@ void GFMDSolverB200::set_grid_size(int in_nx, int in_ny, int in_ndof)
     if (me == 0) check(gfmd_b200_get_unique_id(id), "gfmd_b200_get_unique_id");
     MPI_Bcast(id, GFMD_B200_UNIQUE_ID_BYTES, MPI_CHAR, 0, world);
     check(gfmd_b200_comm_init(handle_, id), "gfmd_b200_comm_init");
+
+    /* NVLink peer mappings (CUDA IPC): every rank exposes its two receive buffers and the buffer
+       its row kernels write, everyone maps everyone's -- the transposes then run as peer pushes
+       (or, with GFMD_B200_PEER_DIRECT=1, inside the column kernels) instead of ncclSend/ncclRecv.
+       Optional: if any rank cannot export or import (GPUs of other ranks not visible to this
+       process, no peer access), all ranks stay on the NCCL exchange.  GFMD_B200_NO_PEER=1 skips it. */
+    if (!getenv("GFMD_B200_NO_PEER")) {
+      const int nb = 2*GFMD_B200_IPC_HANDLE_BYTES;
+      char mine[3*GFMD_B200_IPC_HANDLE_BYTES];
+      int ok = gfmd_b200_ipc_export(handle_, mine) == 0 &&
+               gfmd_b200_ipc_export_stage(handle_, mine+nb) == 0;
+      int allok = 0;
+      MPI_Allreduce(&ok, &allok, 1, MPI_INT, MPI_MIN, world);
+      if (allok) {
+        char *recv = new char[(size_t) 2*nb*nprocs];
+        char *stage = recv + (size_t) nb*nprocs;
+        MPI_Allgather(mine, nb, MPI_CHAR, recv, nb, MPI_CHAR, world);
+        MPI_Allgather(mine+nb, GFMD_B200_IPC_HANDLE_BYTES, MPI_CHAR, stage, GFMD_B200_IPC_HANDLE_BYTES,
+                      MPI_CHAR, world);
+        ok = gfmd_b200_ipc_import(handle_, recv) == 0;
+        /* a rank that failed to import would wait at barriers the others never reach: agree first */
+        MPI_Allreduce(&ok, &allok, 1, MPI_INT, MPI_MIN, world);
+        if (!allok)
+          error->all(FLERR,"fix gfmd solver static/b200: mapping the peers' GPU buffers failed on some rank; "
+                     "make all GPUs visible to every rank or set GFMD_B200_NO_PEER=1.");
+        ok = gfmd_b200_ipc_import_stage(handle_, stage) == 0;
+        MPI_Allreduce(&ok, &allok, 1, MPI_INT, MPI_MIN, world);
+        if (!allok)
+          error->all(FLERR,"fix gfmd solver static/b200: mapping the peers' row buffers failed on some rank; "
+                     "set GFMD_B200_NO_PEER=1.");
+        delete [] recv;
+      }
+    }
   }
 
   check(gfmd_b200_get_brick(handle_, &xlo_loc, &xhi_loc, &ylo_loc, &yhi_loc, &nxy_loc, &gammai_),
