@@ -31,8 +31,10 @@ __device__ __forceinline__ size_t col_index(const GridDesc &g, int d, int kl, in
 
 // grid = nky_loc * ngrp CTAs, ngrp = ceil(d / db); CTA (kl, grp) transforms dofs
 // [grp*db, min(d, (grp+1)*db)) of column kl.  in == out is allowed (a CTA only touches its own data).
+// __launch_bounds__(512, 1): with (512) alone ptxas 12.9 caps the kernel at 64 registers, which the
+// 16 complex values a thread keeps across a pass barrier (fft_engine.cuh) already fill.
 template <int DIR>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 1)
 k_cols_split_fft(const double2 *stage_in, double2 *stage_out, GridDesc g, FftDesc fd, int ld, int db)
 {
   extern __shared__ double2 smem[];

@@ -149,6 +149,7 @@ class GFMDSolverB200:
         self.device, self.rank, self.nranks = device, rank, nranks
         self._unique_id = unique_id
         self.u0 = None
+        self.peer_stage_error = None      # why the optional row-buffer mapping is missing, if it is
 
     # -- reference interface ------------------------------------------------
     def get_name(self):
