@@ -91,3 +91,43 @@ def test_integration_doc_covers_every_entry_point():
     syms = sorted(set(re.findall(r"\b(gfmd_b200_[a-z_0-9]+)\s*\(", hdr)))
     assert len(syms) >= 38
     assert [s for s in syms if s not in doc] == []
+
+
+def test_specialised_kernels_keep_their_register_and_stack_budget():
+    """The occupancy the specialised kernels are designed for is a property of
+    the built machine code: rows and radix-16 rows 128 registers (two CTAs of 256 threads, or one of
+    512, per SM), the 16-warp column kernel 128, the 8-warp one 255, and next to no local memory.
+    cuobjdump reads it from the library without a GPU; a change that makes one of them spill shows
+    here, not only as a slower bench."""
+    import re
+    import shutil
+    import subprocess
+    import gfmd_b200
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(gfmd_b200.__file__))), "libgfmd_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("libgfmd_b200.so not built")
+    out = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    usage = {m.group(1): (int(m.group(2)), int(m.group(3)))
+             for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out)}
+    assert usage, "no resource usage found in " + lib
+    budgets = [                                    # (mangled-name fragment, max registers, max stack bytes)
+        ("k_cols_fused_p2_lrI", 128, 160), ("k_cols_fused_p2I", 255, 64),
+        ("k_cols_top_passI", 64, 160), ("8k_gather", 40, 16), ("9k_scatter", 40, 16),
+    ]
+    seen = set()
+    nrows = 0
+    for name, (reg, stack) in usage.items():
+        for frag, rmax, smax in budgets:
+            if frag in name:
+                seen.add(frag)
+                assert reg <= rmax and stack <= smax, (name, reg, stack)
+        m = re.search(r"k_rows_(?:fwd|inv)_(?:p2|r16h?)ILi(\d+)ELi(\d+)ELi(\d+)E", name)
+        if m:      # <NR, RB, T, ...>: two CTAs per SM up to 256 threads, one beyond; 64 K registers per SM
+            nrows += 1
+            threads = int(m.group(3))
+            ctas = 2 if threads <= 256 else 1
+            assert reg * threads * ctas <= 65536 and stack <= 64, (name, reg, stack)
+    assert seen == {b[0] for b in budgets}, seen
+    assert nrows >= 30
