@@ -125,10 +125,13 @@ def run_energy_conservation(gfmd_b200, dev, nsteps, every, table, vx, expect_shi
     s.close()
 
 
-def hertz_minimise(s, x, dxeq, dgid, dmask, n, xprd, yprd):
+def hertz_minimise(s, x, dxeq, dgid, dmask, n, xprd, yprd, dmax=None):
     """Rigid sphere (fix contact/sphere 0 0 99.5 100.0 1.38888888888889 0.890898718140339 1.0) on
     the GFMD layer, FIRE to |f| <= 1e-6 (LAMMPS: min_style cg; minimize 0.0 1e-6 ...).
-    Returns the GFMD force on the atoms at the minimum."""
+    Returns the GFMD force on the atoms at the minimum.  dmax: largest move of any coordinate per
+    iteration (LAMMPS' min_modify dmax, default 0.1 there): the layer first meets the 12-6 wall at
+    speed, and without the cap an atom can step through the wall's singularity (it does for lattice
+    constant 1.3).  None keeps the uncapped iteration the first two Hertz cases were verified with."""
     import torch
     cx, cy, cz, R = 0.0, 0.0, 99.5, 100.0
     eps, sig, cut = 1.38888888888889, 0.890898718140339, 1.0
@@ -178,6 +181,10 @@ def hertz_minimise(s, x, dxeq, dgid, dmask, n, xprd, yprd):
             alpha = 0.1
             npos = 0
         v.add_(f, alpha=dt)
+        if dmax is not None:
+            m = float((v.abs().max() * dt).item())
+            if m > dmax:
+                v.mul_(dmax / m)
         x.add_(v, alpha=dt)
     assert fnorm is not None and fnorm <= 1e-6, fnorm
     fg = torch.zeros_like(x)
@@ -202,7 +209,7 @@ def run_hertz_sc100_128x128(gfmd_b200, dev):
     run_hertz_cubic(gfmd_b200, dev, load_golden("C1_sc100_128x128"), 1.0, 8.0 / 3)
 
 
-def run_hertz_cubic(gfmd_b200, dev, table, a0, E):
+def run_hertz_cubic(gfmd_b200, dev, table, a0, E, dmax=None):
     """One atom per cubic surface cell of lattice constant a0 (lattice sc a0; create_atoms;
     displace_atoms all move 0.5 0.5 0.5 units box)."""
     import torch
@@ -221,7 +228,7 @@ def run_hertz_cubic(gfmd_b200, dev, table, a0, E):
     dmask = torch.ones(n, dtype=torch.int32, device=dev)
     x = dxeq.clone()
     x[:, 2] -= 2.0                                           # displace_atoms all move 0 0 -2.0
-    fg = hertz_minimise(s, x, dxeq, dgid, dmask, n, nx * a0, ny * a0)
+    fg = hertz_minimise(s, x, dxeq, dgid, dmask, n, nx * a0, ny * a0, dmax)
     # eval.py: z-force of the GFMD layer (gfmd.*.r.f2.out = f_xy[2]) vs Hertz, contact modulus E;
     # for a0 != 1 the comparison is in pressure, f / a0^2, at radii in box units
     f_xy = fg[:, 2].reshape(nx, ny).cpu().numpy()

@@ -586,6 +586,6 @@ def test_hertz_contact_long(B, which, oracle_libs):
             oracle_libs, "ft fcc100 1 1.0 pair-potential 1 1.0 height 128", 128, 128), 1.0, 1.39)
     elif which == "hertz_sc100_128x128_a0_1_3":
         test_compound.run_hertz_cubic(B, dev, test_compound.plugin_table(
-            oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128), 1.3, 8.0 / 3 / 1.3)
+            oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128), 1.3, 8.0 / 3 / 1.3, dmax=0.1)
     else:
         getattr(test_compound, "run_" + which)(B, dev)

@@ -42,4 +42,4 @@ def test_hertz_sc100_128x128_a0_1_3(oracle_libs):
         pytest.skip("oracle/_ref/libgfmd_ref.so not built")
     run_hertz_cubic(gfmd_b200, torch.device("cuda"),
                     plugin_table(oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128),
-                    1.3, 8.0 / 3 / 1.3)
+                    1.3, 8.0 / 3 / 1.3, dmax=0.1)
