@@ -299,6 +299,7 @@ def test_row_kernel_variants(B, nx, ny, variant, oracle_libs, monkeypatch):
 @pytest.mark.parametrize("nx,ny,d,force", [
     (2048, 2, 12, 0), (4096, 1, 6, 0), (2000, 2, 9, 0), (1331, 3, 12, 0),      # chosen by plan()
     (37, 16, 6, 4), (64, 37, 6, 1), (30, 42, 9, 2), (11, 13, 15, 7), (1100, 3, 3, 2), (1, 1, 3, 1),
+    (4, 2048, 6, 4),      # specialised rows + host pipeline (per-dof uploads) around the split column stage
 ])
 def test_split_column_stage(B, nx, ny, d, force, oracle_libs, monkeypatch):
     O = oracle_libs
