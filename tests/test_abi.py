@@ -123,7 +123,8 @@ def test_specialised_kernels_keep_their_register_and_stack_budget():
             if frag in name:
                 seen.add(frag)
                 assert reg <= rmax and stack <= smax, (name, reg, stack)
-        m = re.search(r"k_rows_(?:fwd|inv)_(?:p2|r16h?)ILi(\d+)ELi(\d+)ELi(\d+)E", name)
+        m = re.search(r"k_rows_(?:fwd|inv)_(?:p2|r16h?)ILi(\d+)ELi(\d+)ELi(\d+)E", name) or \
+            re.search(r"k_rows_(?:fwd|inv)_r16wILi(\d+)E()Li(\d+)E", name)
         if m:      # <NR, RB, T, ...>: two CTAs per SM up to 256 threads, one beyond; 64 K registers per SM
             nrows += 1
             threads = int(m.group(3))

@@ -32,7 +32,8 @@ def random_case(nx, ny, d):
     return phi, rng.standard_normal(d // 3), rng.uniform(-0.1, 0.1, size=(d, nx, ny))
 
 
-VARIANTS = [(64, 4096, 3, 4104), (6, 4096, 6, 4104), (32, 8192, 3, 8200), (2, 8192, 6, 8200)]
+VARIANTS = [(64, 4096, 3, 4104), (6, 4096, 6, 4104), (32, 8192, 3, 8200), (2, 8192, 6, 8200), (16, 16384, 3, 16392),
+            (3, 16384, 6, 16392)]
 
 
 @pytest.mark.parametrize("nx,ny,d,variant", VARIANTS)
@@ -54,7 +55,7 @@ def test_r16_rows_against_oracle(B, nx, ny, d, variant, oracle_libs, monkeypatch
     s.close()
 
 
-@pytest.mark.parametrize("ny,variant", [(4096, 4104), (8192, 8200)])
+@pytest.mark.parametrize("ny,variant", [(4096, 4104), (8192, 8200), (16384, 16392)])
 def test_r16_rows_match_default_rows(B, ny, variant, monkeypatch):
     """Many row tiles (256 rows x 3 dofs, generic columns): radix-16 rows against the default rows
     of the same grid, to rounding."""

@@ -619,8 +619,8 @@ struct FastRowsCfg { int nr, rb, t; };
 //   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above) in both
 //   directions;  ny = 4096, 8192: +6 fused backward, unfused forward (the default at 4096),
 //   +7 fused both ways with closed-form twiddles (one table load per unit; unmeasured);
-//   ny = 4096, 8192: +8 radix-16 passes, four / five shared-memory sweeps (kernels_rows_r16.cuh;
-//   unmeasured).
+//   ny = 4096, 8192, 16384: +8 radix-16 passes, four / five / six shared-memory sweeps
+//   (kernels_rows_r16.cuh; unmeasured).
 // Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
 // rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
 // three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
@@ -632,7 +632,7 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
     case 4096: case 4099: case 4101: case 4102: case 4103: case 4104: c = {2048, 2, 256}; return true;
     case 4097: c = {2048, 4, 512}; return true;
     case 8192: case 8195: case 8197: case 8198: case 8199: case 8200: c = {4096, 2, 512}; return true;
-    case 16384: case 16389: c = {8192, 1, 512}; return true;
+    case 16384: case 16389: case 16392: c = {8192, 1, 512}; return true;
     default: return false;
   }
 }
@@ -710,6 +710,13 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
           e = cudaFuncSetAttribute(k_rows_inv_r16<2048, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) fast_rows_smem(rc));
         break;
+      case 16392:
+        e = cudaFuncSetAttribute(k_rows_fwd_r16w<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) fast_rows_smem(rc));
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(k_rows_inv_r16w<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) fast_rows_smem(rc));
+        break;
       case 8200:
         e = cudaFuncSetAttribute(k_rows_fwd_r16h<4096, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) fast_rows_smem(rc));
@@ -779,6 +786,7 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
 #undef ROWS_LAUNCH
     case 4104: k_rows_fwd_r16<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     case 8200: k_rows_fwd_r16h<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 16392: k_rows_fwd_r16w<8192, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     default: return 1;
   }
   ++*launches;
@@ -800,6 +808,7 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
 #undef ROWS_LAUNCH
     case 4104: k_rows_inv_r16<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     case 8200: k_rows_inv_r16h<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 16392: k_rows_inv_r16w<8192, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     default: return 1;
   }
   ++*launches;

@@ -470,4 +470,201 @@ k_rows_inv_r16h(const double2 *__restrict__ stage, double *__restrict__ f, GridD
   }
 }
 
+// ------------------------------------------------------------------ NR = 8192 ---
+// NR = 16 * 8 * 8 * 8 (ny = 16384, one row per CTA: 128 KB).  Pass 1 as above (512 threads); two
+// radix-8 passes in shared memory, two items per thread (blocks of 512: in place; blocks of 64: into
+// the swizzled group layout); the last radix-8 pass of both partner groups klow and 1024 - klow in
+// one thread, fused with the (un)mixing.  W, RW, RW, R = six sweeps (the radix-8 kernel: ~twelve).
+// Shared memory is [q0][q1][q2][t ^ s], s = (q2 & 3) | (q1 & 1) << 2; the unit -> group map r16w_klow
+// gives the eight units of a quarter warp eight different s, and their partner groups too.
+
+__device__ __forceinline__ int r16w_slot(int grp, int t)
+{
+  const int q1 = (grp >> 4) & 7, q2 = grp >> 7;
+  return ((grp & 15) << 9) + (q1 << 6) + (q2 << 3) + (t ^ ((q2 & 3) | ((q1 & 1) << 2)));
+}
+
+// unit p in [0, 512) -> klow in [0, 512), 0 -> 0: q2 = p & 3, q1 = (p >> 7) << 1 | (p >> 2) & 1, q0 = (p >> 3) & 15
+__device__ __forceinline__ int r16w_klow(int p)
+{
+  const int q1 = ((p >> 7) << 1) | ((p >> 2) & 1);
+  return ((p >> 3) & 15) | (q1 << 4) | ((p & 3) << 7);
+}
+
+template <int NR, int T>
+__global__ void __launch_bounds__(T, 1)
+k_rows_fwd_r16w(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+{
+  static_assert(NR == 8192 && NR / 16 == T, "k_rows_fwd_r16w: NR = 16 * 8 * 8 * 8, one row per CTA");
+  constexpr int S = NR / 8;                   // 1024: frequency stride of the last pass
+  extern __shared__ double2 sm[];
+  const int dof = dof0 + blockIdx.x / g.nx_loc;
+  const int ix = blockIdx.x % g.nx_loc;
+  const int t = threadIdx.x;
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = src[t + T * j];
+    dft16<-1>(v);
+    r16_twiddle<-1, true>(v, __ldg(tw + t));
+#pragma unroll
+    for (int q0 = 0; q0 < 16; ++q0) sm[q0 * T + t] = v[r16_out(q0)];
+  }
+  __syncthreads();
+  // blocks of 512 = 8 x 64, in place
+#pragma unroll 1
+  for (int i = t; i < NR / 8; i += T) {
+    const int t1 = i & 63;
+    double2 *blk = sm + (i >> 6) * 512 + t1;
+    double2 v[8], w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = blk[64 * j];
+    Butterfly<8, -1>::run(v);
+    tw_powers<8>(__ldg(tw + 16 * t1), w);
+    p2_apply_tw<8, -1>(v, w);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) blk[64 * q] = v[q];
+  }
+  __syncthreads();
+  // blocks of 64 = 8 x 8, into the swizzled group layout (the 8 threads of a block share a quarter warp)
+#pragma unroll 1
+  for (int i = t; i < NR / 8; i += T) {
+    const int t2 = i & 7, q1 = (i >> 3) & 7;
+    double2 *blk = sm + (i >> 3) * 64;
+    double2 v[8], w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = blk[t2 + 8 * j];
+    Butterfly<8, -1>::run(v);
+    tw_powers<8>(__ldg(tw + 128 * t2), w);
+    p2_apply_tw<8, -1>(v, w);
+    __syncwarp();
+#pragma unroll
+    for (int q2 = 0; q2 < 8; ++q2) blk[(q2 << 3) + (t2 ^ ((q2 & 3) | ((q1 & 1) << 2)))] = v[q2];
+  }
+  __syncthreads();
+  {
+    const int p = t;
+    const int klow = r16w_klow(p);
+    const int klow2 = p == 0 ? S / 2 : S - klow;
+    double2 v1[8], v2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v1[e] = sm[r16w_slot(klow, e)];
+      v2[e] = sm[r16w_slot(klow2, e)];
+    }
+    Butterfly<8, -1>::run(v1);
+    Butterfly<8, -1>::run(v2);
+    const RowsFuseTw<NR, 2> w(tw_ny, klow, klow2, p == 0);
+    if (p == 0) {
+      stage[stage_index(g, 0, dof, ix)] = rows_unmix(v1[0], v1[0], w.get(0, 0));
+      stage[stage_index(g, NR, dof, ix)] = rows_unmix(v1[0], v1[0], w.nyquist());
+#pragma unroll
+      for (int q = 1; q < 8; ++q) stage[stage_index(g, q * S, dof, ix)] = rows_unmix(v1[q], v1[8 - q], w.get(0, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        stage[stage_index(g, S / 2 + q * S, dof, ix)] = rows_unmix(v2[q], v2[7 - q], w.get(1, q));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        stage[stage_index(g, klow + q * S, dof, ix)] = rows_unmix(v1[q], v2[7 - q], w.get(0, q));
+        stage[stage_index(g, klow2 + q * S, dof, ix)] = rows_unmix(v2[q], v1[7 - q], w.get(1, q));
+      }
+    }
+  }
+}
+
+template <int NR, int T>
+__global__ void __launch_bounds__(T, 1)
+k_rows_inv_r16w(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+{
+  static_assert(NR == 8192 && NR / 16 == T, "k_rows_inv_r16w: NR = 16 * 8 * 8 * 8, one row per CTA");
+  constexpr int S = NR / 8;
+  extern __shared__ double2 sm[];
+  const int dof = dof0 + blockIdx.x / g.nx_loc;
+  const int ix = blockIdx.x % g.nx_loc;
+  const int t = threadIdx.x;
+  {
+    const int p = t;
+    const int klow = r16w_klow(p);
+    const int klow2 = p == 0 ? S / 2 : S - klow;
+    double2 y1[8], y2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      y1[q] = stage[stage_index(g, klow + q * S, dof, ix)];
+      y2[q] = stage[stage_index(g, klow2 + q * S, dof, ix)];
+    }
+    const RowsFuseTw<NR, 2> w(tw_ny, klow, klow2, p == 0);
+    if (p == 0) {
+      const double2 yh0 = stage[stage_index(g, NR, dof, ix)];
+      double2 z[8];
+      z[0] = rows_premix(y1[0], yh0, w.get(0, 0));
+#pragma unroll
+      for (int q = 1; q < 8; ++q) z[q] = rows_premix(y1[q], y1[8 - q], w.get(0, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y1[q] = z[q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) z[q] = rows_premix(y2[q], y2[7 - q], w.get(1, q));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y2[q] = z[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double2 a = y1[q], b = y2[7 - q];
+        y1[q] = rows_premix(a, b, w.get(0, q));
+        y2[7 - q] = rows_premix(b, a, w.get(1, 7 - q));
+      }
+    }
+    Butterfly<8, +1>::run(y1);
+    Butterfly<8, +1>::run(y2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sm[r16w_slot(klow, e)] = y1[e];
+      sm[r16w_slot(klow2, e)] = y2[e];
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int i = t; i < NR / 8; i += T) {
+    const int t2 = i & 7, q1 = (i >> 3) & 7;
+    double2 *blk = sm + (i >> 3) * 64;
+    double2 v[8], w[8];
+#pragma unroll
+    for (int q2 = 0; q2 < 8; ++q2) v[q2] = blk[(q2 << 3) + (t2 ^ ((q2 & 3) | ((q1 & 1) << 2)))];
+    tw_powers<8>(__ldg(tw + 128 * t2), w);
+    p2_apply_tw<8, +1>(v, w);
+    Butterfly<8, +1>::run(v);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) blk[t2 + 8 * j] = v[j];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int i = t; i < NR / 8; i += T) {
+    const int t1 = i & 63;
+    double2 *blk = sm + (i >> 6) * 512 + t1;
+    double2 v[8], w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = blk[64 * q];
+    tw_powers<8>(__ldg(tw + 16 * t1), w);
+    p2_apply_tw<8, +1>(v, w);
+    Butterfly<8, +1>::run(v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) blk[64 * j] = v[j];
+  }
+  __syncthreads();
+  {
+    double2 v[16];
+#pragma unroll
+    for (int q0 = 0; q0 < 16; ++q0) v[q0] = sm[q0 * T + t];
+    r16_twiddle<+1, false>(v, __ldg(tw + t));
+    dft16<+1>(v);
+    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[t + T * j] = v[r16_out(j)];
+  }
+}
+
 }  // namespace gfmd
