@@ -651,7 +651,7 @@ int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
 
 // Column stage of the generic kernels: `in` holds the received columns, the result goes to `out`
 // (in == out on a single rank).  Either the fused kernel (a column set fits one CTA) or the
-// three-phase form of kernel_cols_split.cuh.  Returns the number of energy partials written.
+// three-phase form of kernel_cols_split.cuh.  *nepart receives the number of energy partials written.
 int launch_generic_cols(gfmd_b200 *h, double2 *in, double2 *out, int *nepart)
 {
   const GridDesc &g = h->g;
