@@ -575,7 +575,7 @@ def test_pipelined_column_kernel_variant():
                                    "hertz_sc100_128x128_a0_1_3"])
 def test_hertz_contact_long(B, which, oracle_libs):
     """The Hertz acceptance tests of tests/test_compound.py on the emulation build: thousands of FIRE
-    steps, 17 to 30 minutes each on one core (all pass), so only with GFMD_EMU_LONG=1."""
+    steps, 17 to 28 minutes each on one core (all four pass), so only with GFMD_EMU_LONG=1."""
     import os
     if not os.environ.get("GFMD_EMU_LONG"):
         pytest.skip("long: set GFMD_EMU_LONG=1")
