@@ -422,12 +422,12 @@ def test_energy_conservation_two_layers_short(B):
 
 def test_energy_conservation_fcc100_short(B, oracle_libs):
     """TEST_energy_conservation_fcc100 (single layer, closed-form `fcc100 1.0 1` kernel, table from the
-    reference plugin): first 1500 steps; the full 100 000 emulated steps pass too (19 minutes)."""
+    reference plugin): first 500 steps; the full 100 000 emulated steps pass too (19 minutes)."""
     import torch
     import test_compound
     if not oracle_libs.ref_available():
         pytest.skip("oracle/_ref/libgfmd_ref.so not built")
-    test_compound.run_energy_conservation(B, torch.device("cpu"), 1500, 100,
+    test_compound.run_energy_conservation(B, torch.device("cpu"), 500, 50,
                                           table=test_compound.plugin_table(oracle_libs, "fcc100 1.0 1", 10, 10),
                                           vx=0.0, expect_shift=False)
 
