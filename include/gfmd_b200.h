@@ -146,6 +146,9 @@ int gfmd_b200_set_linf(gfmd_b200_t *h, const double *linf);
  * GFMD_B200_EPHI, where the reference aborts ("Out of iterations ...").  normalise != 0 applies the 1/(nx*ny) of fill_phi_buffer.  ndof 3, 6, 9, 12. */
 int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv_ri, int ky_first, int nky, int height,
                                 int normalise);
+/* Same, with the (U0, U, V) blocks already in DEVICE memory (large grids: the host never holds them). */
+int gfmd_b200_build_phi_columns_device(gfmd_b200_t *h, const double *d_uuv_ri, int ky_first, int nky, int height,
+                                       int normalise);
 
 /* Deviations found by the last gfmd_b200_set_phi: max |Phi - Phi^H| and
  * max |Phi(q) - conj Phi(-q)|, both relative to max |Phi|. */

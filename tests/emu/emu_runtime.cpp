@@ -9,6 +9,7 @@
 #include "cuda_runtime.h"
 
 #include <sys/mman.h>
+#include <sched.h>
 #include <ucontext.h>
 
 #include <chrono>
@@ -305,3 +306,20 @@ cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned)
   return cudaSuccess;
 }
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t emuStreamWriteValue32(cudaStream_t, unsigned *addr, unsigned value)
+{
+  __atomic_store_n(addr, value, __ATOMIC_RELEASE);
+  return cudaSuccess;
+}
+cudaError_t emuStreamWaitValue32Geq(cudaStream_t, unsigned *addr, unsigned value)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  while ((int) (__atomic_load_n(addr, __ATOMIC_ACQUIRE) - value) < 0) {
+    sched_yield();
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(600)) {
+      fprintf(stderr, "cuda emu: stream wait on a flag timed out (value %u never arrived)\n", value);
+      return cudaErrorInvalidValue;
+    }
+  }
+  return cudaSuccess;
+}

@@ -122,4 +122,8 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *);
 cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned);
 cudaError_t cudaIpcCloseMemHandle(void *);
+/* stream memory operations (the product uses the driver's cuStreamWriteValue32 / cuStreamWaitValue32):
+ * streams are synchronous here, so the write happens at once and the wait spins (ranks = host threads) */
+cudaError_t emuStreamWriteValue32(cudaStream_t, unsigned *addr, unsigned value);
+cudaError_t emuStreamWaitValue32Geq(cudaStream_t, unsigned *addr, unsigned value);
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F *, cudaFuncAttribute, int) { return cudaSuccess; }

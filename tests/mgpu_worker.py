@@ -24,33 +24,44 @@ def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # GFMD_TEST_ONE_DEVICE=1: every rank (process) uses cuda:0 -- the whole slab path (CUDA IPC
+    # mappings, peer pushes, flag words, in-kernel peer loads / stores) on a box with ONE GPU.
+    # NCCL refuses two ranks on one device, so there is no communicator: the ranks order their
+    # transfers through the flag words alone; the host-side plumbing (handle exchange) is gloo.
+    one_device = os.environ.get("GFMD_TEST_ONE_DEVICE", "0") == "1"
+    if one_device:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    buf = torch.zeros(gfmd_b200.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
-    if rank == 0:
-        buf.copy_(torch.frombuffer(bytearray(gfmd_b200.get_unique_id()), dtype=torch.uint8))
-    dist.broadcast(buf, 0)
-    uid = bytes(buf.cpu().numpy().tobytes())
+    if one_device:
+        dist.init_process_group("gloo")
+        cdev = torch.device("cpu")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+        cdev = dev
     s = None
     ok = True
 
-    peer_copy = os.environ.get("GFMD_TEST_EXCHANGE", "ipc") == "ipc"
+    peer_copy = os.environ.get("GFMD_TEST_EXCHANGE", "ipc") == "ipc" or one_device
+    use_nccl = not one_device and os.environ.get("GFMD_TEST_NO_COMM", "0") != "1"
     if rank == 0:
-        print("exchange:", "CUDA IPC peer copies + NCCL barrier" if peer_copy else "NCCL send/recv", flush=True)
+        print("exchange:", ("CUDA IPC peer copies" if peer_copy else "NCCL send/recv") +
+              (", NCCL communicator present" if use_nccl else ", no NCCL communicator") +
+              (", all ranks on cuda:0" if one_device else ""), flush=True)
 
     def new_slab(nx, ny, d):
-        nonlocal uid
-        # a fresh communicator per solver: rank 0 hands out a new id
-        b = torch.zeros(gfmd_b200.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            b.copy_(torch.frombuffer(bytearray(gfmd_b200.get_unique_id()), dtype=torch.uint8))
-        dist.broadcast(b, 0)
-        sl = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world,
-                                      unique_id=bytes(b.cpu().numpy().tobytes()))
+        uid = None
+        if use_nccl:
+            # a fresh communicator per solver: rank 0 hands out a new id
+            b = torch.zeros(gfmd_b200.UNIQUE_ID_BYTES, dtype=torch.uint8, device=cdev)
+            if rank == 0:
+                b.copy_(torch.frombuffer(bytearray(gfmd_b200.get_unique_id()), dtype=torch.uint8))
+            dist.broadcast(b, 0)
+            uid = bytes(b.cpu().numpy().tobytes())
+        sl = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world, unique_id=uid)
         sl.set_grid_size(nx, ny, d)
         if peer_copy:
-            sl.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(dev, world))
+            sl.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(cdev, world))
         return sl
 
     # (a) golden vectors through the slab path (generic kernels)
@@ -68,7 +79,7 @@ def main():
             e = s.post_force(u, f)
             fref = z["f_" + c][:, rank * nxl:(rank + 1) * nxl, :].reshape(d, nxl * ny)
             err = np.abs(f - fref).max() / np.abs(z["f_" + c]).max()
-            et = torch.tensor([e], device=dev, dtype=torch.float64)
+            et = torch.tensor([e], device=cdev, dtype=torch.float64)
             dist.all_reduce(et)                       # the fix sums the per-rank energies
             eref = float(z["epot_" + c])
             eerr = abs(et.item() - eref) / abs(eref)
@@ -107,7 +118,7 @@ def main():
             s.post_force_device(uslab, fslab)
             rs = s.results()
         err = (fslab - ffull[:, rank * nxl:(rank + 1) * nxl, :]).abs().max().item() / ffull.abs().max().item()
-        et = torch.tensor([rs["epot"]], device=dev, dtype=torch.float64)
+        et = torch.tensor([rs["epot"]], device=cdev, dtype=torch.float64)
         dist.all_reduce(et)
         eerr = abs(et.item() - r1["epot"]) / abs(r1["epot"])
         u0err = np.abs(rs["u0"] - r1["u0"]).max() / np.abs(r1["u0"]).max()
@@ -120,7 +131,7 @@ def main():
         s.close()
         one.close()
 
-    flag = torch.tensor([1 if ok else 0], device=dev)
+    flag = torch.tensor([1 if ok else 0], device=cdev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if rank == 0:

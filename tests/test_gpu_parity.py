@@ -297,7 +297,9 @@ def test_async_pre_force_and_errors(B):
 
 
 @pytest.mark.parametrize("nx,ny,variant", [(64, 4096, 4097), (64, 4096, 4099), (32, 8192, 8195),
-                                            (64, 2048, 2053), (128, 4096, 4101), (64, 4096, 4096), (32, 8192, 8197), (16, 16384, 16389)])
+                                            (64, 2048, 2053), (128, 4096, 4101), (64, 4096, 4096), (32, 8192, 8197), (16, 16384, 16389),
+                                            (128, 4096, 4102), (64, 4096, 4103), (32, 8192, 8198), (32, 8192, 8199),
+                                            (32, 8192, 8192), (16, 16384, 16384)])
 def test_row_kernel_variants_against_oracle(B, nx, ny, variant, oracle_libs, monkeypatch):
     """Experimental row-kernel variants (GFMD_B200_ROWS_VARIANT, csrc/kernels_fast.cuh: 256-bit
     transposed accesses, four rows per CTA, last pass fused with the real/complex (un)mixing) keep the same parity bar."""

@@ -42,7 +42,8 @@ def step(B, nx, ny, d, phi, linf, u, expect):
     f = np.full_like(uu, np.nan)
     e = s.post_force(uu, f)
     u0 = s.get_u0().copy()
-    assert s.launch_count() >= 6       # rows, fft, contract, fft, finalize, rows
+    # split: rows, fft, contract, fft, finalize, rows; fused: rows, cols_fused, finalize, rows
+    assert s.launch_count() >= (6 if expect == "k_cols_split_fft" else 4)
     s.close()
     return f.reshape(d, nx, ny), e, u0
 
@@ -80,6 +81,6 @@ def test_split_equals_fused_in_forces(B, monkeypatch):
 
 
 def test_two_atoms_per_cell_4096_energy_identity_and_linearity(B):
-    """Full-size property test on 4096 x 1024, ndof 6 (specialised rows + split columns): with
+    """Full-size property test on 4096 x 2048, ndof 6 (specialised rows + split columns): with
     linf = 0, E = -1/2 sum f.u (SURVEY 8a restatement) and f is linear in u."""
-    split_checks.energy_identity_and_linearity(B, 4096, 1024, 6, expect=("k_cols_split_fft", "[fast"))
+    split_checks.energy_identity_and_linearity(B, 4096, 2048, 6, expect=("k_cols_split_fft", "[fast"))

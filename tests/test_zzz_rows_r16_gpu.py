@@ -57,19 +57,18 @@ def test_r16_rows_against_oracle(B, nx, ny, d, variant, oracle_libs, monkeypatch
 
 @pytest.mark.parametrize("ny,variant", [(4096, 4104), (8192, 8200), (16384, 16392)])
 def test_r16_rows_match_default_rows(B, ny, variant, monkeypatch):
-    """Many row tiles (256 rows x 3 dofs, generic columns): radix-16 rows against the default rows
-    of the same grid, to rounding."""
+    """Many row tiles (256 rows x 3 dofs, generic columns): radix-16 rows (the default since round 2)
+    against the radix-8 rows of the same grid (variant id ny + 0), to rounding."""
     from gfmd_b200 import synthetic
     nx, d = 256, 3
     rng = np.random.default_rng(3)
     u = rng.uniform(-1e-3, 1e-3, size=(d, nx * ny))
     out = []
-    for v in (None, variant):
-        if v:
-            monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(v))
+    for v in (ny, variant):
+        monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(v))
         s = B.GFMDSolverB200()
         s.set_grid_size(nx, ny, d)
-        assert ("k_rows_*_r16" in s.describe()) == bool(v), s.describe()
+        assert ("k_rows_*_r16" in s.describe()) == (v == variant), s.describe()
         for k0 in range(0, s.nky, 512):
             nk = min(512, s.nky - k0)
             s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)

@@ -27,6 +27,7 @@ torch.cuda.set_device(local); dev = torch.device('cuda', local)
 dist.init_process_group('nccl', device_id=dev)
 grids = {1: (4096, 4096), 2: (4096, 8192), 4: (8192, 8192), 8: (16384, 8192)}
 nx, ny = grids[world]; d = 3
+if os.environ.get('GRID'): nx, ny = (int(v) for v in os.environ['GRID'].split('x'))      # e.g. GRID=16384x16384
 SETTINGS = {
     'default': {},
     'peer_store': {'GFMD_B200_PEER_STORE': '1'},
@@ -37,10 +38,15 @@ SETTINGS = {
     'r16_direct': {'GFMD_B200_ROWS_VARIANT': str(ny + 8), 'GFMD_B200_PEER_DIRECT': '1'},
     'chunks8': {'GFMD_B200_CHUNKS': '8'},
     'nccl': {'EXCH': 'nccl'},
+    'sync_nccl': {'GFMD_B200_SYNC': 'nccl'},                       # round-1 ordering: all-reduce barriers
+    'direct_sync_nccl': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_SYNC': 'nccl'},
+    'chunks2': {'GFMD_B200_CHUNKS': '2'},
+    'chunks1': {'GFMD_B200_CHUNKS': '1'},
+    'rows_r8': {'GFMD_B200_ROWS_VARIANT': str(ny)},                # the round-1 row kernels
 }
 names = os.environ['AB'].split(',') if os.environ.get('AB') else list(SETTINGS)
 if world == 1: names = [n for n in names if n in ('default', 'rows_fused', 'rows_r16')]
-KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_PEER_DIRECT', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH')
+KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_PEER_DIRECT', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH', 'GFMD_B200_SYNC')
 nxl = nx // world
 u = torch.rand((d, nxl * ny), device=dev, dtype=torch.float64, generator=torch.Generator(dev).manual_seed(7 + rank)) - 0.5
 f0 = None
@@ -53,9 +59,10 @@ for name in names:
     s = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world, unique_id=bytes(b.cpu().numpy().tobytes()))
     s.set_grid_size(nx, ny, d)
     if world > 1 and os.environ.get('EXCH', 'ipc') == 'ipc': s.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(dev, world))
-    for k0 in range(s.kylo, s.kylo + s.nky, 128):
-        nk = min(128, s.kylo + s.nky - k0)
-        s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+    # timing only: the sc100 matrices evaluated on the GPU, two layers (one recursion step)
+    for k0 in range(s.kylo, s.kylo + s.nky, 64):
+        nk = min(64, s.kylo + s.nky - k0)
+        s.build_kernel_columns_device(synthetic.sc100_dynamical_matrices_torch(nx, ny, k0, nk, dev), k0, nk, height=2)
     s.set_linf(np.zeros(1))
     f = torch.empty_like(u); torch.cuda.synchronize()
     for i in range(5): s.post_force_device(u, f)

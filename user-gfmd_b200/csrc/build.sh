@@ -2,7 +2,7 @@
 # Builds libgfmd_b200.so in-tree for sm_100a (no other architecture, no fallback).
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
-OUT="$HERE/../libgfmd_b200.so"
+OUT=${GFMD_OUT:-"$HERE/../libgfmd_b200.so"}
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
   -Xcompiler -fPIC -shared ${GFMD_NVCC_EXTRA} \

@@ -2,6 +2,9 @@
 // No CPU fallback anywhere in this file: every compute entry point launches
 // kernels on the handle's device or fails with an error code.
 #include <cuda_runtime.h>
+#ifndef GFMD_CUDA_EMU
+#include <cuda.h>       // types of the stream memory operations; entry points are fetched at run time
+#endif
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -30,6 +33,8 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in dynamic shared memory per CTA
+constexpr size_t kFlagTail = 256;     // complex elements (4096 B) behind d_stage2: flag words, then the u0 zone
+constexpr size_t kFlagU0Bytes = 2048; // byte offset of the u0 landing zone inside that tail
 
 // ------------------------------------------------------------------- NCCL ---
 
@@ -80,6 +85,73 @@ bool nccl_load()
   LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
 #undef LOAD
   return true;
+}
+
+// ------------------------------------------------- stream memory operations ---
+// Cross-rank ordering without a collective: a rank WRITES a sequence number into a flag word in a
+// peer's memory from the stream that carried the data (cuStreamWriteValue32 -- ordered after the
+// copies / kernels queued before it), the peer's stream WAITS for it (cuStreamWaitValue32, >=).
+// Both are executed by the GPU's front end: no SM is occupied by a spinning kernel and no host
+// thread takes part.  The driver entry points come from cudaGetDriverEntryPoint, so the library
+// has no link-time dependency on libcuda.
+
+struct MemOps {
+  bool tried = false, ok = false;
+#ifndef GFMD_CUDA_EMU
+  CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+#endif
+  std::string err;
+};
+
+MemOps &memops()
+{
+  static MemOps m;
+  return m;
+}
+
+bool memops_load()
+{
+  MemOps &m = memops();
+  if (m.tried) return m.ok;
+  m.tried = true;
+#ifdef GFMD_CUDA_EMU
+  m.ok = true;
+#else
+  void *fw = nullptr, *fq = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  cudaError_t e1 = cudaGetDriverEntryPoint("cuStreamWriteValue32", &fw, cudaEnableDefault, &q1);
+  cudaError_t e2 = cudaGetDriverEntryPoint("cuStreamWaitValue32", &fq, cudaEnableDefault, &q2);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || !fw || !fq || q1 != cudaDriverEntryPointSuccess ||
+      q2 != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    m.err = "the driver does not provide cuStreamWriteValue32 / cuStreamWaitValue32";
+    return false;
+  }
+  m.write32 = reinterpret_cast<decltype(m.write32)>(fw);
+  m.wait32 = reinterpret_cast<decltype(m.wait32)>(fq);
+  m.ok = true;
+#endif
+  return m.ok;
+}
+
+// 0 on success
+int stream_write32(cudaStream_t s, unsigned *addr, unsigned value)
+{
+#ifdef GFMD_CUDA_EMU
+  return emuStreamWriteValue32(s, addr, value) == cudaSuccess ? 0 : 1;
+#else
+  return memops().write32((CUstream) s, (CUdeviceptr) addr, value, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS ? 0 : 1;
+#endif
+}
+
+int stream_wait32_geq(cudaStream_t s, unsigned *addr, unsigned value)
+{
+#ifdef GFMD_CUDA_EMU
+  return emuStreamWaitValue32Geq(s, addr, value) == cudaSuccess ? 0 : 1;
+#else
+  return memops().wait32((CUstream) s, (CUdeviceptr) addr, value, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS ? 0 : 1;
+#endif
 }
 
 // --------------------------------------------------------------- FFT plans ---
@@ -251,6 +323,12 @@ struct gfmd_b200 {
   cudaStream_t copy_stream[kMaxRanks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxRanks] = {};
   double *d_barrier = nullptr;
+  // flag words + u0 landing zone at the end of d_stage2 (mapped by every peer together with it):
+  // peers write sequence numbers there with stream memory operations, this rank's stream waits
+  bool sync_flags = false;                    // cross-rank ordering by flags instead of NCCL all-reduces
+  unsigned seq = 0;                           // step counter, the value the flags carry
+  unsigned *flags = nullptr, *peer_flags[kMaxRanks] = {};
+  double *u0_in = nullptr, *peer_u0_in[kMaxRanks] = {};
   // chunked pipeline: column chunks overlap their own transposes
   static constexpr int kMaxChunks = 8;
   int nchunks = 1, chunk_kl = 0;
@@ -534,7 +612,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_u, nxy * g.d);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_f, nxy * g.d);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_stage, nstage);
-  if (ce == cudaSuccess && g.P > 1) ce = dmalloc(h, &h->d_stage2, nstage);
+  if (ce == cudaSuccess && g.P > 1) ce = dmalloc(h, &h->d_stage2, nstage + kFlagTail);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_phi, nphi);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_linf, (size_t) GFMD_B200_MAX_NDOF);
   if (ce == cudaSuccess) ce = dmalloc(h, &h->d_epart, ((size_t) g.kyb + 1) * kColsNW * 4);
@@ -543,7 +621,7 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   if (ce == cudaSuccess) ce = cudaMemset(h->d_u, 0, sizeof(double) * nxy * g.d);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_f, 0, sizeof(double) * nxy * g.d);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_stage, 0, sizeof(double2) * nstage);
-  if (ce == cudaSuccess && g.P > 1) ce = cudaMemset(h->d_stage2, 0, sizeof(double2) * nstage);
+  if (ce == cudaSuccess && g.P > 1) ce = cudaMemset(h->d_stage2, 0, sizeof(double2) * (nstage + kFlagTail));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_linf, 0, sizeof(double) * GFMD_B200_MAX_NDOF);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_epart, 0, sizeof(double) * (g.kyb + 1) * kColsNW * 4);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_res, 0, sizeof(StepResults));
@@ -553,6 +631,10 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
     return bail(GFMD_B200_ECUDA);
   }
   memset(h->h_res, 0, sizeof(StepResults));
+  if (g.P > 1) {
+    h->flags = reinterpret_cast<unsigned *>(h->d_stage2 + nstage);
+    h->u0_in = reinterpret_cast<double *>(reinterpret_cast<char *>(h->flags) + kFlagU0Bytes);
+  }
   h->phi_cols_set.assign(g.nky_loc > 0 ? g.nky_loc : 0, 0);
   h->phi_set = g.nky_loc == 0;      // a rank without q columns has no table to wait for
   for (int i = 0; i <= GFMD_B200_NSTAGES; ++i) cudaEventCreate(&h->ev[i]);
@@ -560,9 +642,9 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   char rows[160], cols[200], buf[512];
   FastRowsCfg frc;
   if (h->fast_rows && fast_rows_cfg(h->fast_rows, frc))
-    snprintf(rows, sizeof(rows), "k_rows_*_%s half-length len %d, %d rows/CTA, %d threads, smem %zu [fast%s]",
-             h->fast_rows == h->g.ny + 8 ? "r16" : "p2", frc.nr, frc.rb, frc.t, fast_rows_smem(frc),
-             h->fast_rows == fast_rows_default(h->g.ny) ? "" : (", variant " + std::to_string(h->fast_rows)).c_str());
+    snprintf(rows, sizeof(rows), "k_rows_*_%s half-length len %d, %d rows/CTA, %d threads, smem %zu [fast, variant %d%s]",
+             h->fast_rows == h->g.ny + 8 ? "r16" : "p2", frc.nr, frc.rb, frc.t, fast_rows_smem(frc), h->fast_rows,
+             h->fast_rows == fast_rows_default(h->g.ny) ? " = default" : "");
   else
     snprintf(rows, sizeof(rows), "k_rows_* %s len %d%s, %d rows/CTA, %d threads, smem %zu",
              h->even ? "half-length" : "full-length", h->fft_rows.desc.n,
@@ -607,6 +689,52 @@ int atom_blocks(const gfmd_b200 *h, int nall)
   return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
 
+// ---- cross-rank ordering by flags (see MemOps above) ----
+// Flag words of a rank live behind its forward receive buffer (d_stage2), which every peer maps:
+//   kFlagFwd + src * kMaxChunks + c   chunk c of src's forward blocks has landed here
+//   kFlagRet + src                    src's return blocks (and, from rank 0, u0) have landed here
+//   kFlagRows + src                   src's row transforms are complete (mode without transposes)
+// Values are the step counter h->seq; a rank can never be more than one step ahead of a peer it
+// exchanges with (it needs that peer's return blocks to finish its own step), so ">= seq" is exact.
+constexpr int kFlagFwd = 0;
+constexpr int kFlagRet = gfmd_b200::kMaxRanks * gfmd_b200::kMaxChunks;
+constexpr int kFlagRows = kFlagRet + gfmd_b200::kMaxRanks;
+static_assert((kFlagRows + gfmd_b200::kMaxRanks) * sizeof(unsigned) <= kFlagU0Bytes, "flag words overlap the u0 zone");
+
+int signal_peer(gfmd_b200 *h, cudaStream_t s, int r, int slot)
+{
+  if (stream_write32(s, h->peer_flags[r] + slot, h->seq))
+    return fail(h, GFMD_B200_ECUDA, "cuStreamWriteValue32 into rank %d's flags failed", r);
+  return 0;
+}
+
+// this rank's stream waits until every peer has signalled slot_base + src * stride for this step
+int wait_peers(gfmd_b200 *h, int slot_base, int stride)
+{
+  for (int k = 1; k < h->g.P; ++k) {
+    const int p = (h->g.rank + k) % h->g.P;
+    if (stream_wait32_geq(h->stream, h->flags + slot_base + p * stride, h->seq))
+      return fail(h, GFMD_B200_ECUDA, "cuStreamWaitValue32 on the flag of rank %d failed", p);
+  }
+  return 0;
+}
+
+// u0 = Re u~(q = 0) lives on rank 0 only (the ky = 0 column): the reference's MPI_Allreduce
+// (gfmd_solver_static.cpp:176) is a broadcast here.  Rank 0 pushes it ahead of its return flag.
+int push_u0(gfmd_b200 *h, cudaStream_t s, int r)
+{
+  if (h->g.rank != 0) return 0;
+  CU(h, cudaMemcpyAsync(h->peer_u0_in[r], h->d_res->u0, sizeof(double) * h->g.d, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int take_u0(gfmd_b200 *h)
+{
+  if (h->g.rank == 0) return 0;
+  CU(h, cudaMemcpyAsync(h->d_res->u0, h->u0_in, sizeof(double) * h->g.d, cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
 // All-to-all of the staging blocks: block r of src goes to rank r, block p of dst comes
 // from rank p.  which = 0 forward transpose, 1 return transpose.
 //
@@ -620,7 +748,8 @@ int atom_blocks(const gfmd_b200 *h, int nall)
 int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
 {
   const GridDesc &g = h->g;
-  if (!h->comm) return fail(h, GFMD_B200_ESTATE, "slab handle used before gfmd_b200_comm_init");
+  if (!h->comm && !h->sync_flags)
+    return fail(h, GFMD_B200_ESTATE, "slab handle used before gfmd_b200_comm_init / gfmd_b200_ipc_import");
   const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;   // complex elements per peer block
   NcclApi &a = nccl();
   CU(h, cudaMemcpyAsync(dst + g.rank * blk, src + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
@@ -632,8 +761,19 @@ int exchange(gfmd_b200 *h, const double2 *src, double2 *dst, int which)
       CU(h, cudaStreamWaitEvent(h->copy_stream[r], h->ev_fork, 0));
       CU(h, cudaMemcpyAsync(h->peer_recv[which][r] + g.rank * blk, src + r * blk, blk * sizeof(double2),
                             cudaMemcpyDeviceToDevice, h->copy_stream[r]));
+      if (h->sync_flags) {
+        int rc = which == 1 ? push_u0(h, h->copy_stream[r], r) : 0;
+        if (!rc) rc = signal_peer(h, h->copy_stream[r], r, which == 0 ? kFlagFwd + g.rank * gfmd_b200::kMaxChunks
+                                                                       : kFlagRet + g.rank);
+        if (rc) return rc;
+      }
       CU(h, cudaEventRecord(h->ev_join[r], h->copy_stream[r]));
       CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[r], 0));
+    }
+    if (h->sync_flags) {
+      int rc = which == 0 ? wait_peers(h, kFlagFwd, gfmd_b200::kMaxChunks) : wait_peers(h, kFlagRet, 1);
+      if (!rc && which == 1) rc = take_u0(h);
+      return rc;
     }
     if (which == 0)   // the return transpose is followed by the u0 all-reduce, which is its barrier
       NC(h, a.AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
@@ -710,6 +850,7 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
   const size_t pitch = dblk * sizeof(double2);
   const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
   const int nc = h->nchunks, ck = h->chunk_kl;
+  const bool flags = h->sync_flags;
   PeerOut po{};
   if (h->peer_store)
     for (int r = 0; r < g.P; ++r) po.p[r] = (r == g.rank ? B2 : h->peer_recv[1][r]) + g.rank * blk;
@@ -732,6 +873,9 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
           CU(h, cudaMemcpyAsync(h->peer_recv[0][r] + g.rank * blk + off, A + r * blk + off,
                                 (size_t) (k1 - k0) * g.nx_loc * sizeof(double2), cudaMemcpyDeviceToDevice,
                                 h->copy_stream[r]));
+          // in stream order behind ALL earlier pushes to r: chunk c of every dof has landed there
+          if (flags && (rc = signal_peer(h, h->copy_stream[r], r, kFlagFwd + g.rank * gfmd_b200::kMaxChunks + c)))
+            return rc;
           CU(h, cudaEventRecord(h->ev_chunk[c][r], h->copy_stream[r]));
         }
       }
@@ -745,8 +889,15 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
   for (int c = 0; c < nc; ++c) {
     const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
     const size_t off = (size_t) k0 * g.nx_loc, width = (size_t) (k1 - k0) * g.nx_loc * sizeof(double2);
+    // own pushes of this chunk have left A (the column kernel overwrites it) ...
     for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[c][(g.rank + k) % g.P], 0));
-    NC(h, a.AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    // ... and every peer's chunk has arrived in B
+    if (flags) {
+      int rc = wait_peers(h, kFlagFwd + c, gfmd_b200::kMaxChunks);
+      if (rc) return rc;
+    } else {
+      NC(h, a.AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    }
     int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, A, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi,
                              h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, k0, k1,
                              h->peer_store ? &po : nullptr);
@@ -758,7 +909,13 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
       CU(h, cudaStreamWaitEvent(h->copy_stream[r], h->ev_k2[c], 0));
       CU(h, cudaMemcpy2DAsync(h->peer_recv[1][r] + g.rank * blk + off, pitch, A + r * blk + off, pitch, width,
                               g.d, cudaMemcpyDeviceToDevice, h->copy_stream[r]));
-      if (c == nc - 1) CU(h, cudaEventRecord(h->ev_join[r], h->copy_stream[r]));
+      if (c == nc - 1) {
+        if (flags) {      // u0 (written by chunk 0's kernel on rank 0) rides ahead of the return flag
+          if ((rc = push_u0(h, h->copy_stream[r], r))) return rc;
+          if ((rc = signal_peer(h, h->copy_stream[r], r, kFlagRet + g.rank))) return rc;
+        }
+        CU(h, cudaEventRecord(h->ev_join[r], h->copy_stream[r]));
+      }
     }
   }
   k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc << h->cols_top, h->d_res);
@@ -768,6 +925,18 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
     CU(h, cudaMemcpyAsync(B2 + g.rank * blk, A + g.rank * blk, blk * sizeof(double2), cudaMemcpyDeviceToDevice,
                           h->stream));
     for (int k = 1; k < g.P; ++k) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join[(g.rank + k) % g.P], 0));
+  } else if (flags) {
+    for (int k = 1; k < g.P; ++k) {
+      const int r = (g.rank + k) % g.P;
+      int rc = push_u0(h, h->stream, r);
+      if (!rc) rc = signal_peer(h, h->stream, r, kFlagRet + g.rank);
+      if (rc) return rc;
+    }
+  }
+  if (flags) {
+    int rc = wait_peers(h, kFlagRet, 1);
+    if (!rc) rc = take_u0(h);
+    return rc;
   }
   // u0 all-reduce (gfmd_solver_static.cpp:176) doubles as the barrier of the return pushes
   NC(h, a.AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm, h->stream));
@@ -835,6 +1004,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   double2 *B2 = (g.P > 1 && h->ipc_on) ? h->d_stage3 : B;          // rows arrive here on the way back
 
   CU(h, cudaMemsetAsync(&h->d_res->epot, 0, offsetof(StepResults, fsum), h->stream));
+  if (g.P > 1) ++h->seq;
 
   // GFMD_B200_PEER_DIRECT: no transposes -- the column stage loads and stores the pieces in the peers' memory
   const bool direct = g.P > 1 && h->ipc_on && h->peer_direct && h->fast_cols == 4096 && h->peer_stage[(g.rank + 1) % g.P];
@@ -859,7 +1029,14 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   {
     stage_mark(h, 2);
     if (g.P > 1) {
-      if (direct) {     // barrier: every rank's rows are complete before anyone loads them
+      if (direct && h->sync_flags) {   // every rank's rows are complete before anyone loads them
+        for (int k = 1; k < g.P; ++k) {
+          int rc = signal_peer(h, h->stream, (g.rank + k) % g.P, kFlagRows + g.rank);
+          if (rc) return rc;
+        }
+        int rc = wait_peers(h, kFlagRows, 1);
+        if (rc) return rc;
+      } else if (direct) {
         NC(h, nccl().AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclSum, h->comm, h->stream));
       } else {
         int rc = exchange(h, A, B, 0);
@@ -894,11 +1071,22 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
     stage_mark(h, 4);
     if (g.P > 1) {
       if (!peer_store) {
-        int rc = exchange(h, A, B2, 1);
+        int rc = exchange(h, A, B2, 1);      // with flags: carries u0 and waits for the peers' return flags
+        if (rc) return rc;
+      } else if (h->sync_flags) {            // the kernels stored into the peers' buffers themselves
+        for (int k = 1; k < g.P; ++k) {
+          const int r = (g.rank + k) % g.P;
+          int rc = push_u0(h, h->stream, r);
+          if (!rc) rc = signal_peer(h, h->stream, r, kFlagRet + g.rank);
+          if (rc) return rc;
+        }
+        int rc = wait_peers(h, kFlagRet, 1);
+        if (!rc) rc = take_u0(h);
         if (rc) return rc;
       }
-      NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
-                             h->stream));
+      if (!(h->sync_flags && h->ipc_on))
+        NC(h, nccl().AllReduce(h->d_res->u0, h->d_res->u0, (size_t) g.d, ncclDouble, ncclSum, h->comm,
+                               h->stream));
     }
   }
   }   // !pipelined
@@ -1207,6 +1395,11 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
                     "in use)", r, cudaGetErrorString(e));
       h->peer_recv[w][r] = (double2 *) p;
     }
+    {
+      const size_t nstage = (size_t) h->g.P * h->g.d * h->g.kyb * h->g.nx_loc;
+      h->peer_flags[r] = reinterpret_cast<unsigned *>(h->peer_recv[0][r] + nstage);
+      h->peer_u0_in[r] = reinterpret_cast<double *>(reinterpret_cast<char *>(h->peer_flags[r]) + kFlagU0Bytes);
+    }
     if (!h->copy_stream[r]) {
       CU(h, cudaStreamCreateWithFlags(&h->copy_stream[r], cudaStreamNonBlocking));
       CU(h, cudaEventCreateWithFlags(&h->ev_join[r], cudaEventDisableTiming));
@@ -1239,6 +1432,18 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     }
   }
   h->ipc_on = true;
+  // cross-rank ordering: flag words written and awaited by the streams themselves (default), or
+  // GFMD_B200_SYNC=nccl: one-element NCCL all-reduces as barriers (needs gfmd_b200_comm_init)
+  {
+    const char *e = getenv("GFMD_B200_SYNC");
+    const bool want_nccl = e && !strcmp(e, "nccl");
+    h->sync_flags = !want_nccl && memops_load();
+    if (!h->sync_flags && !h->comm)
+      return fail(h, GFMD_B200_ESTATE, "ipc_import: %s and no NCCL communicator (gfmd_b200_comm_init) to fall back on",
+                  want_nccl ? "GFMD_B200_SYNC=nccl" : memops().err.c_str());
+    if (h->desc.find("sync: ") == std::string::npos)
+      h->desc += h->sync_flags ? " | sync: stream flags in peer memory" : " | sync: NCCL all-reduce barriers";
+  }
   if (const char *e = getenv("GFMD_B200_PEER_STORE")) h->peer_store = atoi(e) != 0;
   if (const char *e = getenv("GFMD_B200_PEER_DIRECT")) h->peer_direct = atoi(e) != 0;
   if (h->peer_store && !h->peer_direct && h->fast_cols == 4096 && h->desc.find("return: ") == std::string::npos)
@@ -1455,8 +1660,9 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
   return 0;
 }
 
-int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first, int nky, int height,
-                                int normalise)
+// uuv_is_device: the (U0, U, V) blocks already live in device memory (gfmd_b200_build_phi_columns_device)
+static int build_phi_columns_impl(gfmd_b200_t *h, const double *uuv, int ky_first, int nky, int height,
+                                  int normalise, bool uuv_is_device)
 {
   if (!h || !uuv) return fail(h, GFMD_B200_EINVAL, "build_phi_columns: null argument");
   const GridDesc &g = h->g;
@@ -1469,13 +1675,21 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
   const int d = g.d, nx = g.nx;
   const size_t dsq = (size_t) d * d;
   const size_t n = (size_t) nx * nky * 3 * dsq;
-  double2 *d_uuv = nullptr;
+  if (!(d == 3 || d == 6 || d == 9 || d == 12))
+    return fail(h, GFMD_B200_EUNSUPPORTED, "build_phi_columns: ndof %d (3, 6, 9, 12 supported)", d);
+  double2 *d_own = nullptr;
+  int *d_flag = nullptr;
   CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMalloc((void **) &d_uuv, n * sizeof(double2) + sizeof(int)));
-  int *d_flag = reinterpret_cast<int *>(d_uuv + n);        // "out of iterations" flag (height < 0)
+  if (uuv_is_device) CU(h, cudaDeviceSynchronize());     // the caller's producer may run on another stream
+  CU(h, cudaMalloc((void **) &d_flag, sizeof(int)));     // "out of iterations" flag (height < 0)
   int flag = 0;
-  cudaError_t e = h2d_blocking(d_uuv, uuv, n * sizeof(double2));
-  if (e == cudaSuccess) e = h2d_blocking(d_flag, &flag, sizeof(int));
+  cudaError_t e = h2d_blocking(d_flag, &flag, sizeof(int));
+  const double2 *d_uuv = reinterpret_cast<const double2 *>(uuv);
+  if (e == cudaSuccess && !uuv_is_device) {
+    e = cudaMalloc((void **) &d_own, n * sizeof(double2));
+    if (e == cudaSuccess) e = h2d_blocking(d_own, uuv, n * sizeof(double2));
+    d_uuv = d_own;
+  }
   if (e == cudaSuccess) {
     const double scale = normalise ? 1.0 / ((double) nx * (double) g.ny) : 1.0;
     double *dst = h->d_phi + (size_t) (ky_first - g.ky0) * dsq * nx;
@@ -1486,16 +1700,14 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
       case 3: k_build_phi<3><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
       case 6: k_build_phi<6><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
       case 9: k_build_phi<9><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
-      case 12: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
-      default:
-        cudaFree(d_uuv);
-        return fail(h, GFMD_B200_EUNSUPPORTED, "build_phi_columns: ndof %d (3, 6, 9, 12 supported)", d);
+      default: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
     }
     h->launches++;
     e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
   }
-  cudaFree(d_uuv);
+  cudaFree(d_own);
+  cudaFree(d_flag);
   CU(h, e);
   if (flag)      // the reference aborts here (iterate_Gnn, surface_stiffness.cpp:541-543)
     return fail(h, GFMD_B200_EPHI, "build_phi_columns: out of iterations while evaluating the continued fraction "
@@ -1505,6 +1717,18 @@ int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first,
   for (char c : h->phi_cols_set) all = all && c;
   h->phi_set = all;
   return 0;
+}
+
+int gfmd_b200_build_phi_columns(gfmd_b200_t *h, const double *uuv, int ky_first, int nky, int height,
+                                int normalise)
+{
+  return build_phi_columns_impl(h, uuv, ky_first, nky, height, normalise, false);
+}
+
+int gfmd_b200_build_phi_columns_device(gfmd_b200_t *h, const double *d_uuv, int ky_first, int nky, int height,
+                                       int normalise)
+{
+  return build_phi_columns_impl(h, d_uuv, ky_first, nky, height, normalise, true);
 }
 
 int gfmd_b200_phi_deviation(const gfmd_b200_t *h, double *herm_dev, double *conj_dev)
@@ -1625,8 +1849,7 @@ int gfmd_b200_prec_gradient_host(gfmd_b200_t *h, const double *cavg, const doubl
   const size_t bytes = sizeof(double) * (size_t) g.d * g.nx_loc * g.ny;
   if (!h->d_cavg) CU(h, dmalloc(h, &h->d_cavg, (size_t) GFMD_B200_MAX_NDOF * GFMD_B200_MAX_NDOF));
   CU(h, cudaMemcpyAsync(h->d_cavg, cavg, sizeof(double) * g.d * g.d, cudaMemcpyHostToDevice, h->stream));
-  try_pin(h, grad, bytes);
-  try_pin(h, gP, bytes);
+  // g / gP belong to the minimiser, which may reallocate them: never page-lock them here
   CU(h, cudaMemcpyAsync(h->d_u, grad, bytes, cudaMemcpyHostToDevice, h->stream));
   rc = enqueue_aux(h, AUX_PREC, h->d_u, h->d_f, false, first3_only ? 3 : g.d);
   if (rc) return rc;

@@ -49,8 +49,7 @@ struct PeerOut {
 // x = x0 + xi of dof a lives in source-rank piece p = x / nx_loc at
 // ((p*D + a)*kyb + kl) * nx_loc + x % nx_loc.  The piece of a butterfly element relative to
 // the first one is known at compile time (offset >> LNXLC).
-// PIPE (experimental; compiled only with -DGFMD_EXPERIMENTAL_COLS_PIPE, then selected at run time
-// with GFMD_B200_COLS_PIPE=1; the CPU emulation build of tests/emu always compiles it): the last
+// PIPE (the default; GFMD_B200_COLS_PIPE=0 selects the plain form): the last
 // backward pass of column c is fused with
 // pass 0 of column c + gridDim.x (p2_pass0_inv_fwd_blk): the loads of the next column are in
 // flight while the finished column is transformed and stored, instead of after it.
@@ -101,9 +100,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     const double *ph = phi + (size_t) vc * D * D * N;
 
     // ---- pass 0 straight from global memory (block-wide mapping: full 128-byte lines)
-#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
-    if (!PIPE || vc == (kl0 << ltop) + (int) blockIdx.x)
-#endif
+    if (!PIPE || vc == (kl0 << ltop) + (int) blockIdx.x) {
     if constexpr (PEER == 2) {
       const size_t rel0 = ((size_t) (vc >> ltop)) << lnxl;
       p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) {
@@ -111,6 +108,7 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
       });
     } else
     p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) { return sin[addr(a, base, off)]; });
+    }
     __syncthreads();
     PHASE_MARK(0);
     p2_groupA_rest_seq<N, NW, -1, D, 0>(sm, tw, tws, lane, warp);
@@ -218,7 +216,6 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
     p2_groupA_rest_seq<N, NW, +1, D, 0>(sm, tw, tws, lane, warp);
     __syncthreads();
     PHASE_MARK(7);
-#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
     if (PIPE && vc + (int) gridDim.x < nvc) {
       const size_t ncol = column_base(vc + gridDim.x);
       p2_pass0_inv_fwd_blk<N, T, D, 0>(
@@ -227,7 +224,6 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
             return sin[ncol + a * dstride + (size_t) (off >> LNXLC) * pstride + (size_t) ((off & XMASK) + base)];
           });
     } else
-#endif
     if constexpr (PEER != 0) {
       // ltop == 0: the sub-column is the column, piece = off >> LNXLC is a compile-time constant
       const size_t rel0 = ((size_t) (vc >> ltop)) << lnxl;

@@ -656,11 +656,12 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
   X(16384, 8192, 1, 512, 0, false, 0, 0)  \
   X(16389, 8192, 1, 512, 0, false, 1, 1)
 
-// the variant a grid gets when GFMD_B200_ROWS_VARIANT does not say otherwise: for ny = 4096 the
-// unfused forward kernel with the FUSED backward kernel (measured: rows_inv 0.263 instead of
-// 0.308 ms, rows_fwd 0.291 fused against 0.273 unfused); the other lengths are unmeasured and
-// keep the unfused pair
-inline int fast_rows_default(int ny) { return ny == 4096 ? 4102 : ny; }
+// the variant a grid gets when GFMD_B200_ROWS_VARIANT does not say otherwise: the radix-16 kernels
+// (kernels_rows_r16.cuh) wherever they exist.  Measured on a B200 (profiles/r2_rows_variants.txt),
+// rows_fwd / rows_inv in ms: 4096 x 4096: 0.192 / 0.218 against 0.272 / 0.263 (ny + 6, the round-1
+// default) and 0.244 / 0.243 (ny + 7); 4096 x 8192: 0.514 / 0.612 against 0.564 / 0.746 (ny + 0)
+// and 0.539 / 0.596 (ny + 7); 2048 x 16384: 0.769 / 0.711 against 0.962 / 0.890
+inline int fast_rows_default(int ny) { return (ny == 4096 || ny == 8192 || ny == 16384) ? ny + 8 : ny; }
 
 inline size_t fast_rows_smem(const FastRowsCfg &c)
 {
@@ -742,14 +743,10 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     const int lp = lnxl >= 12 ? 0 : 12 - lnxl;
     cudaError_t e = cudaSuccess;
     switch (lp) {
-#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
 #define LR_ATTR_PIPE(LP)                                                                                     \
   if (e == cudaSuccess)                                                                                      \
     e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP, true>,                                        \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fast_cols_smem(3, 4096));
-#else
-#define LR_ATTR_PIPE(LP)
-#endif
 #define LR_ATTR(LP)                                                                                          \
   case LP:                                                                                                   \
     e = cudaFuncSetAttribute(k_cols_fused_p2_lr<4096, 512, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -835,10 +832,9 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   if (variant != 4096 && (kl0 != 0 || kl1 != g.nky_loc || peer_out)) return 1;
   const int nvc = (kl1 - kl0) << top;
   const int grid = nvc < num_sms ? nvc : num_sms;
-#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
-  // experimental: software-pipelined column kernel (kernel_cols_lr.cuh)
-  static const bool cols_pipe = getenv("GFMD_B200_COLS_PIPE") && atoi(getenv("GFMD_B200_COLS_PIPE")) != 0;
-#endif
+  // software-pipelined column kernel (kernel_cols_lr.cuh): the default since it was measured
+  // (0.376 -> 0.345 ms at 4096 x 4096, profiles/r2_cols_pipe.txt); GFMD_B200_COLS_PIPE=0 selects the plain one
+  static const bool cols_pipe = !(getenv("GFMD_B200_COLS_PIPE") && atoi(getenv("GFMD_B200_COLS_PIPE")) == 0);
   const int lnxl = ilog2_rt(g.nx_loc);
   const size_t smem = fast_cols_smem(3, variant);
   const long long top_items = (long long) g.d * (kl1 - kl0) * (g.nx >> top);
@@ -859,16 +855,12 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
       break;
     case 4096:
       switch (lnxl >= 12 ? 0 : 12 - lnxl) {
-#ifdef GFMD_EXPERIMENTAL_COLS_PIPE
 #define LR_LAUNCH_PIPE(LP)                                                                                  \
   if (cols_pipe) {                                                                                          \
     k_cols_fused_p2_lr<4096, 512, LP, true><<<grid, 512, smem, s>>>(sin, sout, g, lnxl, top, kl0, kl1,      \
                                                                     tw_sub, phi, linf, epart, res);         \
     break;                                                                                                  \
   }
-#else
-#define LR_LAUNCH_PIPE(LP)
-#endif
 #define LR_LAUNCH(LP)                                                                                       \
   case LP:                                                                                                  \
     if (peer_out && top == 0) {                                                                             \

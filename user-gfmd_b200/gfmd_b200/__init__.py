@@ -48,6 +48,7 @@ ABI = {
     "gfmd_b200_set_phi_columns": (_i, [_vp, _vp, _i, _i, _i]),
     "gfmd_b200_set_linf": (_i, [_vp, _vp]),
     "gfmd_b200_build_phi_columns": (_i, [_vp, _vp, _i, _i, _i, _i]),
+    "gfmd_b200_build_phi_columns_device": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "gfmd_b200_phi_deviation": (_i, [_vp, c_double_p, c_double_p]),
     "gfmd_b200_post_force_host": (_i, [_vp, _vp, _vp, c_double_p, _vp]),
     "gfmd_b200_pre_force_async_host": (_i, [_vp, _vp]),
@@ -90,7 +91,8 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # GFMD_B200_LIB: another build of the SAME library (A/B of compile-time options, tools/ only)
+    p = path or os.environ.get("GFMD_B200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise FileNotFoundError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -169,9 +171,9 @@ class GFMDSolverB200:
         self.h = h
         self.nx, self.ny, self.ndof = nx, ny, ndof
         self.u0 = np.zeros(ndof)
-        if self.nranks > 1:
-            if self._unique_id is None:
-                raise GFMDError(6, "slab solver needs the NCCL unique id of rank 0")
+        # NCCL is optional: with peer mappings (enable_peer_copy) the ranks order their transfers
+        # through flag words in each other's memory and no communicator is needed
+        if self.nranks > 1 and self._unique_id is not None:
             self._check(self.lib.gfmd_b200_comm_init(self.h, self._unique_id))
         v = [ctypes.c_int() for _ in range(6)]
         self._check(self.lib.gfmd_b200_get_brick(self.h, *[ctypes.byref(x) for x in v]))
@@ -251,6 +253,11 @@ class GFMDSolverB200:
         nky = uuv.size // (self.nx * 3 * self.ndof * self.ndof)
         self._check(self.lib.gfmd_b200_build_phi_columns(self.h, uuv.ctypes.data, ky_first, nky, height,
                                                          int(normalize)))
+
+    def build_kernel_columns_device(self, d_uuv, ky_first, nky, height, normalize=True):
+        """build_kernel_columns with the (U0, U, V) blocks in device memory (torch tensor or address)."""
+        self._check(self.lib.gfmd_b200_build_phi_columns_device(self.h, _ptr(d_uuv), ky_first, nky, height,
+                                                                int(normalize)))
 
     def set_linf(self, linf):
         linf = np.ascontiguousarray(linf, dtype=np.float64)
@@ -429,6 +436,7 @@ def all_gather_bytes_fn(dev, world):
     import torch.distributed as dist
 
     def f(b):
+        # dev: where the process group's backend wants its tensors (cuda for nccl, cpu for gloo)
         t = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
         out = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(out, t)

@@ -102,3 +102,91 @@ def sc100_dynamical_matrices(nx, ny, ky_first, nky):
     V[..., 0, 2] = V[..., 2, 0] = 1j * sx
     V[..., 1, 2] = V[..., 2, 1] = 1j * sy
     return M
+
+
+# ---- device-side generators (torch tensors on the GPU) for grids too large to build on the host ---
+# Same physics as above; every value is a pure function of the GLOBAL cell index, so slabs of
+# different ranks -- and a single-GPU run of the whole grid -- see the same field.
+
+def _hash_noise_torch(ix, iy, c, seed):
+    """Uniform(-1, 1) from an integer hash of (ix, iy, c, seed); ix [n,1], iy [1,m] int64 tensors."""
+    h = (ix * 73856093 + iy * 19349663 + c * 83492791 + seed * 2654435761) & 0x7FFFFFFF
+    for _ in range(3):
+        h = (h * 1103515245 + 12345) & 0x7FFFFFFF
+        h = h ^ (h >> 15)
+    return h.to(dtype=__import__("torch").float64) * (2.0 / 2147483648.0) - 1.0
+
+
+def displacement_field_torch(nx, ny, x0, nx_loc, device, seed=1, nwaves=8, amp=1e-3):
+    """[3, nx_loc, ny] float64 on `device`: `nwaves` random-phase plane waves of amplitude `amp` per
+    component (separable form cos(a + b) = cos a cos b - sin a sin b, i.e. two small matrix products)
+    plus hash noise of the same size.  Wave parameters as in displacement_field (seed only)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    kx = rng.integers(0, nx, size=(nwaves, 3))
+    ky = rng.integers(0, ny, size=(nwaves, 3))
+    ph = rng.uniform(0, 2 * np.pi, size=(nwaves, 3))
+    ix = torch.arange(x0, x0 + nx_loc, device=device, dtype=torch.int64)
+    iy = torch.arange(ny, device=device, dtype=torch.int64)
+    u = torch.empty((3, nx_loc, ny), device=device, dtype=torch.float64)
+    for c in range(3):
+        kxc = torch.tensor(kx[:, c], device=device, dtype=torch.int64)
+        kyc = torch.tensor(ky[:, c], device=device, dtype=torch.int64)
+        phc = torch.tensor(ph[:, c], device=device, dtype=torch.float64)
+        # exact argument reduction in integers before the conversion to double
+        ax = ((kxc[None, :] * ix[:, None]) % nx).to(torch.float64) * (2.0 * np.pi / nx) + phc[None, :]
+        ay = ((kyc[:, None] * iy[None, :]) % ny).to(torch.float64) * (2.0 * np.pi / ny)
+        u[c] = torch.cos(ax) @ torch.cos(ay) - torch.sin(ax) @ torch.sin(ay)
+        u[c] += _hash_noise_torch(ix[:, None], iy[None, :], c, seed)
+    u *= amp
+    return u
+
+
+def atoms_for_slab_torch(nx, ny, x0, nx_loc, u):
+    """Device version of atoms_for_slab: x, xeq [n, 3] float64, gid [n, 3] int32, mask [n] int32."""
+    import torch
+    dev = u.device
+    n = nx_loc * ny
+    ix = torch.arange(x0, x0 + nx_loc, device=dev, dtype=torch.int32)[:, None].expand(nx_loc, ny).reshape(n)
+    iy = torch.arange(ny, device=dev, dtype=torch.int32)[None, :].expand(nx_loc, ny).reshape(n)
+    gid = torch.zeros((n, 3), device=dev, dtype=torch.int32)
+    gid[:, 0] = ix
+    gid[:, 1] = iy
+    xeq = torch.empty((n, 3), device=dev, dtype=torch.float64)
+    xeq[:, 0] = ix.to(torch.float64) + 0.5
+    xeq[:, 1] = iy.to(torch.float64) + 0.5
+    xeq[:, 2] = 0.5
+    x = xeq + u.reshape(3, n).t()
+    mask = torch.ones(n, device=dev, dtype=torch.int32)
+    return x, xeq, gid, mask
+
+
+def sc100_dynamical_matrices_torch(nx, ny, ky_first, nky, device):
+    """sc100_dynamical_matrices evaluated on the GPU: [nx, nky, 3, 3, 3] complex128 on `device`."""
+    import torch
+    i = torch.arange(nx, device=device, dtype=torch.float64)
+    j = torch.arange(ky_first, ky_first + nky, device=device, dtype=torch.float64)
+    qx = torch.where(i <= nx // 2, 2.0 * np.pi * i / nx, 2.0 * np.pi * (i - nx) / nx)[:, None]
+    qy = torch.where(j <= ny // 2, 2.0 * np.pi * j / ny, 2.0 * np.pi * (j - ny) / ny)[None, :]
+    cx, cy, sx, sy = torch.cos(qx), torch.cos(qy), torch.sin(qx), torch.sin(qy)
+    M = torch.zeros((nx, nky, 3, 3, 3, 2), device=device, dtype=torch.float64)     # (re, im) pairs
+    U0, U, V = M[:, :, 0], M[:, :, 1], M[:, :, 2]
+    one = torch.ones((nx, nky), device=device, dtype=torch.float64)
+    U[..., 0, 0, 0] = 6 - 2 * cx * (1 + cy)
+    U[..., 1, 1, 0] = 6 - 2 * cy * (1 + cx)
+    U[..., 2, 2, 0] = 6 * one
+    U[..., 0, 1, 0] = 2 * sx * sy
+    U[..., 1, 0, 0] = 2 * sx * sy
+    U0[..., 0, 0, 0] = 5 - 2 * cx * (1 + cy)
+    U0[..., 1, 1, 0] = 5 - 2 * cy * (1 + cx)
+    U0[..., 2, 2, 0] = 3 * one
+    U0[..., 0, 1, 0] = 2 * sx * sy
+    U0[..., 1, 0, 0] = 2 * sx * sy
+    V[..., 0, 0, 0] = -cx * one
+    V[..., 1, 1, 0] = -cy * one
+    V[..., 2, 2, 0] = -1 - cx - cy
+    V[..., 0, 2, 1] = sx * one
+    V[..., 2, 0, 1] = sx * one
+    V[..., 1, 2, 1] = sy * one
+    V[..., 2, 1, 1] = sy * one
+    return M

@@ -33,11 +33,16 @@
 using namespace LAMMPS_NS;
 
 GFMDSolverB200::GFMDSolverB200(LAMMPS *lmp, int narg, int *iarg, char **arg)
-  : GFMDSolver(lmp), handle_(NULL), device_(-1), async_(true), kernel_(NULL), normalize_(true)
+  : GFMDSolver(lmp), handle_(NULL), device_(-1), async_(true), pin_(false), kernel_(NULL), normalize_(true)
 {
   strcpy(name, "static/b200");
 
-  /* optional: `solver static/b200 device <id>` and `sync` (no launch from pre_force) */
+  /* optional: `solver static/b200 device <id>`, `sync` (no launch from pre_force) and `pin`
+     (page-lock the fix's u_xy / f_xy for full-rate PCIe copies).  `pin` is opt-in because the
+     library would then hold a registration on memory the FIX owns: FixGFMD::~FixGFMD frees
+     u_xy / f_xy (fix_gfmd.cpp:479-480) BEFORE it deletes the solver (:486), i.e. while they are
+     still registered.  Use it together with the two-line reordering of that destructor shown in
+     INTEGRATION.md (delete the solver first). */
   while (narg > 0 && *iarg < narg) {
     if (!strcmp(arg[*iarg], "device") && *iarg + 1 < narg) {
       device_ = atoi(arg[*iarg + 1]);
@@ -45,6 +50,10 @@ GFMDSolverB200::GFMDSolverB200(LAMMPS *lmp, int narg, int *iarg, char **arg)
     }
     else if (!strcmp(arg[*iarg], "sync")) {
       async_ = false;
+      (*iarg)++;
+    }
+    else if (!strcmp(arg[*iarg], "pin")) {
+      pin_ = true;
       (*iarg)++;
     }
     else break;
@@ -157,7 +166,8 @@ void GFMDSolverB200::set_grid_size(int in_nx, int in_ny, int in_ndof)
     error->one(FLERR, errstr);
   }
 
-  gfmd_b200_pin_host_buffers(handle_, 1);   /* u_xy / f_xy live as long as the fix */
+  /* never register caller-owned memory unless asked to (see the constructor) */
+  gfmd_b200_pin_host_buffers(handle_, pin_ ? 1 : 0);
 }
 
 
@@ -186,8 +196,10 @@ void GFMDSolverB200::set_kernel(StiffnessKernel *kernel, bool normalize)
     int nk = MIN(chunk, nky-k0);
     memory->create(phi, nx*nk, ndof_sq, "GFMDSolverB200::phi");
     fill_phi_buffer(ndof, nx, 0, nx-1, ny, kylo+k0, kylo+k0+nk-1, kernel, phi, normalize, error);
-    check(gfmd_b200_set_phi_columns(handle_, reinterpret_cast<double*>(phi[0]), kylo+k0, nk,
-                                    normalize ? 1 : 0), "gfmd_b200_set_phi_columns");
+    /* fill_phi_buffer has applied exactly the normalisation the caller asked for; the library
+       must not add one (with normalize = false the reference uses the raw table too) */
+    check(gfmd_b200_set_phi_columns(handle_, reinterpret_cast<double*>(phi[0]), kylo+k0, nk, 1),
+          "gfmd_b200_set_phi_columns");
     memory->destroy(phi);
   }
 

@@ -46,6 +46,7 @@ class GFMDSolverB200 : public GFMDSolver {
   struct gfmd_b200 *handle_;
   int device_;
   bool async_;
+  bool pin_;       /* `pin`: page-lock the fix's u_xy / f_xy (see the constructor) */
   StiffnessKernel *kernel_;     /* of the last set_kernel; owned by the fix */
   bool normalize_;
   void check(int rc, const char *what);
