@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""GFMD force-evaluation throughput benchmark (BASELINE.json metric).
+"""GFMD force-evaluation throughput benchmark (BASELINE.json metric: GFMD force-eval steps/s vs
+surface grid at 1/2/4/8 B200; % of the HBM roofline).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # reference CPU solver
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU solver
 
-A "step" is one elastic-force evaluation of `fix gfmd` on a synthetic sc100-type
-surface (ndof 3): gather (atoms -> grid), forward 2-D FFT, Phi(q).u(q) contraction
-with energy and gamma point, inverse FFT, scatter (grid -> atoms).
+A "step" is one elastic-force evaluation of `fix gfmd` on a synthetic sc100 surface (ndof 3,
+stiffness kernel `sc100 height 128`): gather (atoms -> grid), forward 2-D FFT, Phi(q).u(q)
+contraction with energy and gamma point, inverse FFT, scatter (grid -> atoms).
 
-  value   steps/s with atoms and grids resident in HBM (gfmd_b200_full_step)
-  e2e     steps/s through the solver-plugin boundary GFMDSolver::post_force with HOST
-          u_xy / f_xy arrays: H2D of u, the GPU step, D2H of f and of (epot, u0) inside
-          the timed region (gfmd_b200_post_force_host)
-  roofline  the fused column kernel (x-FFT, Phi.u, x-IFFT): algorithmic bytes
-          (16 d + 4 d^2) per cell (stage S3) over its CUDA-event time
-  cpu_baseline  the reference's own solver sources (oracle/_ref, FFTW replaced by
-          oracle/fft_plain.c) on this box's host cores, bounded sample
+Workload.  The SAME surface at every N: 16384 x 16384 (the north-star's strong-scaling grid; it
+fits one B200), x-slabs over the N GPUs -> "scaling": "strong".  At N = 1 the line also carries
+`grid_4096`: the 4096 x 4096 surface the north-star quotes the single-GPU roofline target on, with
+its own roofline, e2e, cpu_baseline and the energy check against an independent CPU value.
+
+  value     steps/s with atoms and grids resident in HBM (gfmd_b200_full_step)
+  e2e       steps/s through the solver-plugin boundary GFMDSolver::post_force with HOST u_xy / f_xy:
+            H2D of u, the GPU step, D2H of f and of (epot, u0) inside the timed region
+  roofline  the kernel with the largest share of the step: algorithmic bytes over its
+            CUDA-event time; `stages` lists every stage the same way
+  parity_max_rel_err  (N > 1) slab-decomposed forces against a single-GPU run of the same surface
+            on rank 0 of the same job; (N = 1) the size-independent identity E = -1/2 sum f.u
+  cpu_baseline / --impl reference  the reference's own solver sources (oracle/_ref; FFTW replaced
+            by oracle/fft_plain.c) on this box's host cores
 """
 import argparse
 import json
@@ -33,29 +40,32 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gfmd_force_eval_steps_per_sec"
 UNIT = "steps/s"
+STRONG_GRID = 16384
+EPOT_4096 = 442.2815166173698      # tools/epot_reference_4096.py (numpy rfft2 + np.linalg.solve, ~16 min of CPU)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--grid", type=int, default=0, help="nx = ny (default 4096)")
+    ap.add_argument("--grid", type=int, default=0, help="nx = ny (default %d)" % STRONG_GRID)
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-4096", action="store_true", help="skip the grid_4096 sub-record at N = 1")
+    ap.add_argument("--no-parity", action="store_true", help="skip the single-GPU comparison at N > 1")
     return ap.parse_args()
 
 
-# weak scaling: 4096 x 4096 cells per GPU ("4096^2 -> 16384^2 surface, slab-sharded over 8 x B200")
-WEAK_GRIDS = {1: (4096, 4096), 2: (4096, 8192), 4: (8192, 8192), 8: (16384, 8192)}
-
-
 def workload(args):
-    if args.grid > 0:
-        return args.grid, args.grid, 3
-    nx, ny = WEAK_GRIDS.get(args.gpus, (4096, 4096))
-    return nx, ny, 3
+    n = args.grid if args.grid > 0 else STRONG_GRID
+    return n, n, 3
+
+
+def workload_string(nx, ny, d):
+    return ("synthetic sc100 surface %dx%d, stiffness kernel `sc100 height 128`, ndof %d, 1 atom/cell"
+            % (nx, ny, d))
 
 
 def measured_peaks():
@@ -122,56 +132,57 @@ class ClockSampler:
 
 # --------------------------------------------------------------- reference ---
 
-def reference_run(nx, ny, d, steps, warmup, budget_s=100.0):
-    """Times the reference's GFMDSolverStatic::post_force (its own sources, FFT3d shim
-    backed by oracle/fft_plain.c with OpenMP) on host arrays.  Returns a dict."""
+REF_SAMPLE_GRID = 4096       # the largest surface the reference arm runs in full (2.4 GB table, ~1.3 s / step)
+
+
+def host_threads():
+    """All host cores, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its children."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    return cores
+
+
+def reference_run(nx, ny, d, steps, warmup):
+    """Times the reference's GFMDSolverStatic::post_force (its own sources, FFT3d shim backed by
+    oracle/fft_plain.c with OpenMP) on host arrays, on all host cores.  Surfaces up to 4096^2 run in
+    full; a larger one is SAMPLED by the full 4096^2 surface and the rate scaled by the cell ratio
+    (flagged `extrapolated`): the reference keeps the full complex d x d table in host memory,
+    38.7 GB at 16384^2 and 45 minutes of single-threaded fill_phi_buffer."""
+    cores = host_threads()
     from oracle import gfmd_oracle as O
     from gfmd_b200 import synthetic
     kind = "reference" if O.ref_available() else "port"
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-
-    def one(nxs, nys, nrep, nwarm):
-        phi = synthetic.phi_full(nxs, nys)
-        u = synthetic.displacement_field(nxs, nys, seed=1, nwaves=8)
-        linf = np.zeros(1)
-        if kind == "reference":
-            s = O.RefSolver(nxs, nys, d, fft_backend=1)
-            s.set_phi(phi, linf)
-            fn = lambda: s.post_force(u)
-        else:
-            fn = lambda: O.c_post_force(u, phi, linf, 1)
-        t_first = time.perf_counter()
+    cores = O.set_fft_threads(cores) or cores     # explicit: independent of the launcher's environment
+    nxs, nys = min(nx, REF_SAMPLE_GRID), min(ny, REF_SAMPLE_GRID)
+    phi = synthetic.phi_full(nxs, nys)
+    u = synthetic.displacement_field(nxs, nys, seed=1, nwaves=8)
+    linf = np.zeros(1)
+    if kind == "reference":
+        s = O.RefSolver(nxs, nys, d, fft_backend=1)
+        s.set_phi(phi, linf)
+        fn = lambda: s.post_force(u)
+    else:
+        fn = lambda: O.c_post_force(u, phi, linf, 1)
+    for _ in range(max(warmup, 1)):
         fn()
-        t_first = time.perf_counter() - t_first
-        for _ in range(max(nwarm - 1, 0)):
-            fn()
-        t0 = time.perf_counter()
-        for _ in range(nrep):
-            fn()
-        dt = (time.perf_counter() - t0) / max(nrep, 1)
-        return dt, t_first
-
-    # choose the sample: the full grid if (steps + warmup) fit the budget, else shrink
-    nxs, nys = nx, ny
-    probe_n = min(nx, 1024)
-    dt_probe, _ = one(probe_n, probe_n, 1, 1)
-    # large grids fall out of the caches and run ~2x slower per cell than the probe
-    est_full = dt_probe * (nx * ny) / float(probe_n * probe_n) * 2.5
-    while est_full * (steps + warmup) * (nxs * nys) / float(nx * ny) > budget_s and nxs > 256:
-        nxs //= 2
-        nys //= 2
-    dt, _ = one(nxs, nys, steps, warmup)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
     scale = (nxs * nys) / float(nx * ny)
-    value = scale / dt
-    sample = ("GFMDSolverStatic::post_force on host u_xy/f_xy, %dx%d ndof %d, %d timed steps"
-              % (nxs, nys, d, steps))
+    sample = ("GFMDSolverStatic::post_force on host u_xy/f_xy, %dx%d ndof %d in full, %d timed steps, %d warm-up"
+              % (nxs, nys, d, steps, warmup))
     if scale != 1.0:
-        sample += ("; grid reduced from %dx%d to bound the run, steps/s scaled by the cell ratio %.4g"
-                   % (nx, ny, scale))
-    return {"value": value, "unit": UNIT, "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": kind,
-            "sample": sample + "; FFT = oracle/fft_plain.c (no FFTW/MPI on this box)",
-            "ms_per_step": 1e3 / value}
+        sample += ("; the %dx%d workload is SAMPLED by this surface and the rate scaled by the cell ratio %.4g "
+                   "(extrapolated)" % (nx, ny, scale))
+    return {"value": scale / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": sample + "; FFT = oracle/fft_plain.c, OpenMP (no FFTW / MPI / LAMMPS on this box)",
+            "ms_per_step": 1e3 * dt / scale, "extrapolated": scale != 1.0,
+            "measured": {"grid": "%dx%d" % (nxs, nys), "value": 1.0 / dt, "ms_per_step": 1e3 * dt},
+            "fft": "oracle/fft_plain.c (not FFTW)"}
 
 
 def main_reference(args):
@@ -179,82 +190,105 @@ def main_reference(args):
     if rank != 0:
         return
     nx, ny, d = workload(args)
-    r = reference_run(nx, ny, d, args.steps, args.warmup)
+    # bounded: the driver's K and W are honoured up to what a few minutes allow (1.3 s / step)
+    steps = min(args.steps, 20)
+    warmup = min(args.warmup, 3)
+    r = reference_run(nx, ny, d, steps, warmup)
+    cb = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "fft")}
     out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-           "scaling": "strong" if args.grid > 0 else "weak",
+           "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "synthetic sc100-type surface %dx%d, ndof %d" % (nx, ny, d),
-                      "step": "GFMDSolver::post_force(u_xy, f_xy) on host arrays"},
-           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "config": {"workload": workload_string(nx, ny, d),
+                      "step": "GFMDSolver::post_force(u_xy, f_xy) on host arrays (solver only: no gather / scatter)",
+                      "steps_requested": args.steps, "warmup_requested": args.warmup},
+           "extrapolated": r["extrapolated"],
+           "reference_fft": "oracle/fft_plain.c, not FFTW: a real FFTW build would be faster",
+           "cpu_baseline": cb,
            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "grid_4096": {"workload": workload_string(REF_SAMPLE_GRID, REF_SAMPLE_GRID, d),
+                         "value": r["measured"]["value"], "unit": UNIT, "ms_per_step": r["measured"]["ms_per_step"],
+                         "extrapolated": False,
+                         "e2e": {"value": r["measured"]["value"], "unit": UNIT}},
            "gpu_launches": 0}
     print(json.dumps(out))
 
 
 # -------------------------------------------------------------------- b200 ---
 
-def main_b200(args):
+def stage_bytes_per_cell(d):
+    """Algorithmic bytes per cell of every stage; long columns (nx > 4096) add the
+    top-digit pass of the column transform, one more read + write of the half spectrum each way."""
+    nu = d // 3
+    return {"gather": 64 * nu + 8 * d, "rows_fwd": 16 * d, "cols_top_fwd": 16 * d, "cols_fused": 16 * d + 4 * d * d,
+            "cols_top_inv": 16 * d, "rows_inv": 16 * d, "scatter": 8 * d + 64 * nu}
+
+
+KERNEL_OF_STAGE = {
+    "gather": "k_gather", "rows_fwd": "k_rows_fwd_*", "cols_top_fwd": "k_cols_top_pass<-1>",
+    "cols_fused": "k_cols_fused_p2_lr (x-FFT + Phi.u + energy + gamma point + x-IFFT)",
+    "cols_top_inv": "k_cols_top_pass<+1>", "rows_inv": "k_rows_inv_*", "scatter": "k_scatter + k_sum_partials"}
+
+
+class Ctx:
+    pass
+
+
+def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clocks):
+    """One workload on the ranks of this job: set-up, timed steps, stage times, e2e.  Returns a dict
+    (rank 0) with everything measured, and keeps the solver + fields in c for the parity check."""
     import torch
     import torch.distributed as dist
     import gfmd_b200
     from gfmd_b200 import synthetic
+    world, rank, local, dev = c.world, c.rank, c.local, c.dev
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    # NCCL prints its version banner with a plain printf to stdout when NCCL_DEBUG is set;
-    # keep stdout for the single JSON line: everything else of this process goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     uid = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
         buf = torch.zeros(gfmd_b200.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(gfmd_b200.get_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
         uid = bytes(buf.cpu().numpy().tobytes())
-
-    nx, ny, d = workload(args)
     s = gfmd_b200.GFMDSolverB200(device=local, rank=rank, nranks=world, unique_id=uid)
     s.set_grid_size(nx, ny, d)
     exchange = "none (single GPU)"
     if world > 1:
         try:
             s.enable_peer_copy(gfmd_b200.all_gather_bytes_fn(dev, world))
-            exchange = "CUDA IPC peer pushes over NVLink (copy engines) + NCCL barrier"
+            exchange = "CUDA IPC peer mappings over NVLink"
         except gfmd_b200.GFMDError as ex:          # still a GPU path: grouped ncclSend/ncclRecv
-            exchange = "NCCL send/recv (peer copy unavailable: %s)" % ex
-    # stiffness table of the reference's `sc100 height 128` kernel (semi-infinite-like elastic
-    # substrate, 128 layers) for this rank's q columns: the host evaluates the per-q matrices
-    # U0, U, V (closed form, gfmd_b200.synthetic.sc100_dynamical_matrices == the plugin's
-    # get_dynamical_matrices), the transfer-matrix recursion runs on the GPU
-    # (gfmd_b200_build_phi_columns)
-    for k0 in range(s.kylo, s.kylo + s.nky, 64):
-        nk = min(64, s.kylo + s.nky - k0)
-        s.build_kernel_columns(synthetic.sc100_dynamical_matrices(nx, ny, k0, nk), k0, height=128)
+            exchange = "NCCL send/recv (peer mappings unavailable: %s)" % ex
+    # stiffness table of the reference's `sc100 height 128` kernel for this rank's q columns: the per-q
+    # matrices U0, U, V in closed form (== the plugin's get_dynamical_matrices, tests/test_oracle.py),
+    # evaluated on the GPU; the transfer-matrix recursion runs on the GPU (gfmd_b200_build_phi_columns*)
+    t_setup = time.time()
+    ch = max(8, min(64, (1 << 20) // nx))
+    for k0 in range(s.kylo, s.kylo + s.nky, ch):
+        nk = min(ch, s.kylo + s.nky - k0)
+        if legacy_inputs:
+            s.build_kernel_columns(synthetic.sc100_dynamical_matrices(nx, ny, k0, nk), k0, height=128)
+        else:
+            s.build_kernel_columns_device(synthetic.sc100_dynamical_matrices_torch(nx, ny, k0, nk, dev), k0, nk,
+                                          height=128)
     s.set_linf(np.zeros(d // 3))
 
     nx_loc, x0 = nx // world, rank * (nx // world)
-    u = synthetic.displacement_field(nx, ny, x0, nx_loc, seed=1, nwaves=8)
-    x, xeq, gid, mask = synthetic.atoms_for_slab(nx, ny, x0, nx_loc, u)
-    nat = x.shape[0]
-    dx = torch.tensor(x, device=dev)
-    dxeq = torch.tensor(xeq, device=dev)
-    dgid = torch.tensor(gid, device=dev)
-    dmask = torch.tensor(mask, device=dev)
+    if legacy_inputs:       # the host generators the stored energy of the 4096^2 surface was computed with
+        u_h = synthetic.displacement_field(nx, ny, x0, nx_loc, seed=1, nwaves=8)
+        x, xeq, gid, mask = synthetic.atoms_for_slab(nx, ny, x0, nx_loc, u_h)
+        du = torch.tensor(u_h, device=dev)
+        dx, dxeq = torch.tensor(x, device=dev), torch.tensor(xeq, device=dev)
+        dgid, dmask = torch.tensor(gid, device=dev), torch.tensor(mask, device=dev)
+    else:                   # every value a function of the global cell index, generated on the GPU
+        du = synthetic.displacement_field_torch(nx, ny, x0, nx_loc, dev, seed=1, nwaves=8)
+        dx, dxeq, dgid, dmask = synthetic.atoms_for_slab_torch(nx, ny, x0, nx_loc, du)
+    nat = dx.shape[0]
     dfat = torch.zeros((nat, 3), device=dev, dtype=torch.float64)
-    stream = torch.cuda.Stream(device=dev)
+    stream = c.stream
     s.set_stream(stream.cuda_stream)
     torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
 
     def step():
         s.full_step(dx, dxeq, dgid, dmask, 1, nat, nat, float(nx), float(ny), dfat)
@@ -264,14 +298,21 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    sampler = ClockSampler(local) if (rank == 0 and want_clocks) else None
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             step()
         # short sustained load so that the clock samples are taken under load
         t_end = time.time() + 0.6
         while time.time() < t_end:
-            for _ in range(10):
+            for _ in range(3):
                 step()
             s.synchronize()
         barrier()
@@ -279,7 +320,7 @@ def main_b200(args):
         t_wall0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         e1.record(stream)
         barrier()
@@ -287,83 +328,76 @@ def main_b200(args):
         ms = e0.elapsed_time(e1)
         launches = s.launch_count() - l0
         res = s.results()
-        t_tail = time.time() + 0.4
+        dfat.zero_()
+        step()                      # forces of exactly one step, for the parity check
+        s.synchronize()
+        f_one = dfat.clone()
+        t_tail = time.time() + 0.3
         while time.time() < t_tail:
-            for _ in range(10):
+            for _ in range(3):
                 step()
             s.synchronize()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clocks = sampler.stop(t_wall0 - 0.7, t_wall1 + 0.5) if sampler else None
-    ms_per_step = ms / args.steps
-    value = 1e3 / ms_per_step
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop(t_wall0 - 0.7, t_wall1 + 0.4) if sampler else None
+    ms_per_step = ms / steps
 
     # solver only (device-resident grids), and per-stage times with CUDA events
     with torch.cuda.stream(stream):
         barrier()
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             s.post_force_device()
         e1.record(stream)
         barrier()
-        ms_solver = e0.elapsed_time(e1) / args.steps
+        ms_solver = max_over_ranks(e0.elapsed_time(e1)) / steps
         s.profile(True)
-        for _ in range(min(args.steps, 20)):
+        for _ in range(min(steps, 10)):
             step()
         s.profile(False)
         barrier()
     stages = s.stage_times()
     stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in stages.items()}
 
-    # roofline of the dominant kernel (fused columns): stage S3 bytes, this rank's cells
+    # roofline per stage: algorithmic bytes of this rank's cells over the stage's CUDA-event time
     peaks, peak_src = measured_peaks()
     cells_loc = nx * ny / world
-    alg_bytes = (16 * d + 4 * d * d) * cells_loc
-    t_cols = stage_ms["cols_fused"] * 1e-3
-    achieved = alg_bytes / t_cols / 1e9 if t_cols > 0 else 0.0
-    # DRAM bytes of that kernel from the committed ncu --set full capture (same grid, 1 GPU)
-    traffic = None
-    try:
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")))
-        if world == 1 and (nx, ny) == (4096, 4096):
-            for kname, m in summ.items():
-                if "k_cols_fused" in kname:
-                    def gb(x):
-                        v, unit = x.split()[:2]
-                        return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
-                    traffic = gb(m["dram__bytes_read.sum"]) + gb(m["dram__bytes_write.sum"])
-    except Exception:
-        traffic = None
-    roofline = {"kernel": "k_cols_fused_p2_lr (x-FFT + Phi.u + energy + gamma point + x-IFFT) + k_finalize",
-                "bound": "hbm",
-                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": stage_ms["cols_fused"],
+    bpc = stage_bytes_per_cell(d)
+    roof_stages = {}
+    for k, b in bpc.items():
+        t = stage_ms.get(k, 0.0)
+        if t > 0:
+            a = b * cells_loc / (t * 1e-3) / 1e9
+            roof_stages[k] = {"kernel": KERNEL_OF_STAGE[k], "ms": t, "alg_bytes_per_cell": b, "achieved": a,
+                              "frac": a / peaks["hbm_gbs"]}
+    solver_keys = ("rows_fwd", "cols_top_fwd", "cols_fused", "cols_top_inv", "rows_inv")
+    dom = max((k for k in solver_keys if k in roof_stages), key=lambda k: roof_stages[k]["ms"])
+    rs = roof_stages[dom]
+    roofline = {"kernel": rs["kernel"], "stage": dom, "bound": "hbm", "achieved": rs["achieved"],
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": rs["frac"],
+                "traffic": None,    # ncu dram bytes per launch live in profiles/ (r2_ncu_*.csv); not re-measured here
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": rs["alg_bytes_per_cell"] * cells_loc, "kernel_ms": rs["ms"],
+                "share_of_step": rs["ms"] / ms_per_step,
+                "dominant_of": "FFT + contraction stages of this workload (gather / scatter listed in `stages`)",
+                "stages": roof_stages,
                 "solver_bytes_per_step": (80 * d + 4 * d * d) * cells_loc,
                 "solver_frac": ((80 * d + 4 * d * d) * cells_loc / (ms_solver * 1e-3) / 1e9) / peaks["hbm_gbs"]}
 
-    nvlink = None
+    # size-independent property on the timed workload (linf = 0): E = -1/2 sum_r f.u  
+    fu = float((f_one * (dx - dxeq)).sum().item())
+    esum = res["epot"]
     if world > 1:
-        per_dir = 8.0 * d * cells_loc * (world - 1) / world          # bytes sent per GPU per transpose
-        t_x = (stage_ms["exchange_fwd"] + stage_ms["exchange_inv"]) * 1e-3
-        t_cols = (stage_ms["exchange_fwd"] + stage_ms["cols_fused"] + stage_ms["exchange_inv"]) * 1e-3
-        nvlink = {"bytes_out_per_gpu_per_step": 2 * per_dir,
-                  "non_overlapped_exchange_ms": t_x * 1e3,
-                  "columns_plus_exchange_ms": t_cols * 1e3,
-                  # the pushes run on copy engines underneath the column kernel: their rate is at
-                  # least bytes / (whole column stage)
-                  "link_rate_lower_bound_gbs_per_dir": (2 * per_dir / t_cols / 1e9) if t_cols > 0 else None,
-                  "peak_gbs_per_dir": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
-                  "note": "transposes overlap the column kernel chunk by chunk; exchange_inv includes "
-                          "the u0 all-reduce"}
+        t = torch.tensor([fu, esum], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        fu, esum = float(t[0].item()), float(t[1].item())
+    identity_err = abs(esum + 0.5 * fu) / abs(esum) if esum else None
 
     # end to end through the plugin boundary with pinned host buffers
-    n_e2e = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, 10))
-    hu = torch.tensor(u.reshape(d, nx_loc * ny)).pin_memory()
-    hf = torch.empty_like(hu).pin_memory()
+    n_e2e = e2e_steps if e2e_steps > 0 else max(3, min(steps, 10))
+    hu = torch.empty((d, nx_loc * ny), dtype=torch.float64, pin_memory=True)
+    hu.copy_(du.reshape(d, nx_loc * ny))
+    hf = torch.empty((d, nx_loc * ny), dtype=torch.float64, pin_memory=True)
+    torch.cuda.synchronize()
 
     def time_e2e():
         for _ in range(2):
@@ -373,60 +407,247 @@ def main_b200(args):
         for _ in range(n_e2e):
             s.post_force(hu, hf)
         barrier()
-        dt = (time.perf_counter() - t0) / n_e2e
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
+        return max_over_ranks((time.perf_counter() - t0) / n_e2e)
 
-    # the library default first (that is `e2e`), then -- where the per-dof host pipeline can take
-    # effect at all (single rank, specialised row kernels) -- the other setting for comparison
     hp_default = s.host_pipeline()
     dt_e2e = time_e2e()
     grid_bytes = d * nx_loc * ny * 8
     e2e = {"value": 1.0 / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": grid_bytes,
            "d2h_bytes_per_step": grid_bytes + 8 * (d + 1), "steps": n_e2e,
-           "call": "gfmd_b200_post_force_host (GFMDSolver::post_force boundary), pinned host u_xy/f_xy",
-           "host_pipeline": hp_default}
-    if hp_default or s.host_pipeline(True):
-        s.host_pipeline(not hp_default)
-        e2e["value_with_host_pipeline_%s" % ("off" if hp_default else "on")] = 1.0 / time_e2e()
-    s.host_pipeline(hp_default)
+           "call": "gfmd_b200_post_force_host (GFMDSolver::post_force boundary), pinned host u_xy/f_xy, per rank",
+           "host_pipeline": hp_default,
+           "pcie_floor_ms": 2 * grid_bytes / 55e9 * 1e3}
+    del hu, hf
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    out = {"value": 1e3 / ms_per_step, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
+           "clocks": clocks, "e2e": e2e, "roofline": roofline,
+           "solver_only": {"value": 1e3 / ms_solver, "unit": UNIT, "ms_per_step": ms_solver},
+           "stage_ms": stage_ms, "epot": esum, "energy_identity_rel_err": identity_err,
+           "setup_s": t_setup, "exchange": exchange, "kernels": s.describe(),
+           "l2": "inputs larger than L2 (%.0f MB of atoms + grids per rank and step)"
+                 % ((nat * (48 + 16 + 24) + 2 * grid_bytes) / 1e6)}
+    c.solver, c.f_one, c.nat = s, f_one, nat
+    return out
+
+
+def slab_parity(c, nx, ny, d):
+    """N > 1: rank 0 runs the same surface on ITS GPU alone (single-GPU handle, same inputs) and
+    compares every rank's slab forces and the summed energy with it."""
+    import torch
+    import torch.distributed as dist
+    import gfmd_b200
+    from gfmd_b200 import synthetic
+    world, rank, dev = c.world, c.rank, c.dev
+    nx_loc = nx // world
+    n_loc = nx_loc * ny
+    e_slab = torch.tensor([c.solver.results()["epot"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(e_slab)
+    out = None
+    if rank == 0:
+        one = gfmd_b200.GFMDSolverB200(device=c.local)
+        one.set_grid_size(nx, ny, d)
+        ch = max(8, min(64, (1 << 20) // nx))
+        for k0 in range(0, one.nky, ch):
+            nk = min(ch, one.nky - k0)
+            one.build_kernel_columns_device(synthetic.sc100_dynamical_matrices_torch(nx, ny, k0, nk, dev), k0, nk,
+                                            height=128)
+        one.set_linf(np.zeros(d // 3))
+        du = synthetic.displacement_field_torch(nx, ny, 0, nx, dev, seed=1, nwaves=8)
+        dx, dxeq, dgid, dmask = synthetic.atoms_for_slab_torch(nx, ny, 0, nx, du)
+        del du
+        nat = dx.shape[0]
+        fat = torch.zeros((nat, 3), device=dev, dtype=torch.float64)
+        torch.cuda.synchronize()
+
+        def step1():
+            one.full_step(dx, dxeq, dgid, dmask, 1, nat, nat, float(nx), float(ny), fat)
+        for _ in range(2):
+            step1()
+        one.synchronize()
+        t0 = time.perf_counter()
+        n1 = 5
+        for _ in range(n1):
+            step1()
+        one.synchronize()
+        ms1 = (time.perf_counter() - t0) / n1 * 1e3
+        fat.zero_()
+        step1()
+        r1 = one.results()
+        fmax = float(fat.abs().max().item())
+        err = float((c.f_one - fat[:n_loc]).abs().max().item()) / fmax
+        buf = torch.empty((n_loc, 3), device=dev, dtype=torch.float64)
+        for r in range(1, world):
+            dist.recv(buf, src=r)
+            err = max(err, float((buf - fat[r * n_loc:(r + 1) * n_loc]).abs().max().item()) / fmax)
+        out = {"parity_max_rel_err": err,
+               "parity_epot_rel_err": abs(float(e_slab.item()) - r1["epot"]) / abs(r1["epot"]),
+               "parity_against": "single-GPU run of the same %dx%d surface on rank 0 of this job (gfmd_b200_full_step)"
+                                 % (nx, ny),
+               "single_gpu_same_box": {"value": 1e3 / ms1, "unit": UNIT, "ms_per_step": ms1, "steps": n1,
+                                       "timing": "wall clock around %d synchronised steps" % n1}}
+        one.close()
+    else:
+        dist.send(c.f_one, dst=0)
+    dist.barrier()
+    return out
+
+
+def latency_configs(c):
+    """BASELINE configs C1-C3 (small grids): device time of one solver step through the captured CUDA
+    graph (gfmd_b200_use_graph) next to the reference solver's CPU time on the same table."""
+    import torch
+    import gfmd_b200
+    out = {}
+    cases = [("C1_sc100_128x128", "tests/TEST_Hertz_sc100_128x128"),
+             ("C2_fcc111_64x37", "tests/TEST_Hertz_fcc111_64x37_2"),
+             ("C3_fcc100_two_layers_10x10", "tests/TEST_energy_conservation_two_layers")]
+    for name, ref in cases:
+        p = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        if not os.path.exists(p):
+            continue
+        z = np.load(p)
+        nx, ny, d = int(z["nx"]), int(z["ny"]), int(z["ndof"])
+        s = gfmd_b200.GFMDSolverB200(device=c.local)
+        s.set_grid_size(nx, ny, d)
+        s.set_kernel(z["phi"], z["linf"])
+        s.set_stream(c.stream.cuda_stream)
+        u = torch.tensor(z["u_uniform"].reshape(d, nx * ny), device=c.dev)
+        f = torch.empty_like(u)
+        rec = {"grid": "%dx%d" % (nx, ny), "ndof": d, "reference_test": ref}
+        for mode in ("launches", "graph"):
+            s.use_graph(mode == "graph")
+            with torch.cuda.stream(c.stream):
+                for _ in range(20):
+                    s.post_force_device(u, f)
+                s.synchronize()
+                n = 500
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(c.stream)
+                for _ in range(n):
+                    s.post_force_device(u, f)
+                e1.record(c.stream)
+                s.synchronize()
+                us = e0.elapsed_time(e1) / n * 1e3
+            rec["us_per_step_" + mode] = us
+        rec["steps_per_s"] = 1e6 / min(rec["us_per_step_launches"], rec["us_per_step_graph"])
         try:
-            r = reference_run(nx, ny, d, 3, 1, budget_s=25.0)
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+            from oracle import gfmd_oracle as O
+            if O.ref_available():
+                rs = O.RefSolver(nx, ny, d, fft_backend=1)
+                rs.set_phi(z["phi"], z["linf"])
+                uu = np.ascontiguousarray(z["u_uniform"])
+                for _ in range(3):
+                    rs.post_force(uu)
+                t0 = time.perf_counter()
+                nrep = 50
+                for _ in range(nrep):
+                    rs.post_force(uu)
+                rec["reference_cpu_us_per_step"] = (time.perf_counter() - t0) / nrep * 1e6
+        except Exception as ex:
+            rec["reference_cpu_us_per_step"] = None
+            rec["reference_error"] = repr(ex)
+        s.close()
+        out[name] = rec
+    return out
+
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    c = Ctx()
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL prints its version banner with a plain printf to stdout when NCCL_DEBUG is set;
+    # keep stdout for the single JSON line: everything else of this process goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device("cuda", c.local)
+    c.stream = torch.cuda.Stream(device=c.dev)
+    world, rank = c.world, c.rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=c.dev)
+
+    nx, ny, d = workload(args)
+    main = run_config(c, nx, ny, d, False, args.steps, args.warmup, args.e2e_steps, True)
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = slab_parity(c, nx, ny, d)
+
+    nvlink = None
+    if world > 1:
+        cells_loc = nx * ny / world
+        per_dir = 8.0 * d * cells_loc * (world - 1) / world          # bytes sent per GPU per transpose
+        sm = main["stage_ms"]
+        nvlink = {"bytes_out_per_gpu_per_step": 2 * per_dir,
+                  "peak_gbs_per_dir": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
+                  "min_transfer_ms_per_step": 2 * per_dir / 770e9 * 1e3,
+                  "non_overlapped_exchange_ms": sm.get("exchange_fwd", 0.0) + sm.get("exchange_inv", 0.0),
+                  "frac_of_step_if_exposed": (2 * per_dir / 770e9 * 1e3) / main["ms_per_step"]}
+    c.solver.close()
+    del c.f_one
+
+    sub = lat = cpu = None
+    if world == 1 and rank == 0:
+        if not args.no_4096 and args.grid in (0, STRONG_GRID):
+            torch.cuda.empty_cache()
+            sub = run_config(c, 4096, 4096, d, True, max(args.steps, 50), max(args.warmup, 5), args.e2e_steps, False)
+            c.solver.close()
+            sub["workload"] = workload_string(4096, 4096, d)
+            sub["epot_reference"] = EPOT_4096
+            sub["epot_reference_source"] = ("stored constant; regenerate with tools/epot_reference_4096.py "
+                                            "(independent numpy computation, ~16 min of CPU)")
+            sub["epot_rel_err"] = abs(sub["epot"] - EPOT_4096) / EPOT_4096
+            sub.pop("clocks", None)
+        try:
+            lat = latency_configs(c)
+        except Exception as ex:
+            lat = {"error": repr(ex)}
+        if not args.no_cpu_baseline:
+            try:
+                r = reference_run(nx, ny, d, 3, 1)
+                cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "fft")}
+                cpu["measured"] = r["measured"]
+                if sub is not None:
+                    sub["cpu_baseline"] = dict(r["measured"], unit=UNIT, cores=r["cores"], kind=r["kind"],
+                                               sample="GFMDSolverStatic::post_force, 4096x4096 in full, 3 timed steps; "
+                                                      "FFT = oracle/fft_plain.c")
+            except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-               "scaling": "strong" if args.grid > 0 else "weak",   # --grid fixes the total work
-               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "synthetic surface %dx%d, stiffness kernel `sc100 height 128`, ndof %d, "
-                                      "1 atom/cell" % (nx, ny, d),
+        out = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_string(nx, ny, d),
                           "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",
-                          "decomposition": "x-slabs over %d GPU(s); transposes: %s" % (world, exchange),
-                          "l2": "inputs larger than L2 (%.0f MB of atoms+grids per step)" %
-                                ((nat * (48 + 16 + 24) + 2 * grid_bytes) / 1e6),
-                          "kernels": s.describe()},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-               "cpu_baseline": cpu, "nvlink": nvlink,
-               "solver_only": {"value": 1e3 / ms_solver, "unit": UNIT, "ms_per_step": ms_solver},
-               "stage_ms": stage_ms, "epot": res["epot"]}
-        # full-size check: the energy of this exact workload computed independently on the CPU
-        # (tools/epot_reference_4096.py: numpy rfft2 + np.linalg.solve recursion, ~16 min)
-        if world == 1 and (nx, ny, d) == (4096, 4096, 3):
-            out["epot_reference"] = 442.2815166173698
-            out["epot_rel_err"] = abs(res["epot"] - 442.2815166173698) / 442.2815166173698
+                          "decomposition": "x-slabs over %d GPU(s); transposes: %s" % (world, main["exchange"]),
+                          "l2": main["l2"], "kernels": main["kernels"],
+                          "inputs": "displacement field and atoms generated on the GPU from the global cell index "
+                                    "(gfmd_b200.synthetic.*_torch), atoms in grid order",
+                          "latency": lat},
+               "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
+               "roofline": main["roofline"], "cpu_baseline": cpu, "nvlink": nvlink,
+               "solver_only": main["solver_only"], "stage_ms": main["stage_ms"], "epot": main["epot"],
+               "energy_identity_rel_err": main["energy_identity_rel_err"], "setup_s": main["setup_s"]}
+        if parity:
+            out.update(parity)
+        elif world == 1:
+            out["parity_max_rel_err"] = main["energy_identity_rel_err"]
+            out["parity_against"] = "size-independent identity E = -1/2 sum f.u on the timed surface (linf = 0)"
+        if sub is not None:
+            out["grid_4096"] = sub
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
-    s.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -250,8 +250,10 @@ long long gfmd_b200_launch_count(const gfmd_b200_t *h);
 
 /* Per-stage device times (CUDA events on the handle's stream), accumulated while
  * profiling is on.  stage ids: 0 gather, 1 rows_fwd, 2 exchange_fwd, 3 cols_fused,
- * 4 exchange_inv, 5 rows_inv, 6 scatter.  ms[7], counts[7]. */
-#define GFMD_B200_NSTAGES 7
+ * 4 exchange_inv, 5 rows_inv, 6 scatter, 7 cols_top_fwd, 8 cols_top_inv (the top-digit passes
+ * of long columns, nx > 4096, when the column stage runs unchunked; otherwise inside stage 3).
+ * ms[9], counts[9]. */
+#define GFMD_B200_NSTAGES 9
 int gfmd_b200_profile(gfmd_b200_t *h, int on);
 int gfmd_b200_get_stage_times(gfmd_b200_t *h, double ms[GFMD_B200_NSTAGES],
                               long long counts[GFMD_B200_NSTAGES]);

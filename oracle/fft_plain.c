@@ -264,6 +264,19 @@ void fftp_destroy(fftp_plan *p)
   free(p);
 }
 
+/* Threads of the 2-D transform: 0 = the OpenMP default.  Set explicitly by callers that must not
+ * depend on the environment (torchrun exports OMP_NUM_THREADS=1 to its children). */
+static int g_fftp_threads = 0;
+void fftp_set_threads(int n) { g_fftp_threads = n > 0 ? n : 0; }
+int fftp_get_threads(void)
+{
+#ifdef _OPENMP
+  return g_fftp_threads > 0 ? g_fftp_threads : omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
 /* data: interleaved complex, row-major [nx][ny] (index ix*ny+iy); in place;
  * sign -1: forward exp(-i q r); +1: backward exp(+i q r); unnormalised. */
 void fftp_exec_2d(const fftp_plan *p, double *data, int sign)
@@ -272,7 +285,7 @@ void fftp_exec_2d(const fftp_plan *p, double *data, int sign)
   cplx *d = (cplx *) data;
   enum { CB = 8 };
 #ifdef _OPENMP
-#pragma omp parallel
+#pragma omp parallel num_threads(fftp_get_threads())
 #endif
   {
     size_t sl = scratch_len(p->py);

@@ -370,8 +370,29 @@ def rlib():
         lib.ref_solver_post_force_dump.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_char_p]
         lib.ref_solver_dump_tables.argtypes = [ctypes.c_void_p]
         lib.ref_set_fft_backend.argtypes = [ctypes.c_int]
+        lib.fftp_set_threads.argtypes = [ctypes.c_int]
+        lib.fftp_get_threads.restype = ctypes.c_int
         _rlib = lib
     return _rlib
+
+
+def set_fft_threads(n):
+    """Threads of the substitute FFT (oracle/fft_plain.c) in every oracle library that is loaded or will
+    be: explicit, so that a launcher's OMP_NUM_THREADS=1 (torchrun) cannot shrink the CPU baseline.
+    Returns the thread count in effect."""
+    got = 0
+    if ref_available():
+        rlib().fftp_set_threads(int(n))
+        got = rlib().fftp_get_threads()
+    try:
+        lib = clib()
+        lib.fftp_set_threads.argtypes = [ctypes.c_int]
+        lib.fftp_get_threads.restype = ctypes.c_int
+        lib.fftp_set_threads(int(n))
+        got = got or lib.fftp_get_threads()
+    except Exception:
+        pass
+    return got
 
 
 class RefKernel:

@@ -33,7 +33,7 @@ def random_case(nx, ny, d):
 
 
 VARIANTS = [(64, 4096, 3, 4104), (6, 4096, 6, 4104), (32, 8192, 3, 8200), (2, 8192, 6, 8200), (16, 16384, 3, 16392),
-            (3, 16384, 6, 16392)]
+            (3, 16384, 6, 16392), (16, 16384, 3, 16393), (4, 16384, 6, 16393)]
 
 
 @pytest.mark.parametrize("nx,ny,d,variant", VARIANTS)
@@ -45,6 +45,7 @@ def test_r16_rows_against_oracle(B, nx, ny, d, variant, oracle_libs, monkeypatch
     s = B.GFMDSolverB200()
     s.set_grid_size(nx, ny, d)
     assert "variant %d" % variant in s.describe() and "k_rows_*_r16" in s.describe(), s.describe()
+    assert ("2-CTA clusters" in s.describe()) == (variant == ny + 9)
     s.set_kernel(phi, linf)
     uu = np.ascontiguousarray(u.reshape(d, nx * ny))
     f = np.full_like(uu, np.nan)
@@ -79,3 +80,28 @@ def test_r16_rows_match_default_rows(B, ny, variant, monkeypatch):
         s.close()
     assert rel_err(out[1][0], out[0][0]) < 1e-12
     assert abs(out[1][1] - out[0][1]) <= 1e-12 * abs(out[0][1])
+
+
+def test_cluster_rows_bit_identical_to_single_cta_rows(B, monkeypatch):
+    """ny = 16384: the two-CTA-cluster row kernels (variant ny + 9: staging accesses split by frequency,
+    partner points through distributed shared memory) run the same arithmetic per element as the
+    one-CTA-per-row kernels (ny + 8): forces and energy must agree bit for bit."""
+    from gfmd_b200 import synthetic
+    nx, ny, d = 64, 16384, 3
+    rng = np.random.default_rng(9)
+    u = rng.uniform(-1e-3, 1e-3, size=(d, nx * ny))
+    out = []
+    for v in (ny + 8, ny + 9):
+        monkeypatch.setenv("GFMD_B200_ROWS_VARIANT", str(v))
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        assert "variant %d" % v in s.describe(), s.describe()
+        for k0 in range(0, s.nky, 1024):
+            nk = min(1024, s.nky - k0)
+            s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+        s.set_linf(np.array([0.25]))
+        f = np.full_like(u, np.nan)
+        e = s.post_force(u, f)
+        out.append((f, e))
+        s.close()
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]

@@ -8,7 +8,7 @@ import gfmd_b200
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 ny = int(sys.argv[2]) if len(sys.argv) > 2 else nx
 d = 3
-variants = [0] + [ny + k for k in ((0, 1, 3, 5, 6, 7, 8) if ny == 4096 else (3, 5, 6, 7, 8) if ny == 8192 else (5, 8))]   # 0 = the library default
+variants = [0] + [ny + k for k in ((0, 1, 3, 5, 6, 7, 8) if ny == 4096 else (3, 5, 6, 7, 8) if ny == 8192 else (5, 8, 9))]   # 0 = the library default
 if os.environ.get('AB_ONLY'): variants = [0] + [int(v) for v in os.environ['AB_ONLY'].split(',')]
 rounds = int(os.environ.get('AB_ROUNDS', '2'))
 u = torch.rand((d, nx * ny), device='cuda', dtype=torch.float64) - 0.5

@@ -381,7 +381,9 @@ struct gfmd_b200 {
   bool pin_host = false;
 
   bool profiling = false;
-  cudaEvent_t ev[GFMD_B200_NSTAGES + 1] = {};
+  cudaEvent_t ev[8] = {};                  // marks 0..7 around stages 0..6
+  cudaEvent_t ev_top[2] = {};              // long columns: behind the forward / before the backward top-digit pass
+  bool top_split = false;                  // ev_top were recorded in the last profiled step
   double stage_ms[GFMD_B200_NSTAGES] = {};
   long long stage_cnt[GFMD_B200_NSTAGES] = {};
 
@@ -637,13 +639,15 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   }
   h->phi_cols_set.assign(g.nky_loc > 0 ? g.nky_loc : 0, 0);
   h->phi_set = g.nky_loc == 0;      // a rank without q columns has no table to wait for
-  for (int i = 0; i <= GFMD_B200_NSTAGES; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 2; ++i) cudaEventCreate(&h->ev_top[i]);
 
   char rows[160], cols[200], buf[512];
   FastRowsCfg frc;
   if (h->fast_rows && fast_rows_cfg(h->fast_rows, frc))
     snprintf(rows, sizeof(rows), "k_rows_*_%s half-length len %d, %d rows/CTA, %d threads, smem %zu [fast, variant %d%s]",
-             h->fast_rows == h->g.ny + 8 ? "r16" : "p2", frc.nr, frc.rb, frc.t, fast_rows_smem(frc), h->fast_rows,
+             h->fast_rows == h->g.ny + 9 ? "r16c (2-CTA clusters)" : h->fast_rows == h->g.ny + 8 ? "r16" : "p2", frc.nr, frc.rb,
+             frc.t, h->fast_rows == h->g.ny + 9 ? fast_rows_smem_cluster(frc) : fast_rows_smem(frc), h->fast_rows,
              h->fast_rows == fast_rows_default(h->g.ny) ? " = default" : "");
   else
     snprintf(rows, sizeof(rows), "k_rows_* %s len %d%s, %d rows/CTA, %d threads, smem %zu",
@@ -1009,6 +1013,7 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   // GFMD_B200_PEER_DIRECT: no transposes -- the column stage loads and stores the pieces in the peers' memory
   const bool direct = g.P > 1 && h->ipc_on && h->peer_direct && h->fast_cols == 4096 && h->peer_stage[(g.rank + 1) % g.P];
   const bool pipelined = g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->fast_rows && h->nchunks > 1 && !direct;
+  h->top_split = false;
   if (pipelined) {
     int rc = pipelined_step(h, d_u, A, B, B2);
     if (rc) return rc;
@@ -1058,9 +1063,11 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
       if (h->fast_cols) {
         const double2 *tw_sub = h->cols_top ? h->fft_sub.desc.core.tw : h->fft_cols.desc.core.tw;
         // direct: long columns are assembled in B by the pulling top-digit pass and transformed there in place
+        h->top_split = h->profiling && h->cols_top > 0;
         int rc = fast_cols_fused(h->fast_cols, h->cols_top, B, direct ? B : A, g, tw_sub, h->fft_cols.desc.core.tw,
                                  h->d_phi, h->d_linf, h->d_epart, h->d_res, h->num_sms, h->stream, &h->launches, 0, -1,
-                                 peer_store ? &po : nullptr, direct ? &pin : nullptr);
+                                 peer_store ? &po : nullptr, direct ? &pin : nullptr,
+                                 h->top_split ? h->ev_top : nullptr);
         if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
       } else {
         launch_generic_cols(h, B, A, &nepart);
@@ -1183,13 +1190,23 @@ int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool 
 void accumulate_stage_times(gfmd_b200 *h, int first, int last)
 {
   // events first..last+1 were recorded; requires a stream sync by the caller
-  for (int s = first; s <= last; ++s) {
+  auto add = [&](int stage, cudaEvent_t a, cudaEvent_t b) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]) == cudaSuccess) {
-      h->stage_ms[s] += ms;
-      h->stage_cnt[s]++;
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+      h->stage_ms[stage] += ms;
+      h->stage_cnt[stage]++;
     }
+  };
+  for (int s = first; s <= last; ++s) {
+    if (s == 3 && h->top_split) {       // long columns: top-digit passes (stages 7, 8) around the fused kernel
+      add(7, h->ev[3], h->ev_top[0]);
+      add(3, h->ev_top[0], h->ev_top[1]);
+      add(8, h->ev_top[1], h->ev[4]);
+      continue;
+    }
+    add(s, h->ev[s], h->ev[s + 1]);
   }
+  cudaGetLastError();
 }
 
 int solver_step(gfmd_b200 *h, const double *d_u, double *d_f)
@@ -1526,8 +1543,10 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   free_fft(h->fft_rows);
   free_fft(h->fft_cols);
   free_fft(h->fft_sub);
-  for (int i = 0; i <= GFMD_B200_NSTAGES; ++i)
+  for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_top[i]) cudaEventDestroy(h->ev_top[i]);
   for (int i = 0; i < 2; ++i)
     if (h->hp_stream[i]) cudaStreamDestroy(h->hp_stream[i]);
   for (int i = 0; i < GFMD_B200_MAX_NDOF; ++i) {

@@ -606,6 +606,7 @@ k_rows_inv_p2(const double2 *__restrict__ stage, double *__restrict__ f, GridDes
 }  // namespace gfmd
 
 #include "kernels_rows_r16.cuh"
+#include "kernels_rows_cluster.cuh"
 
 namespace gfmd {
 
@@ -633,6 +634,9 @@ inline bool fast_rows_cfg(int variant, FastRowsCfg &c)
     case 4097: c = {2048, 4, 512}; return true;
     case 8192: case 8195: case 8197: case 8198: case 8199: case 8200: c = {4096, 2, 512}; return true;
     case 16384: case 16389: case 16392: c = {8192, 1, 512}; return true;
+#ifndef GFMD_CUDA_EMU
+    case 16393: c = {8192, 1, 512}; return true;      // two-CTA clusters (kernels_rows_cluster.cuh)
+#endif
     default: return false;
   }
 }
@@ -666,6 +670,11 @@ inline int fast_rows_default(int ny) { return (ny == 4096 || ny == 8192 || ny ==
 inline size_t fast_rows_smem(const FastRowsCfg &c)
 {
   return sizeof(double2) * ((size_t) c.rb * c.nr + 504 + c.rb);
+}
+// cluster variants: the row(s) plus the exchange buffer (8 points per thread and the Nyquist point)
+inline size_t fast_rows_smem_cluster(const FastRowsCfg &c)
+{
+  return sizeof(double2) * ((size_t) c.rb * c.nr + 8 * (size_t) c.t + 8);
 }
 
 inline size_t fast_cols_smem(int d, int nx) { return sizeof(double2) * ((size_t) d * nx + 504); }
@@ -718,6 +727,16 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
           e = cudaFuncSetAttribute(k_rows_inv_r16w<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) fast_rows_smem(rc));
         break;
+#ifndef GFMD_CUDA_EMU
+      case 16393:
+        if (g.nx_loc % 2) { fast_rows = 0; break; }
+        e = cudaFuncSetAttribute(k_rows_fwd_r16c<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) fast_rows_smem_cluster(rc));
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(k_rows_inv_r16c<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) fast_rows_smem_cluster(rc));
+        break;
+#endif
       case 8200:
         e = cudaFuncSetAttribute(k_rows_fwd_r16h<4096, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) fast_rows_smem(rc));
@@ -784,6 +803,9 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
     case 4104: k_rows_fwd_r16<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     case 8200: k_rows_fwd_r16h<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     case 16392: k_rows_fwd_r16w<8192, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+#ifndef GFMD_CUDA_EMU
+    case 16393: k_rows_fwd_r16c<8192, 512><<<grid, 512, fast_rows_smem_cluster(rc), s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+#endif
     default: return 1;
   }
   ++*launches;
@@ -806,6 +828,9 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
     case 4104: k_rows_inv_r16<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     case 8200: k_rows_inv_r16h<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     case 16392: k_rows_inv_r16w<8192, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+#ifndef GFMD_CUDA_EMU
+    case 16393: k_rows_inv_r16c<8192, 512><<<grid, 512, fast_rows_smem_cluster(rc), s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+#endif
     default: return 1;
   }
   ++*launches;
@@ -819,8 +844,9 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
                            const double2 *tw_sub, const double2 *tw_nx, const double *phi, const double *linf,
                            double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches,
                            int kl0 = 0, int kl1 = -1, const PeerOut *peer_out = nullptr,
-                           const PeerOut *peer_in = nullptr)
+                           const PeerOut *peer_in = nullptr, cudaEvent_t *ev_split = nullptr)
 {
+  // ev_split (profiling): [0] recorded behind the forward top-digit pass, [1] before the backward one
   // peer_out (variant 4096 in slab mode): the last kernel of the stage stores the result pieces
   // straight into their owners' return buffers instead of sout.  peer_in (only together with
   // peer_out): the first kernel of the stage loads the pieces straight from the ranks that produced
@@ -849,6 +875,7 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
     else k_cols_top_pass<2, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
   }
+  if (ev_split && top > 0) cudaEventRecord(ev_split[0], s);
   switch (variant) {
     case 2048:
       k_cols_fused_p2<3, 2048, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, tw_sub, phi, linf, epart, res);
@@ -884,6 +911,7 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
     default: return 1;
   }
   ++*launches;
+  if (ev_split && top > 0) cudaEventRecord(ev_split[1], s);
   if (top == 1) {
     if (peer_out) k_cols_top_pass<1, +1, true><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1, *peer_out);
     else k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);

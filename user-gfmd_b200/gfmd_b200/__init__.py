@@ -21,9 +21,9 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgfmd_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)
-NSTAGES = 7
+NSTAGES = 9
 STAGE_NAMES = ("gather", "rows_fwd", "exchange_fwd", "cols_fused", "exchange_inv", "rows_inv",
-               "scatter")
+               "scatter", "cols_top_fwd", "cols_top_inv")
 UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
