@@ -216,12 +216,20 @@ def main_reference(args):
 
 # -------------------------------------------------------------------- b200 ---
 
-def stage_bytes_per_cell(d):
+def stage_bytes_per_cell(d, fused_gather=False, fused_scatter=False):
     """Algorithmic bytes per cell of every stage; long columns (nx > 4096) add the
-    top-digit pass of the column transform, one more read + write of the half spectrum each way."""
+    top-digit pass of the column transform, one more read + write of the half spectrum each way.
+    Fused atom I/O (cell -> atom map): the forward rows read x, xeq (48 B) and the map (4 B) per atom
+    and write the half spectrum (8 B per dof); the inverse rows read it and the map and update f
+    (24 B read + 24 B written per atom) -- the u_xy / f_xy grids do not exist."""
     nu = d // 3
-    return {"gather": 64 * nu + 8 * d, "rows_fwd": 16 * d, "cols_top_fwd": 16 * d, "cols_fused": 16 * d + 4 * d * d,
-            "cols_top_inv": 16 * d, "rows_inv": 16 * d, "scatter": 8 * d + 64 * nu}
+    b = {"gather": 64 * nu + 8 * d, "rows_fwd": 16 * d, "cols_top_fwd": 16 * d, "cols_fused": 16 * d + 4 * d * d,
+         "cols_top_inv": 16 * d, "rows_inv": 16 * d, "scatter": 8 * d + 64 * nu}
+    if fused_gather:
+        b["rows_fwd"] = 52 * nu + 8 * d
+    if fused_scatter:
+        b["rows_inv"] = 8 * d + 52 * nu
+    return b
 
 
 KERNEL_OF_STAGE = {
@@ -288,6 +296,8 @@ def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clock
     stream = c.stream
     s.set_stream(stream.cuda_stream)
     torch.cuda.synchronize()
+    # fused gather / scatter through a cell -> atom map (built once; a fix rebuilds it when it reneighbours)
+    fused_io = os.environ.get("BENCH_FUSED_IO", "1") != "0" and s.build_cell_map(dgid, dmask, 1, nat, nat)
     t_setup = time.time() - t_setup
 
     def step():
@@ -361,13 +371,19 @@ def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clock
     # roofline per stage: algorithmic bytes of this rank's cells over the stage's CUDA-event time
     peaks, peak_src = measured_peaks()
     cells_loc = nx * ny / world
-    bpc = stage_bytes_per_cell(d)
+    fused_gather = fused_io and stage_ms.get("gather", 0.0) == 0.0
+    bpc = stage_bytes_per_cell(d, fused_gather, fused_io)
+    kernel_of = dict(KERNEL_OF_STAGE)
+    if fused_gather:
+        kernel_of["rows_fwd"] = "k_rows_fwd_* with fused gather (atoms -> half spectrum)"
+    if fused_io:
+        kernel_of["rows_inv"] = "k_rows_inv_* with fused scatter (half spectrum -> atoms)"
     roof_stages = {}
     for k, b in bpc.items():
         t = stage_ms.get(k, 0.0)
         if t > 0:
             a = b * cells_loc / (t * 1e-3) / 1e9
-            roof_stages[k] = {"kernel": KERNEL_OF_STAGE[k], "ms": t, "alg_bytes_per_cell": b, "achieved": a,
+            roof_stages[k] = {"kernel": kernel_of[k], "ms": t, "alg_bytes_per_cell": b, "achieved": a,
                               "frac": a / peaks["hbm_gbs"]}
     solver_keys = ("rows_fwd", "cols_top_fwd", "cols_fused", "cols_top_inv", "rows_inv")
     dom = max((k for k in solver_keys if k in roof_stages), key=lambda k: roof_stages[k]["ms"])
@@ -423,7 +439,7 @@ def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clock
            "clocks": clocks, "e2e": e2e, "roofline": roofline,
            "solver_only": {"value": 1e3 / ms_solver, "unit": UNIT, "ms_per_step": ms_solver},
            "stage_ms": stage_ms, "epot": esum, "energy_identity_rel_err": identity_err,
-           "setup_s": t_setup, "exchange": exchange, "kernels": s.describe(),
+           "setup_s": t_setup, "exchange": exchange, "kernels": s.describe(), "fused_atom_io": bool(fused_io),
            "l2": "inputs larger than L2 (%.0f MB of atoms + grids per rank and step)"
                  % ((nat * (48 + 16 + 24) + 2 * grid_bytes) / 1e6)}
     c.solver, c.f_one, c.nat = s, f_one, nat
@@ -630,6 +646,7 @@ def main_b200(args):
                           "step": "gather + forward FFT + Phi.u + inverse FFT + scatter, device resident",
                           "decomposition": "x-slabs over %d GPU(s); transposes: %s" % (world, main["exchange"]),
                           "l2": main["l2"], "kernels": main["kernels"],
+                          "fused_atom_io": main["fused_atom_io"],
                           "inputs": "displacement field and atoms generated on the GPU from the global cell index "
                                     "(gfmd_b200.synthetic.*_torch), atoms in grid order",
                           "latency": lat},

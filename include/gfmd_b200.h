@@ -212,6 +212,19 @@ int gfmd_b200_gather(gfmd_b200_t *h, const double *d_x, const double *d_xeq, int
 int gfmd_b200_scatter(gfmd_b200_t *h, const double *d_fgrid, const int *d_gid,
                       const int *d_mask, int groupbit, int nall, int nlocal, double *d_f);
 
+/* Optional: cell -> atom map for the FUSED form of gfmd_b200_full_step (radix-16 row kernels, ny =
+ * 4096 / 8192 / 16384): the forward row transform reads x and xeq itself and the inverse one adds the
+ * forces to the atoms itself, so the grids u_xy / f_xy never exist in memory (one HBM pass less on
+ * either side).  Same index arithmetic as gfmd_b200_gather incl. the lattice shift (fix_gfmd.cpp:
+ * 734-760).  *usable = 1 if every cell of this handle's brick holds exactly one atom of the group --
+ * only then are gather / scatter through the map the reference's loops exactly (a local atom AND its
+ * ghost image in one cell, or an empty cell, keep the separate kernels) -- and the handle's row
+ * kernels have the fused form.  Call again whenever gid / mask / the atom order change (LAMMPS:
+ * reneighbouring steps); full_step uses the map only when called with the same arrays and counts. */
+int gfmd_b200_build_cell_map(gfmd_b200_t *h, int *d_gid, const int *d_mask, int groupbit, int nall,
+                             int nlocal, int dxshift, int dyshift, int *usable);
+int gfmd_b200_drop_cell_map(gfmd_b200_t *h);
+
 /* gather + post_force + scatter on the library-owned grids, one call. */
 int gfmd_b200_full_step(gfmd_b200_t *h, const double *d_x, const double *d_xeq, int *d_gid,
                         const int *d_mask, int groupbit, int nall, int nlocal, double xprd,

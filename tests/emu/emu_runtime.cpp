@@ -276,6 +276,8 @@ cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaS
 cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = &g_stream_obj; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = &g_stream_obj; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = &g_stream_obj; return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *a, int *b) { *a = 0; *b = -1; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }

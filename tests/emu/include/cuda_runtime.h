@@ -29,6 +29,7 @@
 
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+struct alignas(8) int2 { int x, y; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;
@@ -62,6 +63,7 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int delta)
 }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }       /* fibers: one OS thread */
 static inline double atomicAdd(double *p, double v) { double o = *p; *p += v; return o; }
+static inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
 static inline long long clock64() { return 0; }
 using std::fma;
 static inline int min(int a, int b) { return a < b ? a : b; }
@@ -102,6 +104,8 @@ cudaError_t cudaMemset(void *, int, size_t);
 cudaError_t cudaMemsetAsync(void *, int, size_t, cudaStream_t = nullptr);
 cudaError_t cudaStreamCreate(cudaStream_t *);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *, unsigned, int);
+cudaError_t cudaDeviceGetStreamPriorityRange(int *, int *);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0);

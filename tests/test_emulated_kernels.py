@@ -211,6 +211,59 @@ def test_full_step(B, oracle_libs):
     s.close()
 
 
+@pytest.mark.parametrize("nx,ny,nu", [(4, 4096, 1), (2, 8192, 1), (2, 4096, 2)])
+def test_fused_atom_io_equals_separate_gather_scatter(B, nx, ny, nu, oracle_libs):
+    """gfmd_b200_build_cell_map + full_step: the radix-16 row kernels read x / xeq and add the forces
+    to the atoms themselves.  Atoms in random order, wrapped into the box (minimum image exercised),
+    a few of them ghosts (index >= nlocal): forces on the atoms bit-identical to the separate
+    k_gather / k_scatter path, counters equal, force sum to rounding; against the oracle to 1e-11.
+    A map with an empty cell or a doubly occupied one is refused (the separate kernels stay)."""
+    O = oracle_libs
+    d = 3 * nu
+    rng = np.random.default_rng(nx * ny + nu)
+    x, xeq, gid, mask = make_atoms(nx, ny, nu, rng)
+    mask[:] = 3
+    n = x.shape[0]
+    nlocal = n - n // 9
+    phi, linf, _ = random_case(nx, ny, d)
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    assert "k_rows_*_r16" in s.describe(), s.describe()
+    s.set_kernel(phi, linf)
+    f0 = rng.standard_normal((n, 3))
+    out = []
+    for fused in (False, True):
+        if fused:
+            assert s.build_cell_map(gid, mask, 2, n, nlocal) is True
+        df = f0.copy()
+        l0 = s.launch_count()
+        s.full_step(x, xeq, gid, mask, 2, n, nlocal, float(nx), float(ny), df)
+        r = s.results()
+        out.append((df, r, s.launch_count() - l0))
+    (fa, ra, la), (fb, rb, lb) = out
+    assert la == lb + 2                                   # no k_gather, k_scatter; k_sum_fsum_io replaces k_sum_partials
+    assert np.array_equal(fa, fb)
+    assert ra["epot"] == rb["epot"] and np.array_equal(ra["u0"], rb["u0"])
+    assert ra["natoms_gathered"] == rb["natoms_gathered"] == n and ra["natoms_scattered"] == rb["natoms_scattered"] == n
+    assert np.abs(ra["fsum"] - rb["fsum"]).max() <= 1e-12 * max(1.0, np.abs(ra["fsum"]).max())
+    u_ref, _ = O.gather(x, xeq, gid.copy(), mask, 2, nx, ny, d, float(nx), float(ny))
+    f_ref, e_ref, _ = O.post_force(u_ref.reshape(d, nx, ny), phi, linf)
+    fa_ref, fsum_ref, _ = O.scatter(f_ref.reshape(d, nx * ny), gid, mask, 2, f0.copy(), nlocal=nlocal, nx=nx, ny=ny)
+    assert rel_err(fb - f0, fa_ref - f0) < TOL and abs(rb["epot"] - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(rb["fsum"] - fsum_ref).max() <= 1e-9 * max(1.0, np.abs(fsum_ref).max())
+    # an atom outside the group leaves its cell empty; a second atom in an occupied cell: not usable
+    m2 = mask.copy()
+    m2[3] = 1
+    assert s.build_cell_map(gid, m2, 2, n, nlocal) is False
+    g2 = gid.copy()
+    g2[5] = g2[6]
+    assert s.build_cell_map(g2, mask, 2, n, nlocal) is False
+    df = f0.copy()
+    s.full_step(x, xeq, gid, mask, 2, n, nlocal, float(nx), float(ny), df)      # separate kernels again
+    assert np.array_equal(df, fa)
+    s.close()
+
+
 def test_async_pre_force_and_errors(B):
     g = load_golden("small_sc100_16x12")
     nx, ny, d = int(g["nx"]), int(g["ny"]), int(g["ndof"])

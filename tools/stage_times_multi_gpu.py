@@ -43,10 +43,19 @@ SETTINGS = {
     'chunks2': {'GFMD_B200_CHUNKS': '2'},
     'chunks1': {'GFMD_B200_CHUNKS': '1'},
     'rows_r8': {'GFMD_B200_ROWS_VARIANT': str(ny)},                # the round-1 row kernels
+    'direct_seq': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_CHUNKS': '1'},      # no transposes, not overlapped
+    'direct_x8': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '8'},
+    'direct_x12': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '12'},
+    'direct_x24': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '24'},
+    'direct_x32': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '32'},
+    'direct_x24c4': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '24', 'GFMD_B200_CHUNKS': '4'},
+    'direct_c4': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_CHUNKS': '4'},
+    'pushes': {'GFMD_B200_PEER_DIRECT': '0'},                      # copy-engine pushes, chunked pipeline
 }
 names = os.environ['AB'].split(',') if os.environ.get('AB') else list(SETTINGS)
 if world == 1: names = [n for n in names if n in ('default', 'rows_fused', 'rows_r16')]
-KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_PEER_DIRECT', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH', 'GFMD_B200_SYNC')
+KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_PEER_DIRECT', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH', 'GFMD_B200_SYNC',
+        'GFMD_B200_XCHG_SMS')
 nxl = nx // world
 u = torch.rand((d, nxl * ny), device=dev, dtype=torch.float64, generator=torch.Generator(dev).manual_seed(7 + rank)) - 0.5
 f0 = None

@@ -333,6 +333,12 @@ struct gfmd_b200 {
   static constexpr int kMaxChunks = 8;
   int nchunks = 1, chunk_kl = 0;
   cudaEvent_t ev_chunk[kMaxChunks][kMaxRanks] = {}, ev_k2[kMaxChunks] = {}, ev_row[GFMD_B200_MAX_NDOF] = {};
+  // overlapped step without transposes (long columns): the top-digit passes pull / push the pieces over
+  // NVLink on two side streams, chunk by chunk, next to the fused column kernel on a reduced grid
+  cudaStream_t pull_stream = nullptr, push_stream = nullptr;
+  cudaEvent_t ev_pull[kMaxChunks] = {}, ev_rows_done = nullptr, ev_push_done = nullptr;
+  int xchg_sms = 24;                          // SMs for the pulling and as many for the pushing pass (GFMD_B200_XCHG_SMS);
+                                              // measured at 8 GPUs, 16384^2: 16 -> 4.74 ms, 24 -> 4.09 ms, 32 -> 4.24 ms per solver step
   double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
   int fsum_part_cap = 0;
   StepResults *d_res = nullptr, *h_res = nullptr;
@@ -356,6 +362,15 @@ struct gfmd_b200 {
   bool aux_attr_set = false;
   double2 *d_spec = nullptr;          // Phi.u~ of the last spectrum request
   double *d_cavg = nullptr;
+
+  // fused atom I/O (gfmd_b200_build_cell_map): cell -> atom map and what it was built from
+  int *d_cmap = nullptr, *d_cmap_cnt = nullptr;
+  bool cmap_valid = false;
+  const int *cmap_gid = nullptr, *cmap_mask = nullptr;
+  int cmap_groupbit = 0, cmap_nall = 0, cmap_nlocal = 0;
+  int cmap_cnt[3] = {0, 0, 0};
+  double *d_fsum_io = nullptr;          // [nx_loc / rb][ndof] partial force sums of the fused scatter
+  const AtomIO *io_fwd = nullptr, *io_inv = nullptr;   // set around one enqueue_solver by the fused full step
 
   bool phi_set = false;
   std::vector<char> phi_cols_set;
@@ -947,6 +962,83 @@ int pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, doub
   return 0;
 }
 
+// Multi-GPU step WITHOUT transposes, overlapped (long columns, nx >= 8192; default for more than two
+// ranks).  The exchange is done by the top-digit passes of the column transform themselves: the
+// forward pass LOADS each piece of a column from the rank whose row kernels produced it, the backward
+// pass STORES each result piece into its owner's return buffer (k_cols_top_pass<.., PEER>, NVLink
+// traffic issued by the SMs: 640 GB/s per direction at 8 GPUs against 418 GB/s of copy-engine pushes
+// and 564 GB/s of grouped ncclSend/ncclRecv, profiles/r2_stage_times_8gpu_16384x16384.txt).  Per
+// ky chunk:   pull stream  top-digit pass <- peers            (NVLink RX bound)
+//             main stream  fused column kernel on num_sms - xchg_sms SMs (HBM / FP64 bound)
+//             push stream  top-digit pass -> peers            (NVLink TX bound)
+// so that chunk c + 1 is pulled and chunk c - 1 pushed while chunk c is transformed.  Ordering across
+// ranks: flag words (rows complete -> pull; pushes complete -> backward rows), no collective.
+int direct_pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *B, double2 *B2)
+{
+  const GridDesc &g = h->g;
+  const size_t blk = (size_t) g.d * g.kyb * g.nx_loc;
+  const double2 *tw_sub = h->fft_sub.desc.core.tw;
+  const int nc = h->nchunks, ck = h->chunk_kl;
+  PeerOut po{}, pin{};
+  for (int r = 0; r < g.P; ++r) {
+    po.p[r] = (r == g.rank ? B2 : h->peer_recv[1][r]) + g.rank * blk;
+    pin.p[r] = (r == g.rank ? A : h->peer_stage[r]) + g.rank * blk;
+  }
+  stage_mark(h, 1);
+  int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, 0, -1, h->io_fwd);
+  if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
+  stage_mark(h, 2);
+  // my rows are complete: tell every peer, and let my pull stream wait for theirs
+  for (int k = 1; k < g.P; ++k)
+    if ((rc = signal_peer(h, h->stream, (g.rank + k) % g.P, kFlagRows + g.rank))) return rc;
+  CU(h, cudaEventRecord(h->ev_rows_done, h->stream));
+  CU(h, cudaStreamWaitEvent(h->pull_stream, h->ev_rows_done, 0));
+  for (int k = 1; k < g.P; ++k) {
+    const int p = (g.rank + k) % g.P;
+    if (stream_wait32_geq(h->pull_stream, h->flags + kFlagRows + p, h->seq))
+      return fail(h, GFMD_B200_ECUDA, "cuStreamWaitValue32 on the rows flag of rank %d failed", p);
+  }
+  stage_mark(h, 3);
+  // the fused kernel needs a whole SM per CTA: leave xchg_sms SMs to the pulling and as many to the pushing pass
+  const int cols_sms = h->num_sms - 2 * h->xchg_sms > 8 ? h->num_sms - 2 * h->xchg_sms : h->num_sms;
+  for (int c = 0; c < nc; ++c) {
+    const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
+    // forward top-digit pass of chunk c, inputs straight from the peers' row outputs, into B
+    rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
+                         h->d_epart, h->d_res, h->num_sms, h->pull_stream, &h->launches, k0, k1, &po, &pin, nullptr, 1,
+                         h->xchg_sms);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "top-digit pull launch failed");
+    CU(h, cudaEventRecord(h->ev_pull[c], h->pull_stream));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_pull[c], 0));
+    rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
+                         h->d_epart, h->d_res, cols_sms, h->stream, &h->launches, k0, k1, &po, &pin, nullptr, 2);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+    CU(h, cudaEventRecord(h->ev_k2[c], h->stream));
+    CU(h, cudaStreamWaitEvent(h->push_stream, h->ev_k2[c], 0));
+    // backward top-digit pass of chunk c, results straight into the owners' return buffers
+    rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
+                         h->d_epart, h->d_res, h->num_sms, h->push_stream, &h->launches, k0, k1, &po, &pin, nullptr, 4,
+                         h->xchg_sms);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "top-digit push launch failed");
+  }
+  k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc << h->cols_top, h->d_res);
+  h->launches++;
+  stage_mark(h, 4);
+  // u0 (rank 0, written by chunk 0's fused kernel) and the return flags ride behind the last push
+  CU(h, cudaStreamWaitEvent(h->push_stream, h->ev_k2[nc - 1], 0));
+  for (int k = 1; k < g.P; ++k) {
+    const int r = (g.rank + k) % g.P;
+    rc = push_u0(h, h->push_stream, r);
+    if (!rc) rc = signal_peer(h, h->push_stream, r, kFlagRet + g.rank);
+    if (rc) return rc;
+  }
+  CU(h, cudaEventRecord(h->ev_push_done, h->push_stream));
+  CU(h, cudaStreamWaitEvent(h->stream, h->ev_push_done, 0));      // B and the peers' buffers are free for the next step
+  rc = wait_peers(h, kFlagRet, 1);
+  if (!rc) rc = take_u0(h);
+  return rc;
+}
+
 // Host-pipelined solver step (single rank, specialised row kernels): the upload of dof k + 1
 // runs on a copy stream while the rows of dof k are transformed; the row results of the way
 // back are handed to the download stream dof by dof (events hp_out, consumed by
@@ -998,6 +1090,19 @@ int enqueue_solver_hostpipe(gfmd_b200 *h, const double *u_host)
   return 0;
 }
 
+bool step_is_direct(const gfmd_b200 *h)
+{
+  const GridDesc &g = h->g;
+  return g.P > 1 && h->ipc_on && h->peer_direct && h->fast_cols == 4096 && h->peer_stage[(g.rank + 1) % g.P];
+}
+
+// multi-GPU step with per-dof row launches (pipelined_step): no fused gather there
+bool step_is_pipelined(const gfmd_b200 *h)
+{
+  const GridDesc &g = h->g;
+  return g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->fast_rows && h->nchunks > 1 && !step_is_direct(h);
+}
+
 // the kernels of one solver step, enqueued on h->stream
 int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
 {
@@ -1011,16 +1116,20 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   if (g.P > 1) ++h->seq;
 
   // GFMD_B200_PEER_DIRECT: no transposes -- the column stage loads and stores the pieces in the peers' memory
-  const bool direct = g.P > 1 && h->ipc_on && h->peer_direct && h->fast_cols == 4096 && h->peer_stage[(g.rank + 1) % g.P];
-  const bool pipelined = g.P > 1 && h->ipc_on && h->fast_cols == 4096 && h->fast_rows && h->nchunks > 1 && !direct;
+  const bool direct = step_is_direct(h);
+  const bool pipelined = step_is_pipelined(h);
   h->top_split = false;
-  if (pipelined) {
+  if (direct && h->cols_top > 0 && h->nchunks > 1 && h->sync_flags && h->fast_rows && h->pull_stream) {
+    int rc = direct_pipelined_step(h, d_u, A, B, B2);
+    if (rc) return rc;
+  } else if (pipelined) {
     int rc = pipelined_step(h, d_u, A, B, B2);
     if (rc) return rc;
   } else {
   stage_mark(h, 1);
   if (h->fast_rows) {
-    int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
+    int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, 0, -1,
+                           h->io_fwd);
     if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
   } else {
     if (h->even)
@@ -1099,7 +1208,8 @@ int enqueue_solver(gfmd_b200 *h, const double *d_u, double *d_f)
   }   // !pipelined
   stage_mark(h, 5);
   if (h->fast_rows) {
-    int rc = fast_rows_inv(h->fast_rows, B2, d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches);
+    int rc = fast_rows_inv(h->fast_rows, B2, d_f, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, 0, -1,
+                           h->io_inv);
     if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_inv launch failed");
   } else {
     if (h->even)
@@ -1213,7 +1323,7 @@ int solver_step(gfmd_b200 *h, const double *d_u, double *d_f)
 {
   if (!h->phi_set) return fail(h, GFMD_B200_ESTATE, "post_force before set_phi (set_kernel)");
   if (d_u == d_f) return fail(h, GFMD_B200_EINVAL, "u and f must be different buffers");
-  const bool graph_ok = h->want_graph && h->g.P == 1 && !h->profiling;
+  const bool graph_ok = h->want_graph && h->g.P == 1 && !h->profiling && !h->io_fwd && !h->io_inv;
   if (!graph_ok) {
     int rc = enqueue_solver(h, d_u, d_f);
     if (rc) return rc;
@@ -1428,13 +1538,25 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     CU(h, cudaMemset(h->d_barrier, 0, sizeof(double)));
     CU(h, cudaDeviceSynchronize());
   }
+  // Which exchange: more than two ranks with long columns (nx >= 8192) default to the overlapped step
+  // WITHOUT transposes (direct_pipelined_step; needs gfmd_b200_ipc_import_stage), everything else to the
+  // copy-engine pushes (pipelined_step).  Measured at 16384 x 16384: 8 GPUs 4.46 ms against 5.14 ms even
+  // before the overlap existed (4.09 ms with it), 2 GPUs 13.3 ms against 12.6 ms.  GFMD_B200_PEER_DIRECT=0/1 overrides.
+  h->peer_direct = h->g.P >= 4 && h->cols_top > 0 && h->fast_cols == 4096;
+  if (const char *e = getenv("GFMD_B200_PEER_STORE")) h->peer_store = atoi(e) != 0;
+  if (const char *e = getenv("GFMD_B200_PEER_DIRECT")) h->peer_direct = atoi(e) != 0;
+  if (const char *e = getenv("GFMD_B200_XCHG_SMS")) h->xchg_sms = atoi(e);
+  if (h->xchg_sms < 0) h->xchg_sms = 0;
   // chunking of the column stage: whole waves of the persistent column kernel per chunk
   {
-    int want = 4;
+    const bool overlapped_direct = h->peer_direct && h->cols_top > 0;
+    int want = overlapped_direct ? 8 : 4;
     if (const char *e = getenv("GFMD_B200_CHUNKS")) want = atoi(e);
     if (want < 1) want = 1;
     if (want > gfmd_b200::kMaxChunks) want = gfmd_b200::kMaxChunks;
-    const int per_wave = h->num_sms >> h->cols_top > 0 ? h->num_sms >> h->cols_top : 1;   // ky per wave
+    int sms = h->num_sms;
+    if (overlapped_direct && sms - 2 * h->xchg_sms > 8) sms -= 2 * h->xchg_sms;     // the fused kernel's share of the SMs
+    const int per_wave = sms >> h->cols_top > 0 ? sms >> h->cols_top : 1;   // ky per wave
     int waves = (h->g.kyb + per_wave * want - 1) / (per_wave * want);
     if (waves < 1) waves = 1;
     h->chunk_kl = waves * per_wave;
@@ -1444,6 +1566,7 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
       if (!h->ev_row[i]) CU(h, cudaEventCreateWithFlags(&h->ev_row[i], cudaEventDisableTiming));
     for (int c = 0; c < h->nchunks; ++c) {
       if (!h->ev_k2[c]) CU(h, cudaEventCreateWithFlags(&h->ev_k2[c], cudaEventDisableTiming));
+      if (!h->ev_pull[c]) CU(h, cudaEventCreateWithFlags(&h->ev_pull[c], cudaEventDisableTiming));
       for (int r = 0; r < h->g.P; ++r)
         if (!h->ev_chunk[c][r]) CU(h, cudaEventCreateWithFlags(&h->ev_chunk[c][r], cudaEventDisableTiming));
     }
@@ -1461,8 +1584,6 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     if (h->desc.find("sync: ") == std::string::npos)
       h->desc += h->sync_flags ? " | sync: stream flags in peer memory" : " | sync: NCCL all-reduce barriers";
   }
-  if (const char *e = getenv("GFMD_B200_PEER_STORE")) h->peer_store = atoi(e) != 0;
-  if (const char *e = getenv("GFMD_B200_PEER_DIRECT")) h->peer_direct = atoi(e) != 0;
   if (h->peer_store && !h->peer_direct && h->fast_cols == 4096 && h->desc.find("return: ") == std::string::npos)
     h->desc += " | return: in-kernel peer stores";
   return 0;
@@ -1503,8 +1624,19 @@ int gfmd_b200_ipc_import_stage(gfmd_b200_t *h, const char *all_handles)
                   "in use)", r, cudaGetErrorString(e));
     h->peer_stage[r] = (double2 *) p;
   }
+  if (h->peer_direct && h->fast_cols == 4096 && h->cols_top > 0 && !h->pull_stream) {
+    int least = 0, greatest = 0;
+    CU(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CU(h, cudaStreamCreateWithPriority(&h->pull_stream, cudaStreamNonBlocking, greatest));
+    CU(h, cudaStreamCreateWithPriority(&h->push_stream, cudaStreamNonBlocking, greatest));
+    CU(h, cudaEventCreateWithFlags(&h->ev_rows_done, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->ev_push_done, cudaEventDisableTiming));
+  }
   if (h->peer_direct && h->fast_cols == 4096 && h->desc.find("transposes: ") == std::string::npos)
-    h->desc += " | transposes: none, in-kernel peer loads and stores";
+    h->desc += h->cols_top > 0 && h->nchunks > 1 && h->sync_flags
+                   ? " | transposes: none, in-kernel peer loads and stores, overlapped chunk by chunk (" +
+                         std::to_string(h->nchunks) + " chunks, " + std::to_string(h->xchg_sms) + " SMs for the exchange)"
+                   : " | transposes: none, in-kernel peer loads and stores";
   return 0;
 }
 
@@ -1527,6 +1659,12 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
     if (h->ev_join[r]) cudaEventDestroy(h->ev_join[r]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->pull_stream) cudaStreamDestroy(h->pull_stream);
+  if (h->push_stream) cudaStreamDestroy(h->push_stream);
+  if (h->ev_rows_done) cudaEventDestroy(h->ev_rows_done);
+  if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
+  for (int c = 0; c < gfmd_b200::kMaxChunks; ++c)
+    if (h->ev_pull[c]) cudaEventDestroy(h->ev_pull[c]);
   for (int i = 0; i < GFMD_B200_MAX_NDOF; ++i)
     if (h->ev_row[i]) cudaEventDestroy(h->ev_row[i]);
   for (int c = 0; c < gfmd_b200::kMaxChunks; ++c) {
@@ -1539,6 +1677,7 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   cudaFree(h->d_phi); cudaFree(h->d_linf); cudaFree(h->d_epart); cudaFree(h->d_fsum_part);
   cudaFree(h->d_res); cudaFree(h->d_tw_ny);
   cudaFree(h->d_spec); cudaFree(h->d_cavg);
+  cudaFree(h->d_cmap); cudaFree(h->d_cmap_cnt); cudaFree(h->d_fsum_io);
   if (h->h_res) cudaFreeHost(h->h_res);
   free_fft(h->fft_rows);
   free_fft(h->fft_cols);
@@ -1933,14 +2072,98 @@ int gfmd_b200_scatter(gfmd_b200_t *h, const double *d_fgrid, const int *d_gid, c
   return 0;
 }
 
+int gfmd_b200_build_cell_map(gfmd_b200_t *h, int *d_gid, const int *d_mask, int groupbit, int nall, int nlocal,
+                             int dxshift, int dyshift, int *usable)
+{
+  if (!h || !d_gid || !d_mask) return fail(h, GFMD_B200_EINVAL, "build_cell_map: null argument");
+  if (usable) *usable = 0;
+  int rc = set_device(h);
+  if (rc) return rc;
+  const GridDesc &g = h->g;
+  const size_t ncell = (size_t) (g.d / 3) * g.nx_loc * g.ny;
+  h->cmap_valid = false;
+  if (!h->d_cmap) {
+    CU(h, dmalloc(h, &h->d_cmap, ncell));
+    CU(h, dmalloc(h, &h->d_cmap_cnt, (size_t) 4));
+  }
+  CU(h, cudaMemsetAsync(h->d_cmap, 0xff, sizeof(int) * ncell, h->stream));          // -1: empty cell
+  CU(h, cudaMemsetAsync(h->d_cmap_cnt, 0, sizeof(int) * 4, h->stream));
+  if (nall > 0) {
+    k_build_cellmap<<<atom_blocks(h, nall), kAtomTile, 0, h->stream>>>(d_gid, d_mask, groupbit, nall, g, dxshift,
+                                                                       dyshift, h->d_cmap, h->d_cmap_cnt);
+    h->launches++;
+  }
+  CU(h, cudaMemcpyAsync(h->cmap_cnt, h->d_cmap_cnt, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaGetLastError());
+  // usable: every cell of the brick holds exactly one atom of the group (then gather and scatter
+  // through the map are the reference's loops exactly), and this handle's row kernels have the fused form
+  const bool bijective = h->cmap_cnt[1] == 0 && h->cmap_cnt[2] == 0 && (size_t) h->cmap_cnt[0] == ncell;
+  h->cmap_valid = bijective && fast_rows_has_atomio(h->fast_rows);
+  h->cmap_gid = d_gid; h->cmap_mask = d_mask;
+  h->cmap_groupbit = groupbit; h->cmap_nall = nall; h->cmap_nlocal = nlocal;
+  if (h->cmap_valid && !h->d_fsum_io) {
+    FastRowsCfg frc;
+    fast_rows_cfg(h->fast_rows, frc);
+    CU(h, dmalloc(h, &h->d_fsum_io, (size_t) (g.nx_loc / frc.rb) * g.d));
+  }
+  if (usable) *usable = h->cmap_valid ? 1 : 0;
+  return 0;
+}
+
+int gfmd_b200_drop_cell_map(gfmd_b200_t *h)
+{
+  if (!h) return GFMD_B200_EINVAL;
+  h->cmap_valid = false;
+  return 0;
+}
+
 int gfmd_b200_full_step(gfmd_b200_t *h, const double *d_x, const double *d_xeq, int *d_gid, const int *d_mask,
                         int groupbit, int nall, int nlocal, double xprd, double yprd, double *d_f)
 {
-  int rc = gfmd_b200_gather(h, d_x, d_xeq, d_gid, d_mask, groupbit, nall, xprd, yprd, 0, 0, nullptr);
+  if (!h) return GFMD_B200_EINVAL;
+  // fused path: a valid cell map built from exactly these arrays (gfmd_b200_build_cell_map)
+  const bool mapped = h->cmap_valid && h->cmap_gid == d_gid && h->cmap_mask == d_mask && h->cmap_groupbit == groupbit &&
+                      h->cmap_nall == nall && h->cmap_nlocal == nlocal && d_x && d_xeq && d_f && !h->want_graph;
+  if (!mapped) {
+    int rc = gfmd_b200_gather(h, d_x, d_xeq, d_gid, d_mask, groupbit, nall, xprd, yprd, 0, 0, nullptr);
+    if (rc) return rc;
+    rc = solver_step(h, h->d_u, h->d_f);
+    if (rc) return rc;
+    return gfmd_b200_scatter(h, nullptr, d_gid, d_mask, groupbit, nall, nlocal, d_f);
+  }
+  int rc = set_device(h);
   if (rc) return rc;
+  AtomIO io{};
+  io.x = d_x; io.xeq = d_xeq; io.fat = d_f; io.cmap = h->d_cmap; io.fsum_part = h->d_fsum_io;
+  io.xprd = xprd; io.yprd = yprd; io.nlocal = nlocal;
+  // the multi-GPU pipeline launches its forward rows dof by dof (each launch would re-read the atoms):
+  // separate gather there, fused scatter everywhere
+  const bool fuse_gather = !step_is_pipelined(h);
+  if (!fuse_gather) {
+    rc = gfmd_b200_gather(h, d_x, d_xeq, d_gid, d_mask, groupbit, nall, xprd, yprd, 0, 0, nullptr);
+    if (rc) return rc;
+  } else if (h->profiling) {
+    cudaEventRecord(h->ev[0], h->stream);          // stage 0 (gather) is empty: it lives inside rows_fwd
+    cudaEventRecord(h->ev[1], h->stream);
+  }
+  h->io_fwd = fuse_gather ? &io : nullptr;
+  h->io_inv = &io;
   rc = solver_step(h, h->d_u, h->d_f);
+  h->io_fwd = h->io_inv = nullptr;
   if (rc) return rc;
-  return gfmd_b200_scatter(h, nullptr, d_gid, d_mask, groupbit, nall, nlocal, d_f);
+  FastRowsCfg frc;
+  fast_rows_cfg(h->fast_rows, frc);
+  k_sum_fsum_io<<<1, 256, 0, h->stream>>>(h->d_fsum_io, h->g.nx_loc / frc.rb, h->g.d, h->d_res->fsum);
+  h->launches++;
+  // counters as the separate kernels report them: every atom of the map is gathered and scattered
+  if (fuse_gather) {
+    CU(h, cudaMemcpyAsync(&h->d_res->natoms_gathered, h->d_cmap_cnt, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaMemsetAsync(&h->d_res->n_out_of_range, 0, sizeof(int), h->stream));
+  }
+  CU(h, cudaMemcpyAsync(&h->d_res->natoms_scattered, h->d_cmap_cnt, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CU(h, cudaGetLastError());
+  return 0;
 }
 
 int gfmd_b200_get_results(gfmd_b200_t *h, double *epot, double *u0, double fsum[3], int counters[3])

@@ -243,8 +243,10 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 // PEER, DIR = +1: the results go to the pieces' owners (`peer`, see PeerOut) instead of back into
 // `stage`.  PEER, DIR = -1: the inputs come from the ranks that produced them (`peer`) and the
 // results go to `stage`.
-template <int LR, int DIR, bool PEER = false>
-__global__ void __launch_bounds__(256)
+// U = items per thread and iteration: the PEER forms run on a FEW SMs next to the fused column kernel
+// (direct_pipelined_step) and need U * R independent 16-byte NVLink loads in flight per thread.
+template <int LR, int DIR, bool PEER = false, int T = 256, int U = 1>
+__global__ void __launch_bounds__(T)
 k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx, int kl0,
                 int kl1, PeerOut peer = PeerOut())
 {
@@ -252,39 +254,55 @@ k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2
   const int S = g.nx >> LR;
   const int xmask = (1 << lnxl) - 1;
   const long long total = (long long) g.d * (kl1 - kl0) * S;
-  for (long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long) gridDim.x * blockDim.x) {
-    const int n = (int) (idx % S);
-    const int col = (int) (idx / S);
-    const int dof = col % g.d, kl = kl0 + col / g.d;
-    double2 v[R];
-    size_t a[R];
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long idx0 = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += stride * U) {
+    double2 v[U][R];
+    size_t a[U][R];
+    int nn[U];
+    size_t rel[U];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int x = n + r * S;
-      a[r] = ((((size_t) (x >> lnxl) * g.d + dof) * g.kyb + kl) << lnxl) + (size_t) (x & xmask);
-      if (PEER && DIR < 0) v[r] = peer.p[x >> lnxl][((((size_t) dof) * g.kyb + kl) << lnxl) + (size_t) (x & xmask)];
-      else v[r] = stage[a[r]];
-    }
-    if (DIR > 0) {
+    for (int k = 0; k < U; ++k) {
+      const long long idx = idx0 + k * stride;
+      if (idx < total) {
+        const int n = (int) (idx % S);
+        const int col = (int) (idx / S);
+        const int dof = col % g.d, kl = kl0 + col / g.d;
+        nn[k] = n;
+        rel[k] = ((((size_t) dof) * g.kyb + kl) << lnxl);
 #pragma unroll
-      for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw_nx + (size_t) q * n));
-    }
-    Butterfly<R, DIR>::run(v);
-    if (DIR < 0) {
-#pragma unroll
-      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw_nx + (size_t) q * n));
-    }
-    if constexpr (PEER && DIR > 0) {
-      const size_t rel = ((((size_t) dof) * g.kyb + kl) << lnxl);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int x = n + r * S;
-        peer.p[x >> lnxl][rel + (size_t) (x & xmask)] = v[r];
+        for (int r = 0; r < R; ++r) {
+          const int x = n + r * S;
+          a[k][r] = ((((size_t) (x >> lnxl) * g.d + dof) * g.kyb + kl) << lnxl) + (size_t) (x & xmask);
+          if (PEER && DIR < 0) v[k][r] = peer.p[x >> lnxl][rel[k] + (size_t) (x & xmask)];
+          else v[k][r] = stage[a[k][r]];
+        }
       }
-    } else {
+    }
 #pragma unroll
-      for (int r = 0; r < R; ++r) stage[a[r]] = v[r];
+    for (int k = 0; k < U; ++k) {
+      const long long idx = idx0 + k * stride;
+      if (idx < total) {
+        const int n = nn[k];
+        if (DIR > 0) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[k][q] = cmulc(v[k][q], __ldg(tw_nx + (size_t) q * n));
+        }
+        Butterfly<R, DIR>::run(v[k]);
+        if (DIR < 0) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[k][q] = cmul(v[k][q], __ldg(tw_nx + (size_t) q * n));
+        }
+        if constexpr (PEER && DIR > 0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int x = n + r * S;
+            peer.p[x >> lnxl][rel[k] + (size_t) (x & xmask)] = v[k][r];
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) stage[a[k][r]] = v[k][r];
+        }
+      }
     }
   }
 }

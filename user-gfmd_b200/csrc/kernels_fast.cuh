@@ -713,19 +713,16 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
     break;
       ROWS_VARIANTS(ROWS_ATTR)
 #undef ROWS_ATTR
+#define R16_ATTR(K)                                                                                             \
+  if (e == cudaSuccess)                                                                                         \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fast_rows_smem(rc));
       case 4104:
-        e = cudaFuncSetAttribute(k_rows_fwd_r16<2048, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) fast_rows_smem(rc));
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(k_rows_inv_r16<2048, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int) fast_rows_smem(rc));
+        R16_ATTR((k_rows_fwd_r16<2048, 2, 256>)) R16_ATTR((k_rows_inv_r16<2048, 2, 256>))
+        R16_ATTR((k_rows_fwd_r16<2048, 2, 256, true>)) R16_ATTR((k_rows_inv_r16<2048, 2, 256, true>))
         break;
       case 16392:
-        e = cudaFuncSetAttribute(k_rows_fwd_r16w<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) fast_rows_smem(rc));
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(k_rows_inv_r16w<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int) fast_rows_smem(rc));
+        R16_ATTR((k_rows_fwd_r16w<8192, 512>)) R16_ATTR((k_rows_inv_r16w<8192, 512>))
+        R16_ATTR((k_rows_fwd_r16w<8192, 512, true>)) R16_ATTR((k_rows_inv_r16w<8192, 512, true>))
         break;
 #ifndef GFMD_CUDA_EMU
       case 16393:
@@ -738,12 +735,10 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
         break;
 #endif
       case 8200:
-        e = cudaFuncSetAttribute(k_rows_fwd_r16h<4096, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) fast_rows_smem(rc));
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(k_rows_inv_r16h<4096, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int) fast_rows_smem(rc));
+        R16_ATTR((k_rows_fwd_r16h<4096, 2, 512>)) R16_ATTR((k_rows_inv_r16h<4096, 2, 512>))
+        R16_ATTR((k_rows_fwd_r16h<4096, 2, 512, true>)) R16_ATTR((k_rows_inv_r16h<4096, 2, 512, true>))
         break;
+#undef R16_ATTR
     }
     if (e != cudaSuccess) return 1;
   }
@@ -787,14 +782,29 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
   return 0;
 }
 
+// variants whose kernels have a fused atom I/O form (AtomIO, kernels_rows_r16.cuh)
+inline bool fast_rows_has_atomio(int variant) { return variant == 4104 || variant == 8200 || variant == 16392; }
+
+// io != nullptr: gather fused into the transform (u is not read)
 inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const GridDesc &g, const double2 *tw_ny,
-                         const FftDesc &fd, cudaStream_t s, long long *launches, int dof0 = 0, int ndofs = -1)
+                         const FftDesc &fd, cudaStream_t s, long long *launches, int dof0 = 0, int ndofs = -1,
+                         const AtomIO *io = nullptr)
 {
   FastRowsCfg rc;
   if (!fast_rows_cfg(variant, rc)) return 1;
   if (ndofs < 0) ndofs = g.d - dof0;
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
+  if (io) {
+    switch (variant) {
+      case 4104: k_rows_fwd_r16<2048, 2, 256, true><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0, *io); break;
+      case 8200: k_rows_fwd_r16h<4096, 2, 512, true><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0, *io); break;
+      case 16392: k_rows_fwd_r16w<8192, 512, true><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0, *io); break;
+      default: return 1;
+    }
+    ++*launches;
+    return 0;
+  }
   switch (variant) {
 #define ROWS_LAUNCH(ID, NR, RB, T, MB, W, FF, FI) \
   case ID: k_rows_fwd_p2<NR, RB, T, FF ? MB : 0, W, FF><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
@@ -812,14 +822,27 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   return 0;
 }
 
+// io != nullptr: scatter fused into the transform (f is not written; io->fsum_part receives
+// [nx_loc / rb][ndof] partial force sums)
 inline int fast_rows_inv(int variant, const double2 *stage, double *f, const GridDesc &g, const double2 *tw_ny,
-                         const FftDesc &fd, cudaStream_t s, long long *launches, int dof0 = 0, int ndofs = -1)
+                         const FftDesc &fd, cudaStream_t s, long long *launches, int dof0 = 0, int ndofs = -1,
+                         const AtomIO *io = nullptr)
 {
   FastRowsCfg rc;
   if (!fast_rows_cfg(variant, rc)) return 1;
   if (ndofs < 0) ndofs = g.d - dof0;
   const int grid = ndofs * (g.nx_loc / rc.rb);
   const size_t smem = fast_rows_smem(rc);
+  if (io) {
+    switch (variant) {
+      case 4104: k_rows_inv_r16<2048, 2, 256, true><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0, *io); break;
+      case 8200: k_rows_inv_r16h<4096, 2, 512, true><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0, *io); break;
+      case 16392: k_rows_inv_r16w<8192, 512, true><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0, *io); break;
+      default: return 1;
+    }
+    ++*launches;
+    return 0;
+  }
   switch (variant) {
 #define ROWS_LAUNCH(ID, NR, RB, T, MB, W, FF, FI) \
   case ID: k_rows_inv_p2<NR, RB, T, FI ? MB : 0, W, FI><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
@@ -844,8 +867,12 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
                            const double2 *tw_sub, const double2 *tw_nx, const double *phi, const double *linf,
                            double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches,
                            int kl0 = 0, int kl1 = -1, const PeerOut *peer_out = nullptr,
-                           const PeerOut *peer_in = nullptr, cudaEvent_t *ev_split = nullptr)
+                           const PeerOut *peer_in = nullptr, cudaEvent_t *ev_split = nullptr, int phases = 7,
+                           int top_sms = 0)
 {
+  // phases: bit 0 the forward top-digit pass, bit 1 the fused kernel, bit 2 the backward top-digit pass
+  // (the overlapped multi-GPU step launches them on different streams); top_sms > 0 caps the grid of
+  // the top-digit passes to that many SMs' worth of CTAs
   // ev_split (profiling): [0] recorded behind the forward top-digit pass, [1] before the backward one
   // peer_out (variant 4096 in slab mode): the last kernel of the stage stores the result pieces
   // straight into their owners' return buffers instead of sout.  peer_in (only together with
@@ -864,9 +891,19 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   const int lnxl = ilog2_rt(g.nx_loc);
   const size_t smem = fast_cols_smem(3, variant);
   const long long top_items = (long long) g.d * (kl1 - kl0) * (g.nx >> top);
-  const int top_grid = (int) ((top_items + 255) / 256 < (long long) num_sms * 8 ? (top_items + 255) / 256
-                                                                                : (long long) num_sms * 8);
-  if (top == 1) {
+  const long long top_cap = (long long) (top_sms > 0 ? top_sms : num_sms) * 8;
+  const int top_grid = (int) ((top_items + 255) / 256 < top_cap ? (top_items + 255) / 256 : top_cap);
+  // overlapped multi-GPU step: the exchanging passes are confined to top_sms SMs, ONE fat CTA each (CTAs
+  // are placed breadth-first: many small CTAs would spread over all SMs and keep the fused kernel, which
+  // needs a whole SM per CTA, from starting), with two items = 2 R NVLink loads in flight per thread
+  if (!(phases & 1)) {
+  } else if (top_sms > 0 && peer_in && top == 1) {
+    k_cols_top_pass<1, -1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
+    ++*launches;
+  } else if (top_sms > 0 && peer_in && top == 2) {
+    k_cols_top_pass<2, -1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
+    ++*launches;
+  } else if (top == 1) {
     if (peer_in) k_cols_top_pass<1, -1, true><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
     else k_cols_top_pass<1, -1><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;
@@ -876,6 +913,7 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
     ++*launches;
   }
   if (ev_split && top > 0) cudaEventRecord(ev_split[0], s);
+  if (phases & 2) {
   switch (variant) {
     case 2048:
       k_cols_fused_p2<3, 2048, 256><<<grid, 256, smem, s>>>(sin, sout, g, lnxl, tw_sub, phi, linf, epart, res);
@@ -911,8 +949,16 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
     default: return 1;
   }
   ++*launches;
+  }
   if (ev_split && top > 0) cudaEventRecord(ev_split[1], s);
-  if (top == 1) {
+  if (!(phases & 4)) {
+  } else if (top_sms > 0 && peer_out && top == 1) {
+    k_cols_top_pass<1, +1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1, *peer_out);
+    ++*launches;
+  } else if (top_sms > 0 && peer_out && top == 2) {
+    k_cols_top_pass<2, +1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1, *peer_out);
+    ++*launches;
+  } else if (top == 1) {
     if (peer_out) k_cols_top_pass<1, +1, true><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1, *peer_out);
     else k_cols_top_pass<1, +1><<<top_grid, 256, 0, s>>>(sout, g, lnxl, tw_nx, kl0, kl1);
     ++*launches;

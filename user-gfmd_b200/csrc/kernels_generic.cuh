@@ -122,6 +122,69 @@ k_gather(const double *__restrict__ x, const double *__restrict__ xeq, int *__re
   }
 }
 
+// ---------------------------------------------------------------- cell map ---
+
+// cell -> atom map of the fused gather / scatter row kernels (AtomIO, kernels_rows_r16.cuh): the same
+// index arithmetic as k_gather (lattice shift, wrap, brick test; fix_gfmd.cpp:734-760).  cmap must be
+// preset to -1.  cnt[0] atoms stored, cnt[1] atoms that hit an occupied cell (e.g. a local atom and
+// its own ghost image), cnt[2] atoms with an invalid sublattice index.
+__global__ void __launch_bounds__(kAtomTile)
+k_build_cellmap(int *__restrict__ gid, const int *__restrict__ mask, int groupbit, int nall, GridDesc g,
+                int dxshift, int dyshift, int *__restrict__ cmap, int *cnt)
+{
+  __shared__ int sc[3];
+  if (threadIdx.x < 3) sc[threadIdx.x] = 0;
+  __syncthreads();
+  int stored = 0, dup = 0, bad = 0;
+  const size_t nxy = (size_t) g.nx_loc * g.ny;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nall; i += (long long) gridDim.x * blockDim.x) {
+    if (!(mask[i] & groupbit)) continue;
+    int ix = gid[3 * i] - dxshift;
+    int iy = gid[3 * i + 1] - dyshift;
+    const int iu = gid[3 * i + 2];
+    if (dxshift != 0 || dyshift != 0) {
+      ix %= g.nx; if (ix < 0) ix += g.nx;
+      iy %= g.ny; if (iy < 0) iy += g.ny;
+      gid[3 * i] = ix;
+      gid[3 * i + 1] = iy;
+    }
+    ix -= g.x0;
+    if (ix >= 0 && ix < g.nx_loc && iy >= 0 && iy < g.ny) {
+      if (iu < 0 || 3 * iu + 2 >= g.d) {
+        bad++;
+      } else {
+        const int old = atomicExch(&cmap[(size_t) iu * nxy + (size_t) ix * g.ny + iy], (int) i);
+        stored++;
+        if (old >= 0) dup++;
+      }
+    }
+  }
+  if (stored) atomicAdd(&sc[0], stored);
+  if (dup) atomicAdd(&sc[1], dup);
+  if (bad) atomicAdd(&sc[2], bad);
+  __syncthreads();
+  if (threadIdx.x < 3 && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sc[threadIdx.x]);
+}
+
+// force sum of the fused scatter: part[ntile][d] -> out[c] = sum over tiles and sublattices, fixed order
+__global__ void k_sum_fsum_io(const double *__restrict__ part, int ntile, int d, double *out)
+{
+  __shared__ double sh[256];
+  for (int c = 0; c < 3; ++c) {
+    double a = 0.0;
+    for (int k = threadIdx.x; k < ntile; k += blockDim.x)
+      for (int iu = 0; iu < d / 3; ++iu) a += part[(size_t) k * d + 3 * iu + c];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = sh[0];
+    __syncthreads();
+  }
+}
+
 // ----------------------------------------------------------------- scatter ---
 
 // f[nall][3] += grid force of the atom's cell; per-block partial sums of the forces on

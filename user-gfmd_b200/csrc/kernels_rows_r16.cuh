@@ -83,6 +83,82 @@ template <int DIR, bool OUT_ORDER> __device__ __forceinline__ void r16_twiddle(d
   }
 }
 
+
+// ---- fused atom I/O of the row kernels (MAPPED variants) -----------------------------------------
+// gather o forward rows and inverse rows o scatter in ONE kernel each, through a cell -> atom map
+// (gfmd_b200_build_cell_map; valid only if every cell of the brick holds exactly one atom of the
+// group, otherwise the library keeps the separate k_gather / k_scatter kernels): the displacement
+// grid u_xy and the force grid f_xy never exist in memory.  Same arithmetic per element as
+// k_gather / k_scatter (kernels_generic.cuh), i.e. FixGFMD::pre_force list -> grid
+// (src/main/fix_gfmd.cpp:734-803: u = x - xeq, x / y minimum image) and grid_to_list + f += f_i
+// (:952-1010, :896-902; the force sum runs over atoms i < nlocal only, :997-1001).
+struct AtomIO {
+  const double *x, *xeq;      // [nall][3]
+  double *fat;                // [nall][3], forces accumulate (+=)
+  const int *cmap;            // [nu][nx_loc * ny] atom index of every cell
+  double *fsum_part;          // [ntiles][ndof] per-CTA partial sums of the scattered forces
+  double xprd, yprd;
+  int nlocal;
+};
+
+// packed complex element e of row ixl of dof: (u[2e], u[2e + 1])
+__device__ __forceinline__ double2 atomio_load(const AtomIO &io, const GridDesc &g, int dof, int ixl, int e)
+{
+  const int iu = dof / 3, c = dof - 3 * iu;
+  const int2 a = __ldg(reinterpret_cast<const int2 *>(io.cmap + ((size_t) iu * g.nx_loc + ixl) * g.ny) + e);
+  double u0 = __ldg(io.x + 3 * (size_t) a.x + c) - __ldg(io.xeq + 3 * (size_t) a.x + c);
+  double u1 = __ldg(io.x + 3 * (size_t) a.y + c) - __ldg(io.xeq + 3 * (size_t) a.y + c);
+  if (c < 2) {                                   // x, y: minimum image (z is not wrapped, fix_gfmd.cpp:758)
+    const double prd = c == 0 ? io.xprd : io.yprd, half = 0.5 * prd;
+    while (u0 > half) u0 -= prd;
+    while (u0 < -half) u0 += prd;
+    while (u1 > half) u1 -= prd;
+    while (u1 < -half) u1 += prd;
+  }
+  return make_double2(u0, u1);
+}
+
+// f[atom] += grid force; returns this pair's contribution to the force sum over local atoms
+__device__ __forceinline__ double atomio_store(const AtomIO &io, const GridDesc &g, int dof, int ixl, int e, double2 v)
+{
+  const int iu = dof / 3, c = dof - 3 * iu;
+  const int2 a = __ldg(reinterpret_cast<const int2 *>(io.cmap + ((size_t) iu * g.nx_loc + ixl) * g.ny) + e);
+  double *f0 = io.fat + 3 * (size_t) a.x + c, *f1 = io.fat + 3 * (size_t) a.y + c;
+  *f0 += v.x;
+  *f1 += v.y;
+  return (a.x < io.nlocal ? v.x : 0.0) + (a.y < io.nlocal ? v.y : 0.0);
+}
+
+// fixed-order block sum of `acc`, written to *dst by thread 0 (T threads, all must call)
+template <int T> __device__ __forceinline__ void atomio_block_sum(double acc, double *dst)
+{
+  __shared__ double red[T / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < T / 32; ++k) a += red[k];
+    *dst = a;
+  }
+}
+
+// block -> (dof, first row): MAPPED kernels put the dofs of one tile in neighbouring CTAs, which run
+// at the same time and share the atoms' cache lines in L2 (x, xeq and f are [atom][3])
+template <bool MAPPED> __device__ __forceinline__ void rows_block_map(int ntiles, int dof0, int &dof, int &tile)
+{
+  if (MAPPED) {
+    const int nd = gridDim.x / ntiles;
+    dof = dof0 + blockIdx.x % nd;
+    tile = blockIdx.x / nd;
+  } else {
+    dof = dof0 + blockIdx.x / ntiles;
+    tile = blockIdx.x % ntiles;
+  }
+}
+
 // unit p in [0, 128) -> klow in [0, 128), 0 -> 0: the four units of a quarter warp take four
 // values of q1 & 3 (q1 = klow >> 4); their partner groups 256 - klow then do too
 __device__ __forceinline__ int r16_klow(int p) { return ((p >> 2) & 15) | ((p & 3) << 4) | ((p >> 6) << 6); }
@@ -94,27 +170,32 @@ __device__ __forceinline__ int r16_slot(int klow, int t1, int r)
   return ((klow & 15) << 7) + (q1 << 3) + (t1 ^ ((q1 & 3) | ((r & 1) << 2)));
 }
 
-template <int NR, int RB, int T>
+template <int NR, int RB, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 2)
 k_rows_fwd_r16(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
-               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
 {
   static_assert(NR == 2048 && RB * (NR / 16) == T, "k_rows_fwd_r16: NR = 16 * 16 * 8, one pass-1 item per thread");
   constexpr int M1 = NR / 16;                 // 128: pass-1 threads per row = length of a pass-2 block
   constexpr int S = NR / 8;                   // 256: frequency stride of the last pass
   extern __shared__ double2 sm[];
-  const int nblk = g.nx_loc / RB;
-  const int dof = dof0 + blockIdx.x / nblk;
-  const int ix0 = (blockIdx.x % nblk) * RB;
+  int dof, tile;
+  rows_block_map<MAPPED>(g.nx_loc / RB, dof0, dof, tile);
+  const int ix0 = tile * RB;
   const int r = threadIdx.x / M1, m = threadIdx.x % M1;
   double2 *row = sm + r * NR;
 
   // ---- pass 1: 16 independent 16-byte loads per thread, coalesced over the threads of a row
   {
-    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
     double2 v[16];
+    if constexpr (MAPPED) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+      for (int j = 0; j < 16; ++j) v[j] = atomio_load(io, g, dof, ix0 + r, m + M1 * j);
+    } else {
+      const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+    }
     dft16<-1>(v);
     r16_twiddle<-1, true>(v, __ldg(tw + m));
 #pragma unroll
@@ -172,18 +253,18 @@ k_rows_fwd_r16(const double *__restrict__ u, double2 *__restrict__ stage, GridDe
   }
 }
 
-template <int NR, int RB, int T>
+template <int NR, int RB, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 2)
 k_rows_inv_r16(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
-               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
 {
   static_assert(NR == 2048 && RB * (NR / 16) == T, "k_rows_inv_r16: NR = 16 * 16 * 8, one pass-1 item per thread");
   constexpr int M1 = NR / 16;
   constexpr int S = NR / 8;
   extern __shared__ double2 sm[];
-  const int nblk = g.nx_loc / RB;
-  const int dof = dof0 + blockIdx.x / nblk;
-  const int ix0 = (blockIdx.x % nblk) * RB;
+  int dof, tile;
+  rows_block_map<MAPPED>(g.nx_loc / RB, dof0, dof, tile);
+  const int ix0 = tile * RB;
 
   // ---- transposed load of both groups of a unit (16 independent loads), pre-mix, inverse 8-point DFTs
   {
@@ -253,9 +334,16 @@ k_rows_inv_r16(const double2 *__restrict__ stage, double *__restrict__ f, GridDe
     for (int q0 = 0; q0 < 16; ++q0) v[q0] = row[q0 * M1 + m];
     r16_twiddle<+1, false>(v, __ldg(tw + m));
     dft16<+1>(v);
-    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+    if constexpr (MAPPED) {
+      double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dst[m + M1 * j] = v[r16_out(j)];
+      for (int j = 0; j < 16; ++j) acc += atomio_store(io, g, dof, ix0 + r, m + M1 * j, v[r16_out(j)]);
+      atomio_block_sum<T>(acc, io.fsum_part + (size_t) tile * g.d + dof);
+    } else {
+      double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[m + M1 * j] = v[r16_out(j)];
+    }
   }
 }
 
@@ -321,26 +409,31 @@ __device__ __forceinline__ void r16h_half_inv(double2 *rw, int grp, int e, int r
   for (int t = 0; t < 8; ++t) rw[r16h_slot(grp, t + 8 * e, rr)] = e ? cmulc(z[t], rot16(t)) : z[t];
 }
 
-template <int NR, int RB, int T>
+template <int NR, int RB, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 1)
 k_rows_fwd_r16h(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
-                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
 {
   static_assert(NR == 4096 && RB * (NR / 16) == T, "k_rows_fwd_r16h: NR = 16 * 16 * 16, one pass-1 item per thread");
   constexpr int M1 = NR / 16;                 // 256
   constexpr int S = NR / 8;                   // 512: frequency stride of a unit's outputs
   extern __shared__ double2 sm[];
-  const int nblk = g.nx_loc / RB;
-  const int dof = dof0 + blockIdx.x / nblk;
-  const int ix0 = (blockIdx.x % nblk) * RB;
+  int dof, tile;
+  rows_block_map<MAPPED>(g.nx_loc / RB, dof0, dof, tile);
+  const int ix0 = tile * RB;
   const int r = threadIdx.x / M1, m = threadIdx.x % M1;
   double2 *row = sm + r * NR;
 
   {
-    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
     double2 v[16];
+    if constexpr (MAPPED) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+      for (int j = 0; j < 16; ++j) v[j] = atomio_load(io, g, dof, ix0 + r, m + M1 * j);
+    } else {
+      const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+    }
     dft16<-1>(v);
     r16_twiddle<-1, true>(v, __ldg(tw + m));
 #pragma unroll
@@ -389,18 +482,18 @@ k_rows_fwd_r16h(const double *__restrict__ u, double2 *__restrict__ stage, GridD
   }
 }
 
-template <int NR, int RB, int T>
+template <int NR, int RB, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 1)
 k_rows_inv_r16h(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
-                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
 {
   static_assert(NR == 4096 && RB * (NR / 16) == T, "k_rows_inv_r16h: NR = 16 * 16 * 16, one pass-1 item per thread");
   constexpr int M1 = NR / 16;
   constexpr int S = NR / 8;
   extern __shared__ double2 sm[];
-  const int nblk = g.nx_loc / RB;
-  const int dof = dof0 + blockIdx.x / nblk;
-  const int ix0 = (blockIdx.x % nblk) * RB;
+  int dof, tile;
+  rows_block_map<MAPPED>(g.nx_loc / RB, dof0, dof, tile);
+  const int ix0 = tile * RB;
 
   {
     const int rr = threadIdx.x % RB;
@@ -464,9 +557,16 @@ k_rows_inv_r16h(const double2 *__restrict__ stage, double *__restrict__ f, GridD
     for (int q0 = 0; q0 < 16; ++q0) v[q0] = row[q0 * M1 + m];
     r16_twiddle<+1, false>(v, __ldg(tw + m));
     dft16<+1>(v);
-    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+    if constexpr (MAPPED) {
+      double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dst[m + M1 * j] = v[r16_out(j)];
+      for (int j = 0; j < 16; ++j) acc += atomio_store(io, g, dof, ix0 + r, m + M1 * j, v[r16_out(j)]);
+      atomio_block_sum<T>(acc, io.fsum_part + (size_t) tile * g.d + dof);
+    } else {
+      double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[m + M1 * j] = v[r16_out(j)];
+    }
   }
 }
 
@@ -491,22 +591,27 @@ __device__ __forceinline__ int r16w_klow(int p)
   return ((p >> 3) & 15) | (q1 << 4) | ((p & 3) << 7);
 }
 
-template <int NR, int T>
+template <int NR, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 1)
 k_rows_fwd_r16w(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
-                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
 {
   static_assert(NR == 8192 && NR / 16 == T, "k_rows_fwd_r16w: NR = 16 * 8 * 8 * 8, one row per CTA");
   constexpr int S = NR / 8;                   // 1024: frequency stride of the last pass
   extern __shared__ double2 sm[];
-  const int dof = dof0 + blockIdx.x / g.nx_loc;
-  const int ix = blockIdx.x % g.nx_loc;
+  int dof, ix;
+  rows_block_map<MAPPED>(g.nx_loc, dof0, dof, ix);
   const int t = threadIdx.x;
   {
-    const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
     double2 v[16];
+    if constexpr (MAPPED) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = src[t + T * j];
+      for (int j = 0; j < 16; ++j) v[j] = atomio_load(io, g, dof, ix, t + T * j);
+    } else {
+      const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = src[t + T * j];
+    }
     dft16<-1>(v);
     r16_twiddle<-1, true>(v, __ldg(tw + t));
 #pragma unroll
@@ -575,16 +680,16 @@ k_rows_fwd_r16w(const double *__restrict__ u, double2 *__restrict__ stage, GridD
   }
 }
 
-template <int NR, int T>
+template <int NR, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 1)
 k_rows_inv_r16w(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
-                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0)
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
 {
   static_assert(NR == 8192 && NR / 16 == T, "k_rows_inv_r16w: NR = 16 * 8 * 8 * 8, one row per CTA");
   constexpr int S = NR / 8;
   extern __shared__ double2 sm[];
-  const int dof = dof0 + blockIdx.x / g.nx_loc;
-  const int ix = blockIdx.x % g.nx_loc;
+  int dof, ix;
+  rows_block_map<MAPPED>(g.nx_loc, dof0, dof, ix);
   const int t = threadIdx.x;
   {
     const int p = t;
@@ -661,9 +766,16 @@ k_rows_inv_r16w(const double2 *__restrict__ stage, double *__restrict__ f, GridD
     for (int q0 = 0; q0 < 16; ++q0) v[q0] = sm[q0 * T + t];
     r16_twiddle<+1, false>(v, __ldg(tw + t));
     dft16<+1>(v);
-    double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
+    if constexpr (MAPPED) {
+      double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dst[t + T * j] = v[r16_out(j)];
+      for (int j = 0; j < 16; ++j) acc += atomio_store(io, g, dof, ix, t + T * j, v[r16_out(j)]);
+      atomio_block_sum<T>(acc, io.fsum_part + (size_t) ix * g.d + dof);
+    } else {
+      double2 *dst = reinterpret_cast<double2 *>(f + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[t + T * j] = v[r16_out(j)];
+    }
   }
 }
 

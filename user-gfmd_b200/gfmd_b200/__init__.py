@@ -57,6 +57,8 @@ ABI = {
     "gfmd_b200_prec_gradient_host": (_i, [_vp, _vp, _vp, _vp, _i]),
     "gfmd_b200_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i, _vp]),
     "gfmd_b200_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gfmd_b200_build_cell_map": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, c_int_p]),
+    "gfmd_b200_drop_cell_map": (_i, [_vp]),
     "gfmd_b200_full_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
     "gfmd_b200_get_results": (_i, [_vp, c_double_p, _vp, _vp, _vp]),
     "gfmd_b200_device_u": (_vp, [_vp]),
@@ -339,6 +341,17 @@ class GFMDSolverB200:
     def scatter(self, d_gid, d_mask, groupbit, nall, nlocal, d_f, d_fgrid=None):
         self._check(self.lib.gfmd_b200_scatter(self.h, _ptr(d_fgrid), _ptr(d_gid), _ptr(d_mask),
                                                groupbit, nall, nlocal, _ptr(d_f)))
+
+    def build_cell_map(self, d_gid, d_mask, groupbit, nall, nlocal, dxshift=0, dyshift=0):
+        """Cell -> atom map for the fused gather / scatter form of full_step; returns whether it is
+        usable (one atom per cell and radix-16 row kernels), see include/gfmd_b200.h."""
+        ok = ctypes.c_int()
+        self._check(self.lib.gfmd_b200_build_cell_map(self.h, _ptr(d_gid), _ptr(d_mask), groupbit, nall, nlocal,
+                                                      dxshift, dyshift, ctypes.byref(ok)))
+        return bool(ok.value)
+
+    def drop_cell_map(self):
+        self._check(self.lib.gfmd_b200_drop_cell_map(self.h))
 
     def full_step(self, d_x, d_xeq, d_gid, d_mask, groupbit, nall, nlocal, xprd, yprd, d_f):
         self._check(self.lib.gfmd_b200_full_step(self.h, _ptr(d_x), _ptr(d_xeq), _ptr(d_gid),
