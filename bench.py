@@ -296,8 +296,9 @@ def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clock
     stream = c.stream
     s.set_stream(stream.cuda_stream)
     torch.cuda.synchronize()
-    # fused gather / scatter through a cell -> atom map (built once; a fix rebuilds it when it reneighbours)
-    fused_io = os.environ.get("BENCH_FUSED_IO", "1") != "0" and s.build_cell_map(dgid, dmask, 1, nat, nat)
+    # fused gather / scatter through a cell -> atom map: OPT-IN (BENCH_FUSED_IO=1).  Measured slower than the
+    # separate kernels (profiles/r2_fused_atom_io_ab.md: per-dof CTAs touch 8 of every 24 bytes of x / xeq / f)
+    fused_io = os.environ.get("BENCH_FUSED_IO", "0") == "1" and s.build_cell_map(dgid, dmask, 1, nat, nat)
     t_setup = time.time() - t_setup
 
     def step():

@@ -417,5 +417,6 @@ def test_fused_atom_io_equals_separate_gather_scatter(B, nx, ny, nu):
     assert s.build_cell_map(dgid, m2, 2, n, nlocal) is False
     df = f0.clone()
     s.full_step(dx, dxeq, dgid, dmask, 2, n, nlocal, float(nx), float(ny), df)
+    s.synchronize()                       # the step runs on the handle's own stream
     assert torch.equal(df, fa)
     s.close()

@@ -22,15 +22,18 @@ def run_worker(nranks, port, env=None):
 # awaited by the streams, in-kernel peer loads / stores); no NCCL (it refuses two ranks on a device).
 
 ONE_DEVICE_MODES = {
-    "pushes": {},
+    "pushes": {"GFMD_B200_PEER_DIRECT": "0"},          # copy-engine pushes also where the default is the step without transposes
     "peer_store": {"GFMD_B200_PEER_STORE": "1"},
     "no_transposes": {"GFMD_B200_PEER_DIRECT": "1"},
     "chunks8": {"GFMD_B200_CHUNKS": "8"},
 }
 
 
+ONE_DEVICE_MODES["default"] = {}
+
+
 @pytest.mark.parametrize("nranks,mode", [(2, "pushes"), (4, "pushes"), (2, "peer_store"), (4, "no_transposes"),
-                                         (2, "chunks8")])
+                                         (2, "chunks8"), (4, "default")])
 def test_slab_parity_one_device(nranks, mode):
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"

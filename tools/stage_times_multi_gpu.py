@@ -47,6 +47,19 @@ SETTINGS = {
     'direct_x8': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '8'},
     'direct_x12': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '12'},
     'direct_x24': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '24'},
+    'direct_32_16': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '32,16'},
+    'direct_40_16': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '40,16'},
+    'direct_48_16': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '48,16'},
+    'direct_40_24': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '40,24'},
+    'direct_40_12': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '40,12'},
+    'direct_56_16': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '56,16'},
+    'direct_48_24': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '48,24'},
+    'direct_40_32': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '40,32'},
+    'direct_24_40': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '24,40'},
+    'direct_32_32': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '32,32'},
+    'direct_64_16': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '64,16'},
+    'direct_40_16_tl': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '40,16', 'GFMD_B200_TIMELINE': '1'},
+    'direct_tl': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_TIMELINE': '1'},
     'direct_x32': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '32'},
     'direct_x24c4': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_XCHG_SMS': '24', 'GFMD_B200_CHUNKS': '4'},
     'direct_c4': {'GFMD_B200_PEER_DIRECT': '1', 'GFMD_B200_CHUNKS': '4'},
@@ -55,7 +68,7 @@ SETTINGS = {
 names = os.environ['AB'].split(',') if os.environ.get('AB') else list(SETTINGS)
 if world == 1: names = [n for n in names if n in ('default', 'rows_fused', 'rows_r16')]
 KEYS = ('GFMD_B200_PEER_STORE', 'GFMD_B200_PEER_DIRECT', 'GFMD_B200_ROWS_VARIANT', 'GFMD_B200_CHUNKS', 'EXCH', 'GFMD_B200_SYNC',
-        'GFMD_B200_XCHG_SMS')
+        'GFMD_B200_XCHG_SMS', 'GFMD_B200_TIMELINE')
 nxl = nx // world
 u = torch.rand((d, nxl * ny), device=dev, dtype=torch.float64, generator=torch.Generator(dev).manual_seed(7 + rank)) - 0.5
 f0 = None

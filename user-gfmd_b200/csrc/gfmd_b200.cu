@@ -34,7 +34,7 @@ thread_local std::string g_create_error;
 
 constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in dynamic shared memory per CTA
 constexpr size_t kFlagTail = 256;     // complex elements (4096 B) behind d_stage2: flag words, then the u0 zone
-constexpr size_t kFlagU0Bytes = 2048; // byte offset of the u0 landing zone inside that tail
+constexpr size_t kFlagU0Bytes = 3072; // byte offset of the u0 landing zone inside that tail
 
 // ------------------------------------------------------------------- NCCL ---
 
@@ -337,6 +337,10 @@ struct gfmd_b200 {
   // NVLink on two side streams, chunk by chunk, next to the fused column kernel on a reduced grid
   cudaStream_t pull_stream = nullptr, push_stream = nullptr;
   cudaEvent_t ev_pull[kMaxChunks] = {}, ev_rows_done = nullptr, ev_push_done = nullptr;
+  bool timeline = false;                      // GFMD_B200_TIMELINE=1: per-chunk event times of the overlapped step on stderr
+  cudaEvent_t ev_tl[kMaxChunks][6] = {};      // pull start / end, fused start / end, push start / end
+  long long tl_steps = 0;
+  int push_sms = 24;                          // SMs of the pushing pass (second number of GFMD_B200_XCHG_SMS=pull,push)
   int xchg_sms = 24;                          // SMs for the pulling and as many for the pushing pass (GFMD_B200_XCHG_SMS);
                                               // measured at 8 GPUs, 16384^2: 16 -> 4.74 ms, 24 -> 4.09 ms, 32 -> 4.24 ms per solver step
   double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
@@ -712,13 +716,15 @@ int atom_blocks(const gfmd_b200 *h, int nall)
 // Flag words of a rank live behind its forward receive buffer (d_stage2), which every peer maps:
 //   kFlagFwd + src * kMaxChunks + c   chunk c of src's forward blocks has landed here
 //   kFlagRet + src                    src's return blocks (and, from rank 0, u0) have landed here
-//   kFlagRows + src                   src's row transforms are complete (mode without transposes)
+//   kFlagRows + src + 16 * dof        src's row transforms of that dof are complete (mode without transposes;
+//                                     where the rows are not launched dof by dof: dof 0 stands for all)
 // Values are the step counter h->seq; a rank can never be more than one step ahead of a peer it
 // exchanges with (it needs that peer's return blocks to finish its own step), so ">= seq" is exact.
 constexpr int kFlagFwd = 0;
 constexpr int kFlagRet = gfmd_b200::kMaxRanks * gfmd_b200::kMaxChunks;
-constexpr int kFlagRows = kFlagRet + gfmd_b200::kMaxRanks;
-static_assert((kFlagRows + gfmd_b200::kMaxRanks) * sizeof(unsigned) <= kFlagU0Bytes, "flag words overlap the u0 zone");
+constexpr int kFlagRows = kFlagRet + gfmd_b200::kMaxRanks;      // + src + kMaxRanks * dof (dof 0 alone where rows are not split)
+static_assert((kFlagRows + gfmd_b200::kMaxRanks * GFMD_B200_MAX_NDOF) * sizeof(unsigned) <= kFlagU0Bytes,
+              "flag words overlap the u0 zone");
 
 int signal_peer(gfmd_b200 *h, cudaStream_t s, int r, int slot)
 {
@@ -985,41 +991,69 @@ int direct_pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *
     pin.p[r] = (r == g.rank ? A : h->peer_stage[r]) + g.rank * blk;
   }
   stage_mark(h, 1);
-  int rc = fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, 0, -1, h->io_fwd);
-  if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
-  stage_mark(h, 2);
-  // my rows are complete: tell every peer, and let my pull stream wait for theirs
-  for (int k = 1; k < g.P; ++k)
-    if ((rc = signal_peer(h, h->stream, (g.rank + k) % g.P, kFlagRows + g.rank))) return rc;
-  CU(h, cudaEventRecord(h->ev_rows_done, h->stream));
-  CU(h, cudaStreamWaitEvent(h->pull_stream, h->ev_rows_done, 0));
-  for (int k = 1; k < g.P; ++k) {
-    const int p = (g.rank + k) % g.P;
-    if (stream_wait32_geq(h->pull_stream, h->flags + kFlagRows + p, h->seq))
-      return fail(h, GFMD_B200_ECUDA, "cuStreamWaitValue32 on the rows flag of rank %d failed", p);
+  // Rows dof by dof.  As soon as a dof is complete on EVERY rank (flag words), the pull stream's
+  // top-digit pass fetches it -- on xchg_sms SMs, while the row kernels of the next dof keep the others
+  // busy: NVLink works while the rows are transformed, not only after them.  The last dof is pulled
+  // chunk by chunk next to the fused column kernel (below).
+  const bool split_rows = h->io_fwd == nullptr && g.d > 1;
+  const int nrow_launch = split_rows ? g.d : 1;
+  int rc = 0;
+  for (int i = 0; i < nrow_launch; ++i) {
+    rc = split_rows ? fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, i, 1)
+                    : fast_rows_fwd(h->fast_rows, d_u, A, g, h->d_tw_ny, h->fft_rows.desc, h->stream, &h->launches, 0, -1,
+                                    h->io_fwd);
+    if (rc) return fail(h, GFMD_B200_ECUDA, "fast rows_fwd launch failed");
+    for (int k = 1; k < g.P; ++k)
+      if ((rc = signal_peer(h, h->stream, (g.rank + k) % g.P, kFlagRows + g.rank + gfmd_b200::kMaxRanks * i))) return rc;
+    CU(h, cudaEventRecord(h->ev_row[i], h->stream));
+    CU(h, cudaStreamWaitEvent(h->pull_stream, h->ev_row[i], 0));
+    for (int k = 1; k < g.P; ++k) {
+      const int p = (g.rank + k) % g.P;
+      if (stream_wait32_geq(h->pull_stream, h->flags + kFlagRows + p + gfmd_b200::kMaxRanks * i, h->seq))
+        return fail(h, GFMD_B200_ECUDA, "cuStreamWaitValue32 on the rows flag of rank %d failed", p);
+    }
+    if (split_rows && i < g.d - 1) {       // this dof, all columns, now
+      rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
+                           h->d_epart, h->d_res, h->num_sms, h->pull_stream, &h->launches, 0, g.kyb, &po, &pin, nullptr, 1,
+                           h->xchg_sms, i, 1);
+      if (rc) return fail(h, GFMD_B200_ECUDA, "top-digit pull launch failed");
+    }
   }
+  stage_mark(h, 2);
+  const int pull_dof0 = split_rows ? g.d - 1 : 0, pull_nd = split_rows ? 1 : g.d;   // what the chunk loop still pulls
   stage_mark(h, 3);
+  const bool tl = h->timeline && h->profiling;
+  if (tl)
+    for (int c = 0; c < nc; ++c)
+      for (int k = 0; k < 6; ++k)
+        if (!h->ev_tl[c][k]) cudaEventCreate(&h->ev_tl[c][k]);
   // the fused kernel needs a whole SM per CTA: leave xchg_sms SMs to the pulling and as many to the pushing pass
-  const int cols_sms = h->num_sms - 2 * h->xchg_sms > 8 ? h->num_sms - 2 * h->xchg_sms : h->num_sms;
+  const int cols_sms = h->num_sms - h->xchg_sms - h->push_sms > 8 ? h->num_sms - h->xchg_sms - h->push_sms : h->num_sms;
   for (int c = 0; c < nc; ++c) {
     const int k0 = c * ck, k1 = (c + 1) * ck < g.kyb ? (c + 1) * ck : g.kyb;
     // forward top-digit pass of chunk c, inputs straight from the peers' row outputs, into B
+    if (tl) cudaEventRecord(h->ev_tl[c][0], h->pull_stream);
     rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
                          h->d_epart, h->d_res, h->num_sms, h->pull_stream, &h->launches, k0, k1, &po, &pin, nullptr, 1,
-                         h->xchg_sms);
+                         h->xchg_sms, pull_dof0, pull_nd);
     if (rc) return fail(h, GFMD_B200_ECUDA, "top-digit pull launch failed");
+    if (tl) cudaEventRecord(h->ev_tl[c][1], h->pull_stream);
     CU(h, cudaEventRecord(h->ev_pull[c], h->pull_stream));
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_pull[c], 0));
+    if (tl) cudaEventRecord(h->ev_tl[c][2], h->stream);
     rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
                          h->d_epart, h->d_res, cols_sms, h->stream, &h->launches, k0, k1, &po, &pin, nullptr, 2);
     if (rc) return fail(h, GFMD_B200_ECUDA, "fast cols_fused launch failed");
+    if (tl) cudaEventRecord(h->ev_tl[c][3], h->stream);
     CU(h, cudaEventRecord(h->ev_k2[c], h->stream));
     CU(h, cudaStreamWaitEvent(h->push_stream, h->ev_k2[c], 0));
     // backward top-digit pass of chunk c, results straight into the owners' return buffers
+    if (tl) cudaEventRecord(h->ev_tl[c][4], h->push_stream);
     rc = fast_cols_fused(h->fast_cols, h->cols_top, B, B, g, tw_sub, h->fft_cols.desc.core.tw, h->d_phi, h->d_linf,
                          h->d_epart, h->d_res, h->num_sms, h->push_stream, &h->launches, k0, k1, &po, &pin, nullptr, 4,
-                         h->xchg_sms);
+                         h->push_sms);
     if (rc) return fail(h, GFMD_B200_ECUDA, "top-digit push launch failed");
+    if (tl) cudaEventRecord(h->ev_tl[c][5], h->push_stream);
   }
   k_finalize<<<1, 256, 0, h->stream>>>(h->d_epart, g.nky_loc << h->cols_top, h->d_res);
   h->launches++;
@@ -1036,6 +1070,18 @@ int direct_pipelined_step(gfmd_b200 *h, const double *d_u, double2 *A, double2 *
   CU(h, cudaStreamWaitEvent(h->stream, h->ev_push_done, 0));      // B and the peers' buffers are free for the next step
   rc = wait_peers(h, kFlagRet, 1);
   if (!rc) rc = take_u0(h);
+  if (tl && !rc && ++h->tl_steps == 5) {          // debugging aid: one timeline (ms after the row kernels' mark)
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->pull_stream);
+    cudaStreamSynchronize(h->push_stream);
+    for (int c = 0; c < nc; ++c) {
+      float t[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], h->ev[2], h->ev_tl[c][k]);
+      fprintf(stderr, "gfmd_b200 timeline rank %d chunk %d: pull %.3f-%.3f fused %.3f-%.3f push %.3f-%.3f ms\n", g.rank, c,
+              t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    cudaGetLastError();
+  }
   return rc;
 }
 
@@ -1545,7 +1591,12 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
   h->peer_direct = h->g.P >= 4 && h->cols_top > 0 && h->fast_cols == 4096;
   if (const char *e = getenv("GFMD_B200_PEER_STORE")) h->peer_store = atoi(e) != 0;
   if (const char *e = getenv("GFMD_B200_PEER_DIRECT")) h->peer_direct = atoi(e) != 0;
-  if (const char *e = getenv("GFMD_B200_XCHG_SMS")) h->xchg_sms = atoi(e);
+  if (const char *e = getenv("GFMD_B200_XCHG_SMS")) {       // "<pull>" or "<pull>,<push>"
+    h->xchg_sms = h->push_sms = atoi(e);
+    if (const char *c = strchr(e, ',')) h->push_sms = atoi(c + 1);
+  }
+  if (h->push_sms < 0) h->push_sms = 0;
+  if (const char *e = getenv("GFMD_B200_TIMELINE")) h->timeline = atoi(e) != 0;
   if (h->xchg_sms < 0) h->xchg_sms = 0;
   // chunking of the column stage: whole waves of the persistent column kernel per chunk
   {
@@ -1555,7 +1606,7 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles)
     if (want < 1) want = 1;
     if (want > gfmd_b200::kMaxChunks) want = gfmd_b200::kMaxChunks;
     int sms = h->num_sms;
-    if (overlapped_direct && sms - 2 * h->xchg_sms > 8) sms -= 2 * h->xchg_sms;     // the fused kernel's share of the SMs
+    if (overlapped_direct && sms - h->xchg_sms - h->push_sms > 8) sms -= h->xchg_sms + h->push_sms;   // the fused kernel's share
     const int per_wave = sms >> h->cols_top > 0 ? sms >> h->cols_top : 1;   // ky per wave
     int waves = (h->g.kyb + per_wave * want - 1) / (per_wave * want);
     if (waves < 1) waves = 1;
@@ -1635,7 +1686,8 @@ int gfmd_b200_ipc_import_stage(gfmd_b200_t *h, const char *all_handles)
   if (h->peer_direct && h->fast_cols == 4096 && h->desc.find("transposes: ") == std::string::npos)
     h->desc += h->cols_top > 0 && h->nchunks > 1 && h->sync_flags
                    ? " | transposes: none, in-kernel peer loads and stores, overlapped chunk by chunk (" +
-                         std::to_string(h->nchunks) + " chunks, " + std::to_string(h->xchg_sms) + " SMs for the exchange)"
+                         std::to_string(h->nchunks) + " chunks, " + std::to_string(h->xchg_sms) + " + " +
+                         std::to_string(h->push_sms) + " SMs pull + push)"
                    : " | transposes: none, in-kernel peer loads and stores";
   return 0;
 }
@@ -1663,8 +1715,11 @@ void gfmd_b200_destroy(gfmd_b200_t *h)
   if (h->push_stream) cudaStreamDestroy(h->push_stream);
   if (h->ev_rows_done) cudaEventDestroy(h->ev_rows_done);
   if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
-  for (int c = 0; c < gfmd_b200::kMaxChunks; ++c)
+  for (int c = 0; c < gfmd_b200::kMaxChunks; ++c) {
     if (h->ev_pull[c]) cudaEventDestroy(h->ev_pull[c]);
+    for (int k = 0; k < 6; ++k)
+      if (h->ev_tl[c][k]) cudaEventDestroy(h->ev_tl[c][k]);
+  }
   for (int i = 0; i < GFMD_B200_MAX_NDOF; ++i)
     if (h->ev_row[i]) cudaEventDestroy(h->ev_row[i]);
   for (int c = 0; c < gfmd_b200::kMaxChunks; ++c) {

@@ -248,12 +248,14 @@ k_cols_fused_p2_lr(const double2 *__restrict__ sin, double2 *__restrict__ sout, 
 template <int LR, int DIR, bool PEER = false, int T = 256, int U = 1>
 __global__ void __launch_bounds__(T)
 k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2 *__restrict__ tw_nx, int kl0,
-                int kl1, PeerOut peer = PeerOut())
+                int kl1, PeerOut peer = PeerOut(), int dof0 = 0, int nd = -1)
 {
+  // dofs [dof0, dof0 + nd) of the columns kl0 .. kl1 - 1 (nd < 0: all)
   constexpr int R = 1 << LR;
   const int S = g.nx >> LR;
   const int xmask = (1 << lnxl) - 1;
-  const long long total = (long long) g.d * (kl1 - kl0) * S;
+  if (nd < 0) nd = g.d - dof0;
+  const long long total = (long long) nd * (kl1 - kl0) * S;
   const long long stride = (long long) gridDim.x * blockDim.x;
   for (long long idx0 = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += stride * U) {
     double2 v[U][R];
@@ -266,7 +268,7 @@ k_cols_top_pass(double2 *__restrict__ stage, GridDesc g, int lnxl, const double2
       if (idx < total) {
         const int n = (int) (idx % S);
         const int col = (int) (idx / S);
-        const int dof = col % g.d, kl = kl0 + col / g.d;
+        const int dof = dof0 + col % nd, kl = kl0 + col / nd;
         nn[k] = n;
         rel[k] = ((((size_t) dof) * g.kyb + kl) << lnxl);
 #pragma unroll

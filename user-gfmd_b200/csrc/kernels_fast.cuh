@@ -868,8 +868,9 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
                            double *epart, StepResults *res, int num_sms, cudaStream_t s, long long *launches,
                            int kl0 = 0, int kl1 = -1, const PeerOut *peer_out = nullptr,
                            const PeerOut *peer_in = nullptr, cudaEvent_t *ev_split = nullptr, int phases = 7,
-                           int top_sms = 0)
+                           int top_sms = 0, int pull_dof0 = 0, int pull_nd = -1)
 {
+  // pull_dof0 / pull_nd: dof range of the confined PULLING top-digit pass (phases == 1, top_sms > 0)
   // phases: bit 0 the forward top-digit pass, bit 1 the fused kernel, bit 2 the backward top-digit pass
   // (the overlapped multi-GPU step launches them on different streams); top_sms > 0 caps the grid of
   // the top-digit passes to that many SMs' worth of CTAs
@@ -898,10 +899,10 @@ inline int fast_cols_fused(int variant, int top, double2 *sin, double2 *sout, co
   // needs a whole SM per CTA, from starting), with two items = 2 R NVLink loads in flight per thread
   if (!(phases & 1)) {
   } else if (top_sms > 0 && peer_in && top == 1) {
-    k_cols_top_pass<1, -1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
+    k_cols_top_pass<1, -1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in, pull_dof0, pull_nd);
     ++*launches;
   } else if (top_sms > 0 && peer_in && top == 2) {
-    k_cols_top_pass<2, -1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
+    k_cols_top_pass<2, -1, true, 1024, 2><<<top_sms, 1024, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in, pull_dof0, pull_nd);
     ++*launches;
   } else if (top == 1) {
     if (peer_in) k_cols_top_pass<1, -1, true><<<top_grid, 256, 0, s>>>(sin, g, lnxl, tw_nx, kl0, kl1, *peer_in);
