@@ -340,9 +340,10 @@ struct gfmd_b200 {
   bool timeline = false;                      // GFMD_B200_TIMELINE=1: per-chunk event times of the overlapped step on stderr
   cudaEvent_t ev_tl[kMaxChunks][6] = {};      // pull start / end, fused start / end, push start / end
   long long tl_steps = 0;
-  int push_sms = 24;                          // SMs of the pushing pass (second number of GFMD_B200_XCHG_SMS=pull,push)
-  int xchg_sms = 24;                          // SMs for the pulling and as many for the pushing pass (GFMD_B200_XCHG_SMS);
-                                              // measured at 8 GPUs, 16384^2: 16 -> 4.74 ms, 24 -> 4.09 ms, 32 -> 4.24 ms per solver step
+  int push_sms = 32;                          // SMs of the pushing pass (second number of GFMD_B200_XCHG_SMS=pull,push)
+  int xchg_sms = 40;                          // SMs of the pulling pass (GFMD_B200_XCHG_SMS=pull,push).  Measured at 8 GPUs,
+                                              // 16384^2, solver step (profiles/r2_stage_times_8gpu_sm_split.txt): 24,24 -> 4.04 ms,
+                                              // 40,16 -> 3.88, 48,24 -> 3.69, 40,32 -> 3.69, 56,16 -> 3.74, 64,16 -> 3.78, 24,40 -> 3.91
   double *d_phi = nullptr, *d_linf = nullptr, *d_epart = nullptr, *d_fsum_part = nullptr;
   int fsum_part_cap = 0;
   StepResults *d_res = nullptr, *h_res = nullptr;

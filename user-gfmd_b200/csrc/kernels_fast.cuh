@@ -783,6 +783,20 @@ inline int fast_plan(const GridDesc &g, int &fast_rows, int &fast_cols, int &col
 }
 
 // variants whose kernels have a fused atom I/O form (AtomIO, kernels_rows_r16.cuh)
+// L2 prefetch distance (in CTAs) of the radix-16 row kernels: a CTA prefetches the input tile of the
+// CTA `pf` blocks later, behind its own loads, so that tile's loads hit L2.  Measured (one B200,
+// profiles/r2_rows_prefetch_ab.txt; distance 148 = one wave of SMs): 4096 x 4096 rows_fwd 0.193 ->
+// 0.182 ms, rows_inv 0.219 -> 0.201 ms (296: the same, 592: worse); 2048 x 16384 rows_fwd 0.721 ->
+// 0.692, rows_inv 0.716 -> 0.736 (worse: off).  GFMD_B200_ROWS_PREFETCH=<n> overrides (0 = off).
+inline int fast_rows_prefetch(int variant, int dir)
+{
+  static const int env = getenv("GFMD_B200_ROWS_PREFETCH") ? atoi(getenv("GFMD_B200_ROWS_PREFETCH")) : -1;
+  if (env >= 0) return env;
+  if (variant == 4104) return 148;
+  if (variant == 16392) return dir < 0 ? 148 : 0;
+  return 0;
+}
+
 inline bool fast_rows_has_atomio(int variant) { return variant == 4104 || variant == 8200 || variant == 16392; }
 
 // io != nullptr: gather fused into the transform (u is not read)
@@ -810,9 +824,9 @@ inline int fast_rows_fwd(int variant, const double *u, double2 *stage, const Gri
   case ID: k_rows_fwd_p2<NR, RB, T, FF ? MB : 0, W, FF><<<grid, T, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
-    case 4104: k_rows_fwd_r16<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 4104: k_rows_fwd_r16<2048, 2, 256><<<grid, 256, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0, AtomIO(), fast_rows_prefetch(4104, -1)); break;
     case 8200: k_rows_fwd_r16h<4096, 2, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
-    case 16392: k_rows_fwd_r16w<8192, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
+    case 16392: k_rows_fwd_r16w<8192, 512><<<grid, 512, smem, s>>>(u, stage, g, fd.core.tw, tw_ny, dof0, AtomIO(), fast_rows_prefetch(16392, -1)); break;
 #ifndef GFMD_CUDA_EMU
     case 16393: k_rows_fwd_r16c<8192, 512><<<grid, 512, fast_rows_smem_cluster(rc), s>>>(u, stage, g, fd.core.tw, tw_ny, dof0); break;
 #endif
@@ -848,9 +862,9 @@ inline int fast_rows_inv(int variant, const double2 *stage, double *f, const Gri
   case ID: k_rows_inv_p2<NR, RB, T, FI ? MB : 0, W, FI><<<grid, T, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
     ROWS_VARIANTS(ROWS_LAUNCH)
 #undef ROWS_LAUNCH
-    case 4104: k_rows_inv_r16<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 4104: k_rows_inv_r16<2048, 2, 256><<<grid, 256, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0, AtomIO(), fast_rows_prefetch(4104, +1)); break;
     case 8200: k_rows_inv_r16h<4096, 2, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
-    case 16392: k_rows_inv_r16w<8192, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
+    case 16392: k_rows_inv_r16w<8192, 512><<<grid, 512, smem, s>>>(stage, f, g, fd.core.tw, tw_ny, dof0, AtomIO(), fast_rows_prefetch(16392, +1)); break;
 #ifndef GFMD_CUDA_EMU
     case 16393: k_rows_inv_r16c<8192, 512><<<grid, 512, fast_rows_smem_cluster(rc), s>>>(stage, f, g, fd.core.tw, tw_ny, dof0); break;
 #endif

@@ -173,7 +173,7 @@ __device__ __forceinline__ int r16_slot(int klow, int t1, int r)
 template <int NR, int RB, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 2)
 k_rows_fwd_r16(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
-               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
+               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO(), int pf = 0)
 {
   static_assert(NR == 2048 && RB * (NR / 16) == T, "k_rows_fwd_r16: NR = 16 * 16 * 8, one pass-1 item per thread");
   constexpr int M1 = NR / 16;                 // 128: pass-1 threads per row = length of a pass-2 block
@@ -195,6 +195,12 @@ k_rows_fwd_r16(const double *__restrict__ u, double2 *__restrict__ stage, GridDe
       const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix0 + r) * (2 * NR));
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = src[m + M1 * j];
+      // L2 prefetch of the tile of the CTA that runs `pf` blocks later (behind this tile's own loads)
+      if (pf > 0 && blockIdx.x + pf < gridDim.x) {
+        const int b = blockIdx.x + pf, nt = g.nx_loc / RB;
+        const char *pb = reinterpret_cast<const char *>(u + ((size_t) (dof0 + b / nt) * g.nx_loc + (b % nt) * RB) * (2 * NR));
+        for (int i = threadIdx.x; i < RB * 2 * NR * 8 / 128; i += T) prefetch_l2(pb + (size_t) i * 128);
+      }
     }
     dft16<-1>(v);
     r16_twiddle<-1, true>(v, __ldg(tw + m));
@@ -256,7 +262,7 @@ k_rows_fwd_r16(const double *__restrict__ u, double2 *__restrict__ stage, GridDe
 template <int NR, int RB, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 2)
 k_rows_inv_r16(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
-               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
+               const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO(), int pf = 0)
 {
   static_assert(NR == 2048 && RB * (NR / 16) == T, "k_rows_inv_r16: NR = 16 * 16 * 8, one pass-1 item per thread");
   constexpr int M1 = NR / 16;
@@ -277,6 +283,15 @@ k_rows_inv_r16(const double2 *__restrict__ stage, double *__restrict__ f, GridDe
     for (int q = 0; q < 8; ++q) {
       y1[q] = stage[stage_index(g, klow + q * S, dof, ix0 + rr)];
       y2[q] = stage[stage_index(g, klow2 + q * S, dof, ix0 + rr)];
+    }
+    if (!MAPPED && pf > 0 && blockIdx.x + pf < gridDim.x && rr == 0) {      // one lane per 32-byte sector
+      const int b = blockIdx.x + pf, nt = g.nx_loc / RB;
+      const int pdof = dof0 + b / nt, pix = (b % nt) * RB;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        prefetch_l2(stage + stage_index(g, klow + q * S, pdof, pix));
+        prefetch_l2(stage + stage_index(g, klow2 + q * S, pdof, pix));
+      }
     }
     const RowsFuseTw<NR, 2> w(tw_ny, klow, klow2, p == 0);
     if (p == 0) {
@@ -594,7 +609,7 @@ __device__ __forceinline__ int r16w_klow(int p)
 template <int NR, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 1)
 k_rows_fwd_r16w(const double *__restrict__ u, double2 *__restrict__ stage, GridDesc g,
-                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO(), int pf = 0)
 {
   static_assert(NR == 8192 && NR / 16 == T, "k_rows_fwd_r16w: NR = 16 * 8 * 8 * 8, one row per CTA");
   constexpr int S = NR / 8;                   // 1024: frequency stride of the last pass
@@ -611,6 +626,11 @@ k_rows_fwd_r16w(const double *__restrict__ u, double2 *__restrict__ stage, GridD
       const double2 *src = reinterpret_cast<const double2 *>(u + ((size_t) dof * g.nx_loc + ix) * (2 * NR));
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = src[t + T * j];
+      if (pf > 0 && blockIdx.x + pf < gridDim.x) {
+        const int b = blockIdx.x + pf;
+        const char *pb = reinterpret_cast<const char *>(u + ((size_t) (dof0 + b / g.nx_loc) * g.nx_loc + b % g.nx_loc) * (2 * NR));
+        for (int i = t; i < 2 * NR * 8 / 128; i += T) prefetch_l2(pb + (size_t) i * 128);
+      }
     }
     dft16<-1>(v);
     r16_twiddle<-1, true>(v, __ldg(tw + t));
@@ -683,7 +703,7 @@ k_rows_fwd_r16w(const double *__restrict__ u, double2 *__restrict__ stage, GridD
 template <int NR, int T, bool MAPPED = false>
 __global__ void __launch_bounds__(T, 1)
 k_rows_inv_r16w(const double2 *__restrict__ stage, double *__restrict__ f, GridDesc g,
-                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO())
+                const double2 *__restrict__ tw, const double2 *__restrict__ tw_ny, int dof0, AtomIO io = AtomIO(), int pf = 0)
 {
   static_assert(NR == 8192 && NR / 16 == T, "k_rows_inv_r16w: NR = 16 * 8 * 8 * 8, one row per CTA");
   constexpr int S = NR / 8;
@@ -700,6 +720,15 @@ k_rows_inv_r16w(const double2 *__restrict__ stage, double *__restrict__ f, GridD
     for (int q = 0; q < 8; ++q) {
       y1[q] = stage[stage_index(g, klow + q * S, dof, ix)];
       y2[q] = stage[stage_index(g, klow2 + q * S, dof, ix)];
+    }
+    if (!MAPPED && pf > 0 && blockIdx.x + pf < gridDim.x) {
+      const int b = blockIdx.x + pf;
+      const int pdof = dof0 + b / g.nx_loc, pix = b % g.nx_loc;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        prefetch_l2(stage + stage_index(g, klow + q * S, pdof, pix));
+        prefetch_l2(stage + stage_index(g, klow2 + q * S, pdof, pix));
+      }
     }
     const RowsFuseTw<NR, 2> w(tw_ny, klow, klow2, p == 0);
     if (p == 0) {
