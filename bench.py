@@ -216,6 +216,32 @@ def main_reference(args):
 
 # -------------------------------------------------------------------- b200 ---
 
+def ncu_traffic(stage, nx, ny, d, world, kernels):
+    """DRAM bytes per launch of a stage's kernel from the committed ncu --set full capture of the SAME kernel on
+    the SAME grid (profiles/r2_ncu_full_summary.json, refreshed by tools/ncu_refresh.sh + tools/ncu_summary.py);
+    None when there is no such capture -- never a number for another kernel or grid."""
+    prefix = {"rows_fwd": "k_rows_fwd_r16<", "rows_inv": "k_rows_inv_r16<", "cols_fused": "k_cols_fused_p2_lr<"}.get(stage)
+    if prefix is None or world != 1:
+        return None, None
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_full_summary.json")))
+    except Exception:
+        return None, None
+    mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for name, m in summ.items():
+        if name.startswith(prefix) and m.get("grid") == "%dx%d ndof %d" % (nx, ny, d):
+            if stage.startswith("rows") and "variant 4104" not in kernels:
+                continue
+            if stage == "cols_fused" and "k_cols_fused_p2_lr" not in kernels:
+                continue
+            def gb(x):
+                v, unit = x.split()[:2]
+                return float(v) * mult[unit]
+            return gb(m["dram__bytes_read.sum"]) + gb(m["dram__bytes_write.sum"]), \
+                "ncu --set full capture of %s on this grid, profiles/r2_ncu_full_summary.json (not re-measured in this run)" % name
+    return None, None
+
+
 def stage_bytes_per_cell(d, fused_gather=False, fused_scatter=False):
     """Algorithmic bytes per cell of every stage; long columns (nx > 4096) add the
     top-digit pass of the column transform, one more read + write of the half spectrum each way.
@@ -391,7 +417,7 @@ def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clock
     rs = roof_stages[dom]
     roofline = {"kernel": rs["kernel"], "stage": dom, "bound": "hbm", "achieved": rs["achieved"],
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": rs["frac"],
-                "traffic": None,    # ncu dram bytes per launch live in profiles/ (r2_ncu_*.csv); not re-measured here
+                "traffic": None, "traffic_source": None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rs["alg_bytes_per_cell"] * cells_loc, "kernel_ms": rs["ms"],
                 "share_of_step": rs["ms"] / ms_per_step,
@@ -400,6 +426,7 @@ def run_config(c, nx, ny, d, legacy_inputs, steps, warmup, e2e_steps, want_clock
                 "solver_bytes_per_step": (80 * d + 4 * d * d) * cells_loc,
                 "solver_frac": ((80 * d + 4 * d * d) * cells_loc / (ms_solver * 1e-3) / 1e9) / peaks["hbm_gbs"]}
 
+    roofline["traffic"], roofline["traffic_source"] = ncu_traffic(dom, nx, ny, d, world, s.describe())
     # size-independent property on the timed workload (linf = 0): E = -1/2 sum_r f.u  
     fu = float((f_one * (dx - dxeq)).sum().item())
     esum = res["epot"]
