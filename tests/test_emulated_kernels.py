@@ -116,6 +116,7 @@ def test_device_table_builder(B):
     ("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height 7", 2048, 2),     # specialised table layout
     ("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height -1", 6, 5),      # iterate to convergence
     ("ft fcc111 1 1.0 pair-potential 1 1.0 height -1", 4, 3),
+    ("ft fcc111 1 1.0 pair-potential 1 1.0 height 5", 4096, 2),       # position-ordered table (k_cols_fft_p2)
 ])
 def test_device_built_table_equals_plugin_table(B, kernel, nx, ny, oracle_libs):
     O = oracle_libs
@@ -374,6 +375,43 @@ def test_split_column_stage(B, nx, ny, d, force, oracle_libs, monkeypatch):
     f2 = np.full_like(uu, np.nan)
     assert s.post_force(uu, f2) == e and np.array_equal(f, f2)
     s.close()
+
+
+@pytest.mark.parametrize("nx,ny,d", [(4096, 3, 6), (4096, 2, 12), (4096, 4096, 6)][:2])
+def test_split_column_stage_on_power_of_two_passes(B, nx, ny, d, oracle_libs, monkeypatch):
+    """nx = 4096 with more than one atom per cell: the transform phases of the three-phase column stage run on
+    the specialised power-of-two passes (k_cols_fft_p2), the spectrum stays in position order and the table is
+    stored likewise (phi_slot mode 2) -- through set_kernel (full table), set_kernel_columns and the device
+    table builder.  Against the oracle, and against the same stage on the run-time engine (GFMD_B200_NO_FAST)."""
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    res = []
+    for how in ("full", "columns", "nofast"):
+        if how == "nofast":
+            monkeypatch.setenv("GFMD_B200_NO_FAST", "1")
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        assert ("k_cols_fft_p2" in s.describe()) == (how != "nofast"), s.describe()
+        if how == "columns":
+            p4 = phi.reshape(nx, ny, d, d)
+            for k0 in range(s.nky):
+                s.set_kernel_columns(np.ascontiguousarray(p4[:, k0:k0 + 1]), k0, normalized=True)
+            s.set_linf(linf)
+        else:
+            s.set_kernel(phi, linf)
+        f = np.full_like(uu, np.nan)
+        e = s.post_force(uu, f)
+        assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL
+        assert abs(e - e_ref) <= TOL * abs(e_ref)
+        assert np.abs(s.get_u0() - u0_ref).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+        f2 = np.full_like(uu, np.nan)
+        assert s.post_force(uu, f2) == e and np.array_equal(f, f2)
+        res.append(f)
+        s.close()
+    assert rel_err(res[0], res[1]) < 1e-13         # set_kernel symmetrises the table, set_kernel_columns does not
+    assert rel_err(res[0], res[2]) < 1e-13
 
 
 def test_split_column_stage_equals_fused_bitwise_in_forces(B, monkeypatch):

@@ -36,6 +36,7 @@ def test_sc100_table_built_on_device_reproduces_golden_forces():
     ("ft fcc100 1.0 2 pair-potential 2 1.0 -0.1 height 10", 10, 10),
     ("sc100 height 0", 16, 12),
     ("ft sc100 1 1.0 pair-potential 2 1.0 1.0 height 7", 2048, 8),     # specialised column layout
+    ("ft fcc111 1 1.0 pair-potential 1 1.0 height 5", 4096, 4),        # position-ordered table (k_cols_fft_p2)
 ])
 def test_device_built_table_equals_plugin_table(kernel, nx, ny, oracle_libs):
     O = oracle_libs

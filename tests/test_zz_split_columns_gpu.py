@@ -43,7 +43,7 @@ def step(B, nx, ny, d, phi, linf, u, expect):
     e = s.post_force(uu, f)
     u0 = s.get_u0().copy()
     # split: rows, fft, contract, fft, finalize, rows; fused: rows, cols_fused, finalize, rows
-    assert s.launch_count() >= (6 if expect == "k_cols_split_fft" else 4)
+    assert s.launch_count() >= (4 if expect == "k_cols_fused" else 6)
     s.close()
     return f.reshape(d, nx, ny), e, u0
 
@@ -84,3 +84,19 @@ def test_two_atoms_per_cell_4096_energy_identity_and_linearity(B):
     """Full-size property test on 4096 x 2048, ndof 6 (specialised rows + split columns): with
     linf = 0, E = -1/2 sum f.u (SURVEY 8a restatement) and f is linear in u."""
     split_checks.energy_identity_and_linearity(B, 4096, 2048, 6, expect=("k_cols_split_fft", "[fast"))
+
+
+@pytest.mark.parametrize("nx,ny,d", [(4096, 24, 6), (4096, 8, 12)])
+def test_split_column_stage_on_power_of_two_passes(B, nx, ny, d, oracle_libs, monkeypatch):
+    """nx = 4096 with more than one atom per cell: the transform phases run on the specialised power-of-two
+    passes (k_cols_fft_p2), spectrum and table in position order.  Against the oracle and against the same stage
+    on the run-time engine (GFMD_B200_NO_FAST=1)."""
+    O = oracle_libs
+    phi, linf, u = random_case(nx, ny, d)
+    f_ref, e_ref, u0_ref = O.post_force(u, phi, linf)
+    f1, e1, u01 = step(B, nx, ny, d, phi, linf, u, "k_cols_fft_p2")
+    assert rel_err(f1, f_ref) < TOL and abs(e1 - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(u01 - u0_ref).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+    monkeypatch.setenv("GFMD_B200_NO_FAST", "1")
+    f2, e2, _ = step(B, nx, ny, d, phi, linf, u, "k_cols_split_fft len")
+    assert rel_err(f1, f2) < 1e-13 and abs(e1 - e2) <= 1e-13 * abs(e1)

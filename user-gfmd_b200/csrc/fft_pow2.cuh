@@ -93,10 +93,19 @@ __host__ __device__ inline int p2_pos_to_freq(int log, int pos)
 // the spectrum is digit-reversed (pos) and the planes are interleaved item by item,
 // [pos / 64][(pos & 7) / 2][c][(pos >> 3) & 7][pos & 1], so that the 9 x 16-byte loads of
 // one contraction round of 8 neighbouring threads form one contiguous 1152-byte chunk.
-__host__ __device__ inline void phi_slot(bool fast, int top, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
+// mode 0: generic kernels, plane-major [c][kx].  mode 1: specialised fused column kernels (below).
+// mode 2: plane-major in POSITION order [c][pos(kx)] -- the three-phase column stage on the
+// power-of-two passes (k_cols_fft_p2, kernel_cols_split.cuh) leaves the spectrum digit-reversed in HBM,
+// and the contraction kernel then reads table and spectrum with the same (coalesced) index.
+__host__ __device__ inline void phi_slot(int mode, int top, int lognx, int nx, size_t dsq, int kx, size_t &off, size_t &cstride)
 {
-  if (!fast) {
+  if (mode == 0) {
     off = (size_t) kx;
+    cstride = (size_t) nx;
+    return;
+  }
+  if (mode == 2) {
+    off = (size_t) p2_freq_to_pos(lognx, kx);
     cstride = (size_t) nx;
     return;
   }

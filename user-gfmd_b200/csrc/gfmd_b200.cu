@@ -357,6 +357,9 @@ struct gfmd_b200 {
   int cols_ld = 0, cols_T = 64;
   size_t cols_smem = 0;
   int fast_rows = 0, fast_cols = 0;   // specialised kernels selected
+  bool cols_split_fast = false;       // three-phase column stage on the power-of-two passes (k_cols_fft_p2; nx = 4096,
+                                      // single rank): the spectrum stays in position order, Phi is stored likewise
+  int phi_mode() const { return fast_cols ? 1 : (cols_split_fast ? 2 : 0); }      // layout of d_phi, see phi_slot
   int cols_split_db = 0;              // > 0: column set too large for one CTA, three-phase column stage
                                       // with this many dofs per CTA (kernel_cols_split.cuh)
   int cols_top = 0;                   // log2(nx / 4096): top-digit pass of long columns
@@ -546,6 +549,13 @@ int plan(gfmd_b200 *h)
       h->cols_split_db = db;
       h->cols_smem = (size_t) db * one;
       cols_nb = db;
+      // the transform phases on the specialised power-of-two passes where they exist
+      if (g.nx == 4096 && g.P == 1 && force_db == 0 && !getenv("GFMD_B200_NO_FAST")) {
+        h->cols_split_fast = true;
+        h->cols_split_db = 3;
+        h->cols_smem = fast_cols_smem(3, 4096);
+        cols_nb = 3;
+      }
     }
   }
   if (h->fast_cols) h->cols_smem = fast_cols_smem(3, h->fast_cols);
@@ -563,7 +573,10 @@ int plan(gfmd_b200 *h)
     SET_SMEM(k_rows_fwd<false>, h->rows_smem);
     SET_SMEM(k_rows_inv<false>, h->rows_smem);
   }
-  if (h->cols_split_db) {
+  if (h->cols_split_fast) {
+    SET_SMEM((k_cols_fft_p2<4096, 512, -1>), h->cols_smem);
+    SET_SMEM((k_cols_fft_p2<4096, 512, +1>), h->cols_smem);
+  } else if (h->cols_split_db) {
     SET_SMEM(k_cols_split_fft<-1>, h->cols_smem);
     SET_SMEM(k_cols_split_fft<+1>, h->cols_smem);
   } else if (!h->fast_cols) switch (g.d) {
@@ -679,6 +692,9 @@ int create_common(gfmd_b200_t **out, int nx, int ny, int ndof, int device, int r
   else if (h->fast_cols)
     snprintf(cols, sizeof(cols), "k_cols_fused_p2 len %d, 256 threads, smem %zu [fast]", h->fast_cols,
              h->cols_smem);
+  else if (h->cols_split_fast)
+    snprintf(cols, sizeof(cols), "k_cols_split_fft -> k_cols_fft_p2 len %d (3 dofs/CTA, 512 threads, smem %zu, spectrum in "
+             "position order) + k_cols_contract [fast]", h->g.nx, h->cols_smem);
   else if (h->cols_split_db)
     snprintf(cols, sizeof(cols), "k_cols_split_fft len %d%s (%d dofs/CTA, %d threads, smem %zu) + k_cols_contract",
              h->fft_cols.desc.n, h->fft_cols.desc.bluestein ? " (bluestein)" : "", h->cols_split_db, h->cols_T,
@@ -827,6 +843,10 @@ int launch_generic_cols(gfmd_b200 *h, double2 *in, double2 *out, int *nepart)
     const int db = h->cols_split_db;
     const int ngrp = (g.d + db - 1) / db;
     const int ntile = (g.nx + kContractTile - 1) / kContractTile;
+    const int fgrid = g.nky_loc * ngrp < h->num_sms ? g.nky_loc * ngrp : h->num_sms;
+    if (h->cols_split_fast)
+      k_cols_fft_p2<4096, 512, -1><<<fgrid, 512, h->cols_smem, h->stream>>>(in, in, g, h->fft_cols.desc.core.tw);
+    else
     k_cols_split_fft<-1><<<g.nky_loc * ngrp, h->cols_T, h->cols_smem, h->stream>>>(in, in, g, h->fft_cols.desc,
                                                                                   h->cols_ld, db);
 #define LAUNCH_CONTRACT(DT)                                                                   \
@@ -840,6 +860,9 @@ int launch_generic_cols(gfmd_b200 *h, double2 *in, double2 *out, int *nepart)
       default: LAUNCH_CONTRACT(0); break;
     }
 #undef LAUNCH_CONTRACT
+    if (h->cols_split_fast)
+      k_cols_fft_p2<4096, 512, +1><<<fgrid, 512, h->cols_smem, h->stream>>>(in, out, g, h->fft_cols.desc.core.tw);
+    else
     k_cols_split_fft<+1><<<g.nky_loc * ngrp, h->cols_T, h->cols_smem, h->stream>>>(in, out, g, h->fft_cols.desc,
                                                                                   h->cols_ld, db);
     h->launches += 3;
@@ -1311,7 +1334,7 @@ int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool 
   const int lognx = ilog2_rt(g.nx);
 #define LAUNCH_AUX(DT, MODE)                                                                      \
   k_cols_aux<DT, MODE><<<g.nky_loc, h->cols_T, h->aux_cols_smem, h->stream>>>(                     \
-      A, want_f ? h->d_spec : nullptr, g, h->fft_cols.desc, h->d_phi, h->d_cavg, h->fast_cols != 0, lognx, h->cols_ld, \
+      A, want_f ? h->d_spec : nullptr, g, h->fft_cols.desc, h->d_phi, h->d_cavg, h->phi_mode(), lognx, h->cols_ld, \
       ncopy)
   if (mode == AUX_SPECTRUM) {
     switch (g.d) {
@@ -1819,7 +1842,7 @@ int gfmd_b200_set_phi(gfmd_b200_t *h, const double *phi, int already_normalised,
         const double *M = phi + 2 * dsq * ((size_t) kx * ny + ky);
         const double *Mn = phi + 2 * dsq * ((size_t) kxn * ny + kyn);
         size_t off, cstride;
-        phi_slot(h->fast_cols != 0, h->cols_top, lognx, nx, dsq, kx, off, cstride);
+        phi_slot(h->phi_mode(), h->cols_top, lognx, nx, dsq, kx, off, cstride);
         pack_hermitian(M, Mn, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     }
@@ -1859,7 +1882,7 @@ int gfmd_b200_set_phi_columns(gfmd_b200_t *h, const double *phi, int ky_first, i
       for (int kx = 0; kx < nx; ++kx) {
         const double *M = phi + 2 * dsq * ((size_t) kx * nky + k0 + kl);
         size_t off, cstride;
-        phi_slot(h->fast_cols != 0, h->cols_top, lognx, nx, dsq, kx, off, cstride);
+        phi_slot(h->phi_mode(), h->cols_top, lognx, nx, dsq, kx, off, cstride);
         pack_hermitian(M, nullptr, d, s, buf.data() + (size_t) kl * dsq * nx + off, cstride, amax, hdev, cdev);
       }
     CU(h, h2d_blocking(h->d_phi + (size_t) (ky_first - g.ky0 + k0) * dsq * nx, buf.data(),
@@ -1911,10 +1934,10 @@ static int build_phi_columns_impl(gfmd_b200_t *h, const double *uuv, int ky_firs
     const int grid = (int) ((nq + 63) / 64);
     const int lognx = ilog2_rt(nx);
     switch (d) {
-      case 3: k_build_phi<3><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
-      case 6: k_build_phi<6><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
-      case 9: k_build_phi<9><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
-      default: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->fast_cols != 0, h->cols_top, lognx, dst, d_flag); break;
+      case 3: k_build_phi<3><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->phi_mode(), h->cols_top, lognx, dst, d_flag); break;
+      case 6: k_build_phi<6><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->phi_mode(), h->cols_top, lognx, dst, d_flag); break;
+      case 9: k_build_phi<9><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->phi_mode(), h->cols_top, lognx, dst, d_flag); break;
+      default: k_build_phi<12><<<grid, 64, 0, h->stream>>>(d_uuv, nx, nky, height, scale, h->phi_mode(), h->cols_top, lognx, dst, d_flag); break;
     }
     h->launches++;
     e = cudaStreamSynchronize(h->stream);

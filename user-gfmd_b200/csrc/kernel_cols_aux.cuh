@@ -90,7 +90,7 @@ k_cols_aux(double2 *__restrict__ stage, double2 *__restrict__ stage_f, GridDesc 
   const double *ph = phi + (size_t) kl * dsq * nx;
   for (int kx = threadIdx.x; kx < nx; kx += blockDim.x) {
     size_t off, cs;
-    phi_slot(fast_phi != 0, 0, lognx, nx, dsq, kx, off, cs);
+    phi_slot(fast_phi, 0, lognx, nx, dsq, kx, off, cs);
     if (MODE == AUX_SPECTRUM) {
       if (!stage_f) continue;
       if (DT > 0) {

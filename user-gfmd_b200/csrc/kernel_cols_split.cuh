@@ -15,9 +15,81 @@
 // Layouts as in kernels_generic.cuh: stage [P][d][kyb][nx_loc], phi plane-major [kl][c][kx].
 #pragma once
 
+#include "fft_pow2.cuh"
 #include "kernels_generic.cuh"
 
 namespace gfmd {
+
+// The transform phases on the specialised power-of-two passes (nx = N = 4096, single rank, ndof a multiple
+// of 3): one CTA transforms the three dofs of one sublattice of one ky column, the passes of
+// k_cols_fused_p2_lr (kernel_cols_lr.cuh) without the contraction in between.  Forward leaves the spectrum
+// in HBM in POSITION order (digit-reversed, fft_pow2.cuh) -- nothing is un-permuted: the stiffness table
+// is stored in the same order (phi_slot mode 2) and k_cols_contract reads both with one index.  Round 2:
+// replaces the run-time mixed-radix engine for two atoms per cell on 4096-wide surfaces (4.68 ms per column
+// stage at 4096 x 4096 on the generic engine, profiles/r2_stage_times_call1.txt).
+// grid = min(nky_loc * ngrp, #SMs), persistent over (column, sublattice) pairs.
+template <int N, int T, int DIR>
+__global__ void __launch_bounds__(T, 1)
+k_cols_fft_p2(const double2 *__restrict__ sin, double2 *__restrict__ sout, GridDesc g, const double2 *__restrict__ tw)
+{
+  constexpr int D = 3;
+  constexpr int NW = T / 32;
+  extern __shared__ double2 sm[];
+  double2 *tws = sm + D * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ngrp = g.d / 3;
+  p2_fill_tws<N>(tws, tw);
+  __syncthreads();
+  for (int vc = blockIdx.x; vc < g.nky_loc * ngrp; vc += gridDim.x) {
+    const int kl = vc / ngrp, grp = vc - kl * ngrp;
+    // single rank: dof a of column kl starts at ((3 grp + a) * kyb + kl) * nx
+    const size_t col0 = ((size_t) (3 * grp) * g.kyb + kl) * N, dstride = (size_t) g.kyb * N;
+    if (DIR < 0) {
+      p2_pass0_fwd_blk<N, T, D, 0>(sm, tw, tws, [&](int a, int base, int off) { return sin[col0 + a * dstride + base + off]; });
+      __syncthreads();
+      p2_groupA_rest_seq<N, NW, -1, D, 0>(sm, tw, tws, lane, warp);
+      __syncthreads();
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first_seq<N, -1, D, 0>(sm, tws, idx);
+      __syncwarp();
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < N / 8; idx += T) {
+        const int pos = p2_last_base(idx);
+        const int key = swz_key(pos);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          double2 t[8];
+          p2_last_fwd_load(sm + a * N, pos, key, t);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) sout[col0 + a * dstride + pos + r] = t[r];      // 8 positions = one 128-byte line
+        }
+      }
+      __syncthreads();            // the next column's pass 0 overwrites what other threads may still read
+    } else {
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < N / 8; idx += T) {
+        const int pos = p2_last_base(idx);
+        const int key = swz_key(pos);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          double2 t[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) t[r] = sin[col0 + a * dstride + pos + r];
+          p2_last_inv_store(sm + a * N, pos, key, t);
+        }
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < N / 8; idx += T) p2_groupB_first_seq<N, +1, D, 0>(sm, tws, idx);
+      __syncthreads();
+      p2_groupA_rest_seq<N, NW, +1, D, 0>(sm, tw, tws, lane, warp);
+      __syncthreads();
+      p2_pass0_inv_blk<N, T, D, 0>(sm, tw, tws,
+                                   [&](int a, int base, int off, double2 v) { sout[col0 + a * dstride + base + off] = v; });
+      __syncthreads();
+    }
+  }
+}
 
 constexpr int kContractThreads = 256;
 constexpr int kContractTile = 1024;   // q per CTA of k_cols_contract (4 per thread)

@@ -111,7 +111,7 @@ k_build_phi(const double2 *__restrict__ uuv, int nx, int nky, int height, double
   }
   // Phi = U0 (+ VT), Hermitian part, scaled, packed
   size_t off, cstride;
-  phi_slot(fast != 0, top, lognx, nx, (size_t) D * D, kx, off, cstride);
+  phi_slot(fast, top, lognx, nx, (size_t) D * D, kx, off, cstride);
   double *dst = phi_cols + (size_t) kyl * D * D * nx + off;
   auto P = [&](int i, int j) {
     double2 a = src[i * D + j];
