@@ -184,7 +184,8 @@ int gfmd_b200_post_force_device(gfmd_b200_t *h, const double *d_u, double *d_f);
  * the HOST field u [ndof][nx*ny], and fq = Phi(q).u~(q) with the (normalised) table of this
  * handle, no sign flip.  Both come back in the reference's q_buffer layout,
  * [nx*ny][ndof] complex128 interleaved, idq = ix*ny + iy, full spectrum.  fq may be NULL.
- * Limited to grids whose column set fits one CTA (nx * ndof * 16 B <= 227 KB). */
+ * Column sets that fit one CTA (nx * ndof * 16 B <= 227 KB) take one fused kernel, larger ones the
+ * three-phase column stage (transform, per-q kernel, transform); one column must fit: nx <= 8192. */
 int gfmd_b200_spectrum_host(gfmd_b200_t *h, const double *u, double *uq_ri, double *fq_ri);
 
 /* GFMDSolverStatic::prec_gradient (gfmd_solver_static.cpp:253-271) with

@@ -73,3 +73,35 @@ def check_prec_gradient(B, O, name):
     else:
         assert rel_err(gP2.reshape(d, nx, ny), a["gP"]) > 1e-3       # the quirk is not a no-op
     s.close()
+
+
+def check_large_column_sets(B, O, nx, ny, d):
+    """Column sets beyond one CTA's shared memory (e.g. the 4096-wide bench surface): the services run
+    through the three-phase column stage -- transform phase, per-q kernel on the spectrum in HBM,
+    transform phase -- whatever table layout the per-step kernels of the handle use."""
+    rng = np.random.default_rng(nx + ny + d)
+    Dr = rng.standard_normal((nx, ny, d, d)) * np.exp(-3 * rng.random((nx, ny, 1, 1)))
+    Dm = Dr[(-np.arange(nx)) % nx][:, (-np.arange(ny)) % ny]
+    Dr = 0.5 * (Dr + np.swapaxes(Dm, 2, 3))
+    phi = np.fft.fft2(Dr, axes=(0, 1)).reshape(nx * ny, d, d) / (nx * ny)
+    phi += np.eye(d)[None] * (2.0 / (nx * ny))               # well conditioned for the preconditioner
+    u = rng.uniform(-0.1, 0.1, size=(d, nx, ny))
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    s.set_kernel(phi, np.zeros(d // 3))
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    uq, fq = s.spectrum(uu)
+    uq_ref, fq_ref = O.spectrum(u, phi)
+    assert rel_err(uq, uq_ref) < TOL and rel_err(fq, fq_ref) < TOL
+    if d in (3, 6, 9, 12):
+        cavg = 0.01 * rng.standard_normal((d, d)) / (nx * ny)
+        gP = np.full_like(uu, np.nan)
+        s.prec_gradient(cavg, uu, gP, reference_quirk=False)
+        gP_ref = O.prec_gradient(u, phi, cavg, reference_quirk=False)
+        assert rel_err(gP.reshape(d, nx, ny), gP_ref) < 1e-9
+    # the per-step path is unaffected
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    f_ref, e_ref, _ = O.post_force(u, phi, np.zeros(d // 3))
+    assert rel_err(f.reshape(d, nx, ny), f_ref) < TOL and abs(e - e_ref) <= TOL * abs(e_ref)
+    s.close()

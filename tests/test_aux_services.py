@@ -51,12 +51,33 @@ def test_spectrum_on_other_layouts(B, nx, ny, d, oracle_libs):
     s.close()
 
 
+@pytest.mark.parametrize("nx,ny,d", [(4096, 8, 6), (8192, 4, 3), (4096, 4096, 3), (6000, 6, 6)])
+def test_services_on_column_sets_beyond_one_cta(B, nx, ny, d, oracle_libs):
+    """Round 2: no 227 KB limit any more -- e.g. a `dumpq_every` step on the 4096 x 4096 bench surface."""
+    if nx * ny > 1 << 22:
+        # full surface: spectrum only against numpy's FFT of a smooth field (the oracle's table route needs 2.4 GB)
+        from gfmd_b200 import synthetic
+        s = B.GFMDSolverB200()
+        s.set_grid_size(nx, ny, d)
+        for k0 in range(0, s.nky, 256):
+            nk = min(256, s.nky - k0)
+            s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+        s.set_linf(np.zeros(1))
+        u = synthetic.displacement_field(nx, ny, seed=3, nwaves=4)
+        uq, _ = s.spectrum(np.ascontiguousarray(u.reshape(d, nx * ny)), with_force=False)
+        ref = np.moveaxis(np.fft.fft2(u, axes=(1, 2)).reshape(d, nx * ny), 0, 1)
+        assert rel_err(uq, ref) < aux_checks.TOL
+        s.close()
+        return
+    aux_checks.check_large_column_sets(B, oracle_libs, nx, ny, d)
+
+
 def test_unsupported_sizes_fail_loudly(B):
     s = B.GFMDSolverB200()
-    s.set_grid_size(8192, 4, 3)        # long columns: no single-CTA column set
+    s.set_grid_size(16384, 4, 3)       # one column (256 KB) exceeds a CTA's shared memory
     from gfmd_b200 import synthetic
-    s.set_kernel_columns(synthetic.phi_columns(8192, 4, 0, s.nky), 0, normalized=False)
-    u = np.zeros((3, 8192 * 4))
+    s.set_kernel_columns(synthetic.phi_columns(16384, 4, 0, s.nky), 0, normalized=False)
+    u = np.zeros((3, 16384 * 4))
     with pytest.raises(B.GFMDError) as ei:
         s.spectrum(u)
     assert ei.value.code == 4

@@ -304,6 +304,16 @@ def test_prec_gradient(B, name, oracle_libs):
     aux_checks.check_prec_gradient(B, oracle_libs, name)
 
 
+@pytest.mark.parametrize("nx,ny,d", [(4096, 2, 6), (8192, 2, 3), (4096, 2, 3), (2500, 2, 6)])
+def test_aux_services_on_column_sets_beyond_one_cta(B, nx, ny, d, oracle_libs):
+    """Spectrum and preconditioner through the three-phase column stage (k_cols_split_fft + k_aux_perq) for
+    column sets larger than one CTA's shared memory, in every table layout (interleaved incl. long columns,
+    position order, plane-major)."""
+    if (nx, d) == (4096, 3):
+        pytest.skip("3 x 4096 x 16 B fits one CTA: covered by the fused auxiliary kernel")
+    aux_checks.check_large_column_sets(B, oracle_libs, nx, ny, d)
+
+
 @pytest.mark.parametrize("nx,ny,d", [(2048, 2, 3), (4096, 2, 3), (11, 13, 15)])
 def test_aux_services_read_the_specialised_table_layout(B, nx, ny, d, oracle_libs):
     """The off-path column kernel reads Phi in the digit-reversed, interleaved layout of the

@@ -367,6 +367,8 @@ struct gfmd_b200 {
   int num_sms = 148;
   // auxiliary (off-path) column kernel: q-space dumps and the preconditioner
   size_t aux_cols_smem = 0;           // 0: a column set does not fit one CTA
+  int aux_split_db = 0, aux_split_T = 0;   // then: the services run through the three-phase column stage (nx <= 8192)
+  size_t aux_split_smem = 0;
   bool aux_attr_set = false;
   double2 *d_spec = nullptr;          // Phi.u~ of the last spectrum request
   double *d_cavg = nullptr;
@@ -533,6 +535,18 @@ int plan(gfmd_b200 *h)
   if (tmin > 512 && !h->fast_cols)
     return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d: column transform too long for one CTA", g.nx);
   h->aux_cols_smem = (h->cols_smem <= kMaxSmem && tmin <= 512 && g.P == 1) ? h->cols_smem : 0;
+  if (!h->aux_cols_smem && g.P == 1 && tmin <= 512 && (size_t) cld * sizeof(double2) <= kMaxSmem) {
+    const size_t one = (size_t) cld * sizeof(double2);
+    int db = (int) (kMaxSmem / one);
+    if (db > g.d) db = g.d;
+    h->aux_split_db = db;
+    h->aux_split_smem = (size_t) db * one;
+    int ta = round_up_pow2(db * h->fft_cols.desc.core.len / 8);
+    if (ta < tmin) ta = round_up_pow2(tmin);
+    if (ta < 64) ta = 64;
+    if (ta > 512) ta = 512;
+    h->aux_split_T = ta;
+  }
   int cols_nb = g.d;                     // transforms a column CTA holds
   if (!h->fast_cols) {
     // GFMD_B200_COLS_SPLIT=<n> forces the three-phase column stage with at most n dofs per CTA
@@ -1303,11 +1317,17 @@ int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool 
   if (g.P != 1)
     return fail(h, GFMD_B200_EUNSUPPORTED, "q-space dumps and prec_gradient run on a single rank only (the "
                 "reference's dumps do too, gfmd_solver_fft.cpp:211-212)");
-  if (!h->aux_cols_smem)
-    return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d with ndof = %d: a column set does not fit one CTA; q-space "
-                "dumps and prec_gradient are limited to nx * ndof * 16 B <= %zu B", g.nx, g.d, kMaxSmem);
+  if (!h->aux_cols_smem && !h->aux_split_db)
+    return fail(h, GFMD_B200_EUNSUPPORTED, "nx = %d: one column (%zu B) does not fit one CTA's shared memory (%zu B); "
+                "q-space dumps and prec_gradient are limited to nx <= 8192", g.nx, (size_t) h->cols_ld * sizeof(double2),
+                kMaxSmem);
   if (mode == AUX_PREC && !(g.d == 3 || g.d == 6 || g.d == 9 || g.d == 12))
     return fail(h, GFMD_B200_EUNSUPPORTED, "prec_gradient: ndof %d (3, 6, 9, 12 supported)", g.d);
+  if (!h->aux_attr_set && !h->aux_cols_smem) {
+    CU(h, grow_dyn_smem((const void *) k_cols_split_fft<-1>, h->aux_split_smem));
+    CU(h, grow_dyn_smem((const void *) k_cols_split_fft<+1>, h->aux_split_smem));
+    h->aux_attr_set = true;
+  }
   if (!h->aux_attr_set) {
 #define SET_AUX(DT, MODE) CU(h, grow_dyn_smem((const void *) k_cols_aux<DT, MODE>, h->aux_cols_smem))
     switch (g.d) {
@@ -1332,6 +1352,38 @@ int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool 
                                                                            h->rows_RB, h->rows_ld);
   h->launches++;
   const int lognx = ilog2_rt(g.nx);
+  if (!h->aux_cols_smem) {
+    // column set larger than one CTA: transform phase, per-q kernel on the spectrum in HBM, transform phase
+    const int db = h->aux_split_db, ngrp = (g.d + db - 1) / db;
+    k_cols_split_fft<-1><<<g.nky_loc * ngrp, h->aux_split_T, h->aux_split_smem, h->stream>>>(A, A, g, h->fft_cols.desc,
+                                                                                           h->cols_ld, db);
+    const long long nq = (long long) g.nky_loc * g.nx;
+    const int pgrid = (int) ((nq + 255) / 256 < (long long) h->num_sms * 8 ? (nq + 255) / 256 : (long long) h->num_sms * 8);
+#define LAUNCH_PERQ(DT, MODE)                                                                                          \
+  k_aux_perq<DT, MODE><<<pgrid, 256, 0, h->stream>>>(A, want_f ? h->d_spec : nullptr, g, h->d_phi, h->d_cavg,         \
+                                                     h->phi_mode(), h->cols_top, lognx, ncopy)
+    if (mode == AUX_SPECTRUM) {
+      switch (g.d) {
+        case 3: LAUNCH_PERQ(3, AUX_SPECTRUM); break;
+        case 6: LAUNCH_PERQ(6, AUX_SPECTRUM); break;
+        case 9: LAUNCH_PERQ(9, AUX_SPECTRUM); break;
+        case 12: LAUNCH_PERQ(12, AUX_SPECTRUM); break;
+        default: LAUNCH_PERQ(0, AUX_SPECTRUM); break;
+      }
+    } else {
+      switch (g.d) {
+        case 3: LAUNCH_PERQ(3, AUX_PREC); break;
+        case 6: LAUNCH_PERQ(6, AUX_PREC); break;
+        case 9: LAUNCH_PERQ(9, AUX_PREC); break;
+        default: LAUNCH_PERQ(12, AUX_PREC); break;
+      }
+      k_cols_split_fft<+1><<<g.nky_loc * ngrp, h->aux_split_T, h->aux_split_smem, h->stream>>>(A, A, g, h->fft_cols.desc,
+                                                                                             h->cols_ld, db);
+      h->launches++;
+    }
+#undef LAUNCH_PERQ
+    h->launches += 2;
+  } else {
 #define LAUNCH_AUX(DT, MODE)                                                                      \
   k_cols_aux<DT, MODE><<<g.nky_loc, h->cols_T, h->aux_cols_smem, h->stream>>>(                     \
       A, want_f ? h->d_spec : nullptr, g, h->fft_cols.desc, h->d_phi, h->d_cavg, h->phi_mode(), lognx, h->cols_ld, \
@@ -1354,6 +1406,7 @@ int enqueue_aux(gfmd_b200 *h, int mode, const double *d_in, double *d_out, bool 
   }
 #undef LAUNCH_AUX
   h->launches++;
+  }
   if (mode == AUX_PREC) {
     if (h->even)
       k_rows_inv<true><<<nrow_blocks, h->rows_T, h->rows_smem, h->stream>>>(A, d_out, g, h->fft_rows.desc,

@@ -148,4 +148,70 @@ k_cols_aux(double2 *__restrict__ stage, double2 *__restrict__ stage_f, GridDesc 
   }
 }
 
+// The per-q operation of k_cols_aux on a spectrum that lives in HBM (natural kx order, single rank):
+// for column sets that do not fit one CTA, between the transform phases of the three-phase column stage
+// (k_cols_split_fft, kernel_cols_split.cuh).  One thread per (kl, kx).
+template <int DT, int MODE>
+__global__ void __launch_bounds__(256)
+k_aux_perq(double2 *__restrict__ stage, double2 *__restrict__ stage_f, GridDesc g, const double *__restrict__ phi,
+           const double *__restrict__ cavg, int phi_mode, int top, int lognx, int ncopy)
+{
+  const int d = DT > 0 ? DT : g.d;
+  const int nx = g.nx;
+  const size_t dsq = (size_t) d * d;
+  const long long total = (long long) g.nky_loc * nx;
+  for (long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x) {
+    const int kl = (int) (idx / nx), kx = (int) (idx - (long long) kl * nx);
+    const double *ph = phi + (size_t) kl * dsq * nx;
+    size_t off, cs;
+    phi_slot(phi_mode, top, lognx, nx, dsq, kx, off, cs);
+    auto at = [&](int i) -> size_t { return ((size_t) i * g.kyb + kl) * nx + kx; };
+    if (MODE == AUX_SPECTRUM) {
+      if (!stage_f) continue;
+      if (DT > 0) {
+        double2 uv[DT > 0 ? DT : 1], F[DT > 0 ? DT : 1];
+#pragma unroll
+        for (int i = 0; i < DT; ++i) uv[i] = stage[at(i)];
+        phi_matvec<DT>(uv, F, [&](int c) { return __ldg(ph + off + (size_t) c * cs); });
+#pragma unroll
+        for (int i = 0; i < DT; ++i) stage_f[at(i)] = F[i];
+      } else {
+        double2 uv[24], F[24];
+        for (int i = 0; i < d; ++i) uv[i] = stage[at(i)];
+        for (int i = 0; i < d; ++i) {
+          const double a = __ldg(ph + off + (size_t) i * cs);
+          F[i] = make_double2(a * uv[i].x, a * uv[i].y);
+        }
+        int c = d;
+        for (int i = 0; i < d; ++i)
+          for (int j = i + 1; j < d; ++j) {
+            const double2 p = make_double2(__ldg(ph + off + (size_t) c * cs), __ldg(ph + off + (size_t) (c + 1) * cs));
+            c += 2;
+            F[i].x = fma(p.x, uv[j].x, fma(-p.y, uv[j].y, F[i].x));
+            F[i].y = fma(p.x, uv[j].y, fma(p.y, uv[j].x, F[i].y));
+            F[j].x = fma(p.x, uv[i].x, fma(p.y, uv[i].y, F[j].x));
+            F[j].y = fma(p.x, uv[i].y, fma(-p.y, uv[i].x, F[j].y));
+          }
+        for (int i = 0; i < d; ++i) stage_f[at(i)] = F[i];
+      }
+    } else if (DT > 0) {
+      double2 M[DT > 0 ? DT * DT : 1], b[DT > 0 ? DT : 1];
+      int c = DT;
+      for (int i = 0; i < DT; ++i) {
+        M[i * DT + i] = make_double2(__ldg(ph + off + (size_t) i * cs) + __ldg(cavg + i * DT + i), 0.0);
+        for (int j = i + 1; j < DT; ++j) {
+          const double re = __ldg(ph + off + (size_t) c * cs), im = __ldg(ph + off + (size_t) (c + 1) * cs);
+          c += 2;
+          M[i * DT + j] = make_double2(re + __ldg(cavg + i * DT + j), im);
+          M[j * DT + i] = make_double2(re + __ldg(cavg + j * DT + i), -im);
+        }
+      }
+      for (int i = 0; i < DT; ++i) b[i] = stage[at(i)];
+      csolve_vec<DT>(M, b);
+      for (int i = 0; i < DT; ++i)
+        if (i < ncopy) stage[at(i)] = b[i];
+    }
+  }
+}
+
 }  // namespace gfmd
