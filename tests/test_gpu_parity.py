@@ -420,3 +420,37 @@ def test_fused_atom_io_equals_separate_gather_scatter(B, nx, ny, nu):
     s.synchronize()                       # the step runs on the handle's own stream
     assert torch.equal(df, fa)
     s.close()
+
+
+def test_bench_surface_against_reference_solver(B, oracle_libs):
+    """4096 x 4096, ndof 3 -- the surface the north-star quotes the single-GPU target on -- DIRECTLY against the
+    reference's own GFMDSolverStatic::post_force (oracle/_ref: its solver sources compiled unchanged,
+    src/solvers/gfmd_solver_static.cpp:145-249): forces, energy and u0 to 1e-11.  About 40 s of host time."""
+    import torch
+    from gfmd_b200 import synthetic
+    O = oracle_libs
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libgfmd_ref.so not built")
+    nx = ny = 4096
+    d = 3
+    O.set_fft_threads(len(__import__("os").sched_getaffinity(0)))
+    u = synthetic.displacement_field(nx, ny, seed=2, nwaves=4)
+    linf = np.array([0.125])
+    ref = O.RefSolver(nx, ny, d, fft_backend=1)
+    ref.set_phi(synthetic.phi_full(nx, ny), linf)
+    f_ref, e_ref, u0_ref = ref.post_force(u)
+    del ref
+    s = B.GFMDSolverB200()
+    s.set_grid_size(nx, ny, d)
+    assert "k_cols_fused_p2_lr" in s.describe() and "k_rows_*_r16" in s.describe(), s.describe()
+    for k0 in range(0, s.nky, 256):
+        nk = min(256, s.nky - k0)
+        s.set_kernel_columns(synthetic.phi_columns(nx, ny, k0, nk), k0, normalized=False)
+    s.set_linf(linf)
+    uu = np.ascontiguousarray(u.reshape(d, nx * ny))
+    f = np.full_like(uu, np.nan)
+    e = s.post_force(uu, f)
+    assert rel_err(f.reshape(d, nx, ny), np.asarray(f_ref).reshape(d, nx, ny)) < TOL
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    assert np.abs(s.get_u0() - np.asarray(u0_ref)).max() <= TOL * max(1.0, np.abs(u0_ref).max())
+    s.close()

@@ -502,6 +502,15 @@ int plan(gfmd_b200 *h)
   if (RB < 1) RB = 1;
   if (RB > 32) RB = 32;
   if (RB > g.nx_loc) RB = g.nx_loc;
+  // small grids (BASELINE configs C1-C3): a step is latency-bound, and 32 rows per CTA leave a 128 x 128 or
+  // 64 x 37 surface on a dozen SMs.  Fewer rows per CTA until the row kernels fill the GPU (round 2:
+  // config.latency of the bench line).
+  {
+    const long long total_rows = (long long) g.d * g.nx_loc;
+    long long fill = (total_rows + h->num_sms - 1) / h->num_sms;
+    if (fill < 1) fill = 1;
+    if ((long long) RB > fill) RB = (int) fill;
+  }
   while (RB > 1 && (size_t) RB * ld * sizeof(double2) > 200 * 1024) --RB;
   h->rows_RB = RB;
   h->rows_smem = (size_t) RB * ld * sizeof(double2);
