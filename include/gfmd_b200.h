@@ -30,11 +30,17 @@
  *   GFMD_B200_ROWS_VARIANT=<id>  a specific row-kernel variant (csrc/kernels_fast.cuh)
  *   GFMD_B200_COLS_SPLIT=<n>     three-phase column stage with at most n dofs per CTA even where a
  *                                column set fits one CTA (csrc/kernel_cols_split.cuh; for tests)
- *   GFMD_B200_CHUNKS=<n>         column chunks of the multi-GPU pipeline (default 4)
+ *   GFMD_B200_CHUNKS=<n>         column chunks of the multi-GPU pipelines (default 4; 8 without transposes)
  *   GFMD_B200_PEER_STORE=1       read by gfmd_b200_ipc_import: the column stage stores its results
- *                                straight into the peers' return buffers (experimental)
- *   GFMD_B200_PEER_DIRECT=1      likewise; with gfmd_b200_ipc_import_stage: no transposes at all, the
- *                                column stage also loads its input from the peers (experimental)
+ *                                straight into the peers' return buffers (opt-in)
+ *   GFMD_B200_PEER_DIRECT=0/1    with gfmd_b200_ipc_import_stage: no transposes at all, the column stage loads
+ *                                its input from the peers and stores its results into them, overlapped chunk by
+ *                                chunk (default for >= 4 ranks with nx >= 8192; 0 = copy-engine pushes)
+ *   GFMD_B200_XCHG_SMS=<a>[,<b>] SMs of the pulling / pushing top-digit passes of that mode (default 40,32)
+ *   GFMD_B200_SYNC=nccl          one-element NCCL all-reduces as cross-rank barriers instead of flag words
+ *   GFMD_B200_TIMELINE=1         with profiling on: one per-chunk timeline of that mode on stderr
+ *   GFMD_B200_COLS_PIPE=0        the plain instead of the software-pipelined fused column kernel
+ *   GFMD_B200_ROWS_PREFETCH=<n>  L2 prefetch distance (CTAs) of the radix-16 row kernels (0 = off)
  *   GFMD_B200_HOST_PIPE=0        no per-dof upload / download pipeline on the host path
  *   GFMD_B200_NCCL_LIB=<path>    the NCCL build to dlopen before libnccl.so.2
  */
@@ -92,7 +98,7 @@ int gfmd_b200_ipc_import(gfmd_b200_t *h, const char *all_handles /* [nranks][2][
  * kernels write (one handle), gathered and imported the same way.  With it and
  * GFMD_B200_PEER_DIRECT=1 the transposes disappear altogether: after a barrier the column stage
  * loads its pieces straight from the ranks that produced them and stores its results straight
- * into their return buffers, NVLink traffic issued by the kernels themselves (experimental;
+ * into their return buffers, NVLink traffic issued by the kernels themselves (
  * replaces, like the pushes, what MPI does inside the reference's FFT3d remap,
  * src/solvers/gfmd_solver_fft.cpp:72-80). */
 int gfmd_b200_ipc_export_stage(gfmd_b200_t *h, char *handle /* [64] */);

@@ -51,7 +51,6 @@ def build(force=False):
     with open(os.path.join(OUT, "src", "include", "gfmd_b200.h"), "w") as f:
         f.write(hdr)
     cmd = ["g++", "-std=c++17", "-O2", "-g", "-march=native", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-DGFMD_EXPERIMENTAL_COLS_PIPE",          # experimental code paths are emulated too
            "-I", os.path.join(HERE, "include"), "-o", LIB,
            os.path.join(src, "gfmd_b200.cpp"), os.path.join(HERE, "emu_runtime.cpp"), "-ldl"]
     subprocess.check_call(cmd)

@@ -1,5 +1,5 @@
 """Size-independent checks of the three-phase column stage, shared by the GPU test
-(tests/test_zz_split_columns_gpu.py, full size) and the emulated one (small, forced split)."""
+(tests/test_split_columns_gpu.py, full size) and the emulated one (small, forced split)."""
 import numpy as np
 
 

@@ -1,8 +1,7 @@
 """More of the reference's compound acceptance tests on the CUDA path, through the helpers of
 tests/test_compound.py, with the stiffness tables taken from the reference plugin at test time
-(oracle/_ref).  Written after the round's GPU budget was spent: all three pass on the emulation
-build (tests/test_emulated_kernels.py, GFMD_EMU_LONG=1); first GPU run is the driver's, and the
-file name sorts last so that a surprise here hides nothing else."""
+(oracle/_ref).  All three pass on the emulation build too (tests/test_emulated_kernels.py, GFMD_EMU_LONG=1)
+and on the GPU (round 2)."""
 import pytest
 
 from test_compound import plugin_table, run_energy_conservation, run_hertz_cubic

@@ -447,7 +447,7 @@ def test_split_column_stage_equals_fused_bitwise_in_forces(B, monkeypatch):
 
 
 def test_split_column_stage_energy_identity_and_linearity(B, monkeypatch):
-    """Small version of the full-size GPU property test (tests/test_zz_split_columns_gpu.py)."""
+    """Small version of the full-size GPU property test (tests/test_split_columns_gpu.py)."""
     monkeypatch.setenv("GFMD_B200_COLS_SPLIT", "4")
     split_checks.energy_identity_and_linearity(B, 96, 40, 6, expect=("k_cols_split_fft",))
 

@@ -80,7 +80,7 @@ def test_slab_parity(nranks):
 
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_slab_parity_in_kernel_peer_stores(nranks):
-    """GFMD_B200_PEER_STORE=1 (opt-in, emulator-verified, not yet run on GPUs): the column stage
+    """GFMD_B200_PEER_STORE=1 (opt-in): the column stage
     stores its result pieces straight into the peers' return buffers over NVLink."""
     import torch
     if torch.cuda.device_count() < nranks:
@@ -94,7 +94,7 @@ def test_slab_parity_in_kernel_peer_stores(nranks):
 
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_slab_parity_no_transposes(nranks):
-    """GFMD_B200_PEER_DIRECT=1 (opt-in, emulator-verified, not yet run on GPUs): the column stage loads
+    """GFMD_B200_PEER_DIRECT=1 (the default for >= 4 ranks with long columns): the column stage loads
     and stores its pieces in the peers' memory itself; no transposes."""
     import torch
     if torch.cuda.device_count() < nranks:

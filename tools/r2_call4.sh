@@ -3,7 +3,7 @@
 set -x
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 600 python -m pytest tests/test_zzz_rows_r16_gpu.py -m gpu -q > $OUT/r2_c4_r16_tests.txt 2>&1
+timeout 600 python -m pytest tests/test_rows_r16_gpu.py -m gpu -q > $OUT/r2_c4_r16_tests.txt 2>&1
 AB_ROUNDS=2 timeout 300 python tools/rows_variants_ab.py 2048 16384 > $OUT/r2_c4_rows_variants_16384.txt 2>&1
 GFMD_B200_ROWS_VARIANT=16393 timeout 600 python tools/stage_times.py 16384 16384 3 > $OUT/r2_c4_stage_16384_r16c.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_(gather|rows|cols|scatter|finalize|sum)" -c 60 --csv \

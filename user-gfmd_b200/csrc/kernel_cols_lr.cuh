@@ -53,7 +53,7 @@ struct PeerOut {
 // backward pass of column c is fused with
 // pass 0 of column c + gridDim.x (p2_pass0_inv_fwd_blk): the loads of the next column are in
 // flight while the finished column is transformed and stored, instead of after it.
-// PEER (experimental, slab mode with peer mappings, ltop == 0).  1 (GFMD_B200_PEER_STORE=1): the
+// PEER (slab mode with peer mappings, ltop == 0; opt-in).  1 (GFMD_B200_PEER_STORE=1): the
 // last backward pass stores each piece straight into its owner's return buffer (`outp`) -- full
 // 128-byte lines over NVLink -- instead of the local staging buffer.  2 (GFMD_B200_PEER_DIRECT=1):
 // pass 0 also LOADS each piece straight from the row-kernel output of the rank that produced it

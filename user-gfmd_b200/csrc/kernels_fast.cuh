@@ -614,14 +614,14 @@ namespace gfmd {
 
 struct FastRowsCfg { int nr, rb, t; };
 
-// variant id = ny + k: k = 0 the default; experimental variants, selected with the environment
-// variable GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
+// variant id = ny + k (k = 8, the radix-16 kernels, is the default where it exists: fast_rows_default);
+// the others are selected with GFMD_B200_ROWS_VARIANT=<id> at handle creation (see ROWS_VARIANTS below):
 //   ny = 4096: +1 four rows per CTA, +3 256-bit transposed accesses;  ny = 8192: +3 likewise;
 //   every ny: +5 last pass fused with the real/complex (un)mixing (FUSE, see above) in both
 //   directions;  ny = 4096, 8192: +6 fused backward, unfused forward (the default at 4096),
-//   +7 fused both ways with closed-form twiddles (one table load per unit; unmeasured);
+//   +7 fused both ways with closed-form twiddles (one table load per unit);
 //   ny = 4096, 8192, 16384: +8 radix-16 passes, four / five / six shared-memory sweeps
-//   (kernels_rows_r16.cuh; unmeasured).
+//   (kernels_rows_r16.cuh);  ny = 16384: +9 the same as two-CTA clusters (kernels_rows_cluster.cuh).
 // Measured on a B200 at 4096 x 4096 (tools/rows_variants_ab.py, profiles/r1_rows_variants.txt):
 // rows_fwd / rows_inv 0.273 / 0.308 ms default, 0.266 / 0.339 (+1), 0.268 / 0.304 (+3); forcing
 // three CTAs per SM with __launch_bounds__(256, 3) (85 registers, spills) was 25 % slower and
