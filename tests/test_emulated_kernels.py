@@ -631,7 +631,8 @@ def test_results_do_not_depend_on_thread_order(order):
     env = dict(os.environ, GFMD_EMU_SCHED=order)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
                         "-k", "random_tables or (row_kernel_variants and (4103 or 4104 or 8199 or 8200 or 16389 or 16392)) "
-                              "or split_column_stage or device_table_builder or prec_gradient"],
+                              "or split_column_stage or device_table_builder or prec_gradient or fused_atom_io "
+                              "or aux_services_on_column_sets"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
