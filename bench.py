@@ -697,6 +697,16 @@ def main_b200(args):
             out["parity_against"] = "size-independent identity E = -1/2 sum f.u on the timed surface (linf = 0)"
         if sub is not None:
             out["grid_4096"] = sub
+            try:    # the north-star's single-GPU roofline target is quoted on THIS surface: repeat its fractions up front
+                st = sub["roofline"]["stages"]
+                out["roofline"]["north_star_surface_4096x4096"] = {
+                    "frac_rows_fwd": st["rows_fwd"]["frac"], "frac_cols_fused": st["cols_fused"]["frac"],
+                    "frac_rows_inv": st["rows_inv"]["frac"], "peak": sub["roofline"]["peak"], "unit": "GB/s",
+                    "note": "FFT and fused Phi(q) stages of the 4096x4096 sc100 surface (grid_4096.roofline.stages); the "
+                            "top-level roofline object describes the dominant kernel of the 16384x16384 workload of "
+                            "`value`, whose rows (one 128 KB row per CTA) are the weakest stage"}
+            except Exception:
+                pass
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
