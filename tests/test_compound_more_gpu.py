@@ -42,3 +42,18 @@ def test_hertz_sc100_128x128_a0_1_3(oracle_libs):
     run_hertz_cubic(gfmd_b200, torch.device("cuda"),
                     plugin_table(oracle_libs, "ft sc100 1.3 1 pair-potential 2 1.0 1.0 height 128", 128, 128),
                     1.3, 8.0 / 3 / 1.3, dmax=0.1)
+
+
+def test_error_convergence_two_layers_lj():
+    """TEST_error_convergence_ft_two_layers_lj_cut restated (tests/errconv.py): a Lennard-Jones fcc(100) crystal on
+    a GFMD substrate (two GFMD layers, ndof 6, the reference plugin's `ft fcc100 ... pair-potential 2x ...` table
+    with the LJ force constants) against its all-atom twin (golden fixture, plain numpy): the force error on the
+    displaced probe atom must go like dstep^2 (exponent >= 1.9) and stay below 10 % at dstep = 0.01."""
+    import os
+    import numpy as np
+    import gfmd_b200
+    import errconv
+    from conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "errconv_fcc100_two_layers_lj.npz"))
+    goeslike, relerr = errconv.check(gfmd_b200, g)
+    print("force error goes like dstep^%.3f; relative errors %s" % (goeslike, relerr))

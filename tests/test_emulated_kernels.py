@@ -617,6 +617,19 @@ def test_random_call_sequences(B, oracle_libs):
         h["s"].close()
 
 
+def test_error_convergence_two_layers_lj(B):
+    """The reference's error-convergence criterion (tests/TEST_error_convergence_ft_two_layers_lj_cut, eval.py:
+    207-226) on the emulated CUDA path: GFMD substrate under a Lennard-Jones crystal against the all-atom twin
+    (golden fixture); the force error on the probe atom must shrink like the square of its displacement.
+    See tests/errconv.py."""
+    import errconv
+    from conftest import GOLDEN_DIR
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, "errconv_fcc100_two_layers_lj.npz"))
+    goeslike, relerr = errconv.check(B, g)
+    print("force error goes like dstep^%.3f; relative errors %s" % (goeslike, relerr))
+
+
 @pytest.mark.parametrize("order", ["reverse", "random:7"])
 def test_results_do_not_depend_on_thread_order(order):
     """CUDA promises no execution order between barriers.  The emulation runs the threads of a
