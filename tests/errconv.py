@@ -14,7 +14,7 @@ harmonic expansion of the twin: the difference must shrink like dstep^2 (criteri
 between a small and a large step, and < 10 % relative error at the large one).
 
 The twin needs no stiffness kernel and no FFT: its force changes are a golden fixture
-(tests/golden/errconv_fcc100_two_layers_lj.npz, made by tests/golden/make_golden_errconv.py from this file's
+(tests/golden/compound/errconv_fcc100_two_layers_lj.npz, made by tests/golden/make_golden_errconv.py from this file's
 plain-numpy Lennard-Jones code), together with the kernel's table from the reference plugin.
 """
 import numpy as np

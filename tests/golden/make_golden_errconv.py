@@ -1,4 +1,4 @@
-"""Makes tests/golden/errconv_fcc100_two_layers_lj.npz (about ten minutes; needs oracle/_ref, i.e. /root/reference):
+"""Makes tests/golden/compound/errconv_fcc100_two_layers_lj.npz (about ten minutes; needs oracle/_ref, i.e. /root/reference):
 the stiffness table of the reference plugin for the Lennard-Jones fcc(100) substrate of tests/errconv.py, its
 linear forces, and the force changes on the probe atom of the ALL-ATOM twin (plain numpy, no GFMD)."""
 import os
@@ -18,6 +18,6 @@ k = O.RefKernel(errconv.kernel_string())
 phi = k.phi(errconv.NX, errconv.NY)
 k.close()
 dF_full = errconv.full_atom_twin(list(dsteps))
-np.savez_compressed(os.path.join(HERE, "errconv_fcc100_two_layers_lj.npz"), dsteps=dsteps, phi=phi,
+np.savez_compressed(os.path.join(HERE, "compound", "errconv_fcc100_two_layers_lj.npz"), dsteps=dsteps, phi=phi,
                     linf=errconv.linear_forces(), dF_full=dF_full, kernel=errconv.kernel_string(), a=errconv.A_NN)
 print(dF_full)

@@ -54,6 +54,6 @@ def test_error_convergence_two_layers_lj():
     import gfmd_b200
     import errconv
     from conftest import GOLDEN_DIR
-    g = np.load(os.path.join(GOLDEN_DIR, "errconv_fcc100_two_layers_lj.npz"))
+    g = np.load(os.path.join(GOLDEN_DIR, "compound", "errconv_fcc100_two_layers_lj.npz"))
     goeslike, relerr = errconv.check(gfmd_b200, g)
     print("force error goes like dstep^%.3f; relative errors %s" % (goeslike, relerr))

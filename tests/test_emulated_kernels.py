@@ -625,7 +625,7 @@ def test_error_convergence_two_layers_lj(B):
     import errconv
     from conftest import GOLDEN_DIR
     import os
-    g = np.load(os.path.join(GOLDEN_DIR, "errconv_fcc100_two_layers_lj.npz"))
+    g = np.load(os.path.join(GOLDEN_DIR, "compound", "errconv_fcc100_two_layers_lj.npz"))
     goeslike, relerr = errconv.check(B, g)
     print("force error goes like dstep^%.3f; relative errors %s" % (goeslike, relerr))
 
